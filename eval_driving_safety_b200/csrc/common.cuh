@@ -1,0 +1,44 @@
+// Shared helpers for libb2attack.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/b2attack.h"
+
+namespace b2 {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+void set_error(const char* fmt, ...);
+
+inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+#define B2_REQUIRE(cond, ...)                \
+    do {                                     \
+        if (!(cond)) {                       \
+            b2::set_error(__VA_ARGS__);      \
+            return B2_ERR_BAD_ARG;           \
+        }                                    \
+    } while (0)
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// Grid for a grid-stride streaming kernel: whole waves of the 148 SMs.
+inline int stream_grid(int64_t work_items, int per_block, int max_waves_blocks = kNumSMs * 16) {
+    int64_t need = (work_items + per_block - 1) / per_block;
+    if (need < 1) need = 1;
+    if (need > max_waves_blocks) need = max_waves_blocks;
+    return (int)need;
+}
+
+__device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldcs(p); }
+__device__ __forceinline__ void stg_stream(float4* p, float4 v) { __stcs(p, v); }
+
+}  // namespace b2

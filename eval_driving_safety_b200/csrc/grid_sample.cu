@@ -1,0 +1,290 @@
+// Subsystem (2): frustum -> voxel lifting by bilinear / trilinear grid sampling,
+// forward and DETERMINISTIC backward.  Replaces ATen grid_sampler_{2d,3d} and
+// their atomicAdd backward, reached through F.grid_sample inside
+// StereoNet.forward (attack/DSGN/pgd_attack.py:308, 336).
+//
+// Semantics = F.grid_sample(mode='bilinear', padding_mode='zeros'), both
+// align_corners conventions (ATen grid_sampler_unnormalize formulas).
+//
+// Layout: channels-last.  A sub-warp of C/4 lanes owns one output voxel, every
+// lane a float4 of channels, so each corner read and the output write are one
+// contiguous C*4-byte segment (256 B for the 64-channel PSV feature).
+//
+// Backward: the sampling grid is a fixed function of the calibration, so a CSR
+// plan "input cell -> sorted list of (output voxel, weight)" is built once and
+// reused by every PGD iteration; the backward is then a pure gather with a fixed
+// summation order -> bitwise reproducible, no atomics on floats.
+#include "common.cuh"
+
+namespace b2 {
+
+__device__ __forceinline__ float unnorm(float g, int size, int align) {
+    return align ? ((g + 1.f) / 2.f) * (float)(size - 1) : ((g + 1.f) * (float)size - 1.f) / 2.f;
+}
+
+struct Corners3 {
+    int x0, y0, z0;
+    float wx1, wy1, wz1;  // weight of the +1 corner along each axis
+};
+
+__device__ __forceinline__ Corners3 corners3(const float* g, int D, int H, int W, int align) {
+    float ix = unnorm(g[0], W, align), iy = unnorm(g[1], H, align), iz = unnorm(g[2], D, align);
+    float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+    Corners3 c;
+    // clamp far-out coordinates before the int cast (NaN/inf/huge -> all corners OOB)
+    fx = fminf(fmaxf(fx, -2.f), (float)W + 1.f); if (!(ix == ix)) fx = -2.f;
+    fy = fminf(fmaxf(fy, -2.f), (float)H + 1.f); if (!(iy == iy)) fy = -2.f;
+    fz = fminf(fmaxf(fz, -2.f), (float)D + 1.f); if (!(iz == iz)) fz = -2.f;
+    c.x0 = (int)fx; c.y0 = (int)fy; c.z0 = (int)fz;
+    c.wx1 = ix - floorf(ix); c.wy1 = iy - floorf(iy); c.wz1 = iz - floorf(iz);
+    return c;
+}
+
+__device__ __forceinline__ void fma4(float4& a, float w, float4 v) {
+    a.x += w * v.x; a.y += w * v.y; a.z += w * v.z; a.w += w * v.w;
+}
+
+// LPV = lanes per voxel (= C/4, power of two <= 32).
+template <int LPV>
+__global__ void __launch_bounds__(256)
+grid_sample3d_fwd_kernel(const float4* __restrict__ in, const float* __restrict__ grid,
+                         float* __restrict__ out, int N, int D, int H, int W, int64_t nvox_per_n,
+                         int out_cstride, int out_coff, int align) {
+    const int64_t nvox = (int64_t)N * nvox_per_n;
+    const int lane = threadIdx.x % LPV;
+    const int64_t vstride = (int64_t)gridDim.x * (blockDim.x / LPV);
+    for (int64_t v = (int64_t)blockIdx.x * (blockDim.x / LPV) + threadIdx.x / LPV; v < nvox; v += vstride) {
+        int n = (int)(v / nvox_per_n);
+        const float* g = grid + v * 3;
+        float gg[3] = {__ldg(g), __ldg(g + 1), __ldg(g + 2)};
+        Corners3 c = corners3(gg, D, H, W, align);
+        const float4* base = in + (int64_t)n * D * H * W * LPV + lane;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            int dz = k >> 2, dy = (k >> 1) & 1, dx = k & 1;
+            int z = c.z0 + dz, y = c.y0 + dy, x = c.x0 + dx;
+            float w = (dx ? c.wx1 : 1.f - c.wx1) * (dy ? c.wy1 : 1.f - c.wy1) * (dz ? c.wz1 : 1.f - c.wz1);
+            if (z >= 0 && z < D && y >= 0 && y < H && x >= 0 && x < W)
+                fma4(acc, w, __ldg(base + (((int64_t)z * H + y) * W + x) * LPV));
+        }
+        *reinterpret_cast<float4*>(out + v * out_cstride + out_coff + lane * 4) = acc;
+    }
+}
+
+template <int LPV>
+__global__ void __launch_bounds__(256)
+grid_sample2d_fwd_kernel(const float4* __restrict__ in, const float* __restrict__ grid,
+                         float* __restrict__ out, int N, int H, int W, int64_t nvox_per_n,
+                         int out_cstride, int out_coff, int align) {
+    const int64_t nvox = (int64_t)N * nvox_per_n;
+    const int lane = threadIdx.x % LPV;
+    const int64_t vstride = (int64_t)gridDim.x * (blockDim.x / LPV);
+    for (int64_t v = (int64_t)blockIdx.x * (blockDim.x / LPV) + threadIdx.x / LPV; v < nvox; v += vstride) {
+        int n = (int)(v / nvox_per_n);
+        const float* g = grid + v * 2;
+        float gg[3] = {__ldg(g), __ldg(g + 1), -1.f};
+        Corners3 c = corners3(gg, 1, H, W, align);
+        const float4* base = in + (int64_t)n * H * W * LPV + lane;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int dy = k >> 1, dx = k & 1;
+            int y = c.y0 + dy, x = c.x0 + dx;
+            float w = (dx ? c.wx1 : 1.f - c.wx1) * (dy ? c.wy1 : 1.f - c.wy1);
+            if (y >= 0 && y < H && x >= 0 && x < W)
+                fma4(acc, w, __ldg(base + ((int64_t)y * W + x) * LPV));
+        }
+        *reinterpret_cast<float4*>(out + v * out_cstride + out_coff + lane * 4) = acc;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// CSR plan.  FILL == 0: count entries per input cell; FILL == 1: write them.
+// One thread per output voxel.  Integer atomics only (counts are exact; the
+// slot order inside a row is fixed afterwards by plan_sort).
+// ---------------------------------------------------------------------------
+template <int FILL>
+__global__ void __launch_bounds__(256)
+grid_plan_kernel(const float* __restrict__ grid, int32_t* __restrict__ counts_or_cursor,
+                 const int32_t* __restrict__ row_ptr, int2* __restrict__ entries, int ndim, int N,
+                 int D, int H, int W, int64_t nvox_per_n, int align) {
+    const int64_t nvox = (int64_t)N * nvox_per_n;
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox;
+         v += (int64_t)gridDim.x * blockDim.x) {
+        int n = (int)(v / nvox_per_n);
+        const float* g = grid + v * ndim;
+        float gg[3] = {__ldg(g), __ldg(g + 1), ndim == 3 ? __ldg(g + 2) : -1.f};
+        Corners3 c = corners3(gg, D, H, W, align);
+        if (ndim == 2) { c.z0 = 0; c.wz1 = 0.f; }
+        const int nk = ndim == 3 ? 8 : 4;
+        for (int k = 0; k < nk; ++k) {
+            int dz = k >> 2, dy = (k >> 1) & 1, dx = k & 1;
+            int z = c.z0 + dz, y = c.y0 + dy, x = c.x0 + dx;
+            if (z < 0 || z >= D || y < 0 || y >= H || x < 0 || x >= W) continue;
+            float w = (dx ? c.wx1 : 1.f - c.wx1) * (dy ? c.wy1 : 1.f - c.wy1);
+            if (ndim == 3) w *= (dz ? c.wz1 : 1.f - c.wz1);
+            int64_t cell = (((int64_t)n * D + z) * H + y) * W + x;
+            if (FILL) {
+                int slot = atomicAdd(counts_or_cursor + cell, 1);
+                entries[(int64_t)row_ptr[cell] + slot] = make_int2((int)v, __float_as_int(w));
+            } else {
+                atomicAdd(counts_or_cursor + cell, 1);
+            }
+        }
+    }
+}
+
+// Sort each CSR row by (voxel id, then weight bits) -- insertion sort, rows are short.
+__global__ void __launch_bounds__(256)
+grid_plan_sort_kernel(const int32_t* __restrict__ row_ptr, int2* __restrict__ entries, int64_t ncell) {
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c < ncell;
+         c += (int64_t)gridDim.x * blockDim.x) {
+        int b = row_ptr[c], e = row_ptr[c + 1];
+        for (int i = b + 1; i < e; ++i) {
+            int2 key = entries[i];
+            int j = i - 1;
+            while (j >= b) {
+                int2 o = entries[j];
+                if (o.x < key.x || (o.x == key.x && o.y <= key.y)) break;
+                entries[j + 1] = o;
+                --j;
+            }
+            entries[j + 1] = key;
+        }
+    }
+}
+
+// Gather backward: a sub-warp of LPV lanes owns one input cell.
+template <int LPV>
+__global__ void __launch_bounds__(256)
+grid_sample_bwd_kernel(const float* __restrict__ gout, const int32_t* __restrict__ row_ptr,
+                       const int2* __restrict__ entries, float4* __restrict__ gin, int64_t ncell,
+                       int gout_cstride, int gout_coff) {
+    const int lane = threadIdx.x % LPV;
+    const int64_t cstride = (int64_t)gridDim.x * (blockDim.x / LPV);
+    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x / LPV) + threadIdx.x / LPV; c < ncell; c += cstride) {
+        int b = __ldg(row_ptr + c), e = __ldg(row_ptr + c + 1);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        int i = b;
+        for (; i + 1 < e; i += 2) {  // two independent loads in flight
+            int2 e0 = __ldg(entries + i), e1 = __ldg(entries + i + 1);
+            float4 g0 = __ldg(reinterpret_cast<const float4*>(gout + (int64_t)e0.x * gout_cstride + gout_coff) + lane);
+            float4 g1 = __ldg(reinterpret_cast<const float4*>(gout + (int64_t)e1.x * gout_cstride + gout_coff) + lane);
+            fma4(acc, __int_as_float(e0.y), g0);
+            fma4(acc, __int_as_float(e1.y), g1);
+        }
+        if (i < e) {
+            int2 e0 = __ldg(entries + i);
+            float4 g0 = __ldg(reinterpret_cast<const float4*>(gout + (int64_t)e0.x * gout_cstride + gout_coff) + lane);
+            fma4(acc, __int_as_float(e0.y), g0);
+        }
+        gin[c * LPV + lane] = acc;
+    }
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+#define B2_LPV_SWITCH(C, ...)                                                         \
+    switch ((C) / 4) {                                                                \
+        case 1: { constexpr int LPV = 1; __VA_ARGS__; } break;                               \
+        case 2: { constexpr int LPV = 2; __VA_ARGS__; } break;                               \
+        case 4: { constexpr int LPV = 4; __VA_ARGS__; } break;                               \
+        case 8: { constexpr int LPV = 8; __VA_ARGS__; } break;                               \
+        case 16: { constexpr int LPV = 16; __VA_ARGS__; } break;                             \
+        case 32: { constexpr int LPV = 32; __VA_ARGS__; } break;                             \
+        default:                                                                      \
+            b2::set_error("grid_sample: C must be 4,8,16,32,64 or 128 (got %d)", (C)); \
+            return B2_ERR_UNSUPPORTED;                                                \
+    }
+
+extern "C" int b2_grid_sample3d_fwd(const float* in, const float* grid, float* out, int N, int C,
+                                    int D, int H, int W, int64_t nvox_per_n, int out_cstride,
+                                    int out_coff, int align_corners, void* stream) {
+    B2_REQUIRE(in && grid && out, "grid_sample3d_fwd: null pointer");
+    B2_REQUIRE(C % 4 == 0 && out_cstride % 4 == 0 && out_coff % 4 == 0 && aligned16(in) && aligned16(out),
+               "grid_sample3d_fwd: channel counts/offsets must be multiples of 4 and pointers 16B aligned");
+    if ((int64_t)N * nvox_per_n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t nvox = (int64_t)N * nvox_per_n;
+    B2_LPV_SWITCH(C, {
+        int grid_x = stream_grid(nvox, 256 / LPV, kNumSMs * 16);
+        grid_sample3d_fwd_kernel<LPV><<<grid_x, 256, 0, st>>>((const float4*)in, grid, out, N, D, H, W,
+                                                             nvox_per_n, out_cstride, out_coff, align_corners);
+    });
+    return check_launch("grid_sample3d_fwd");
+}
+
+extern "C" int b2_grid_sample2d_fwd(const float* in, const float* grid, float* out, int N, int C,
+                                    int H, int W, int64_t nvox_per_n, int out_cstride, int out_coff,
+                                    int align_corners, void* stream) {
+    B2_REQUIRE(in && grid && out, "grid_sample2d_fwd: null pointer");
+    B2_REQUIRE(C % 4 == 0 && out_cstride % 4 == 0 && out_coff % 4 == 0 && aligned16(in) && aligned16(out),
+               "grid_sample2d_fwd: channel counts/offsets must be multiples of 4 and pointers 16B aligned");
+    if ((int64_t)N * nvox_per_n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t nvox = (int64_t)N * nvox_per_n;
+    B2_LPV_SWITCH(C, {
+        int grid_x = stream_grid(nvox, 256 / LPV, kNumSMs * 16);
+        grid_sample2d_fwd_kernel<LPV><<<grid_x, 256, 0, st>>>((const float4*)in, grid, out, N, H, W,
+                                                             nvox_per_n, out_cstride, out_coff, align_corners);
+    });
+    return check_launch("grid_sample2d_fwd");
+}
+
+static int plan_args_ok(int ndim, int N, int D, int H, int W, int64_t nvox_per_n) {
+    if (!(ndim == 2 || ndim == 3)) { set_error("grid_plan: ndim must be 2 or 3"); return B2_ERR_BAD_ARG; }
+    if (ndim == 2 && D != 1) { set_error("grid_plan: ndim 2 needs D == 1"); return B2_ERR_BAD_ARG; }
+    if ((int64_t)N * nvox_per_n >= (int64_t)1 << 31 || (int64_t)N * D * H * W >= (int64_t)1 << 31) {
+        set_error("grid_plan: more than 2^31 voxels or cells"); return B2_ERR_UNSUPPORTED;
+    }
+    return 0;
+}
+
+extern "C" int b2_grid_plan_count(const float* grid, int32_t* counts, int ndim, int N, int D, int H,
+                                  int W, int64_t nvox_per_n, int align_corners, void* stream) {
+    B2_REQUIRE(grid && counts, "grid_plan_count: null pointer");
+    if (int e = plan_args_ok(ndim, N, D, H, W, nvox_per_n)) return e;
+    int64_t nvox = (int64_t)N * nvox_per_n;
+    if (nvox == 0) return 0;
+    grid_plan_kernel<0><<<stream_grid(nvox, 256), 256, 0, (cudaStream_t)stream>>>(
+        grid, counts, nullptr, nullptr, ndim, N, D, H, W, nvox_per_n, align_corners);
+    return check_launch("grid_plan_count");
+}
+
+extern "C" int b2_grid_plan_fill(const float* grid, const int32_t* row_ptr, int32_t* cursor,
+                                 void* entries, int ndim, int N, int D, int H, int W,
+                                 int64_t nvox_per_n, int align_corners, void* stream) {
+    B2_REQUIRE(grid && row_ptr && cursor && entries, "grid_plan_fill: null pointer");
+    if (int e = plan_args_ok(ndim, N, D, H, W, nvox_per_n)) return e;
+    int64_t nvox = (int64_t)N * nvox_per_n;
+    if (nvox == 0) return 0;
+    grid_plan_kernel<1><<<stream_grid(nvox, 256), 256, 0, (cudaStream_t)stream>>>(
+        grid, cursor, row_ptr, (int2*)entries, ndim, N, D, H, W, nvox_per_n, align_corners);
+    return check_launch("grid_plan_fill");
+}
+
+extern "C" int b2_grid_plan_sort(const int32_t* row_ptr, void* entries, int64_t ncell, void* stream) {
+    B2_REQUIRE(row_ptr && entries, "grid_plan_sort: null pointer");
+    if (ncell == 0) return 0;
+    grid_plan_sort_kernel<<<stream_grid(ncell, 256), 256, 0, (cudaStream_t)stream>>>(row_ptr, (int2*)entries, ncell);
+    return check_launch("grid_plan_sort");
+}
+
+extern "C" int b2_grid_sample_bwd(const float* gout, const int32_t* row_ptr, const void* entries,
+                                  float* gin, int64_t ncell, int C, int gout_cstride, int gout_coff,
+                                  void* stream) {
+    B2_REQUIRE(gout && row_ptr && entries && gin, "grid_sample_bwd: null pointer");
+    B2_REQUIRE(C % 4 == 0 && gout_cstride % 4 == 0 && gout_coff % 4 == 0 && aligned16(gout) && aligned16(gin),
+               "grid_sample_bwd: channel counts/offsets must be multiples of 4 and pointers 16B aligned");
+    if (ncell == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_LPV_SWITCH(C, {
+        int grid_x = stream_grid(ncell, 256 / LPV, kNumSMs * 16);
+        grid_sample_bwd_kernel<LPV><<<grid_x, 256, 0, st>>>(gout, row_ptr, (const int2*)entries, (float4*)gin,
+                                                           ncell, gout_cstride, gout_coff);
+    });
+    return check_launch("grid_sample_bwd");
+}

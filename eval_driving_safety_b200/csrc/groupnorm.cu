@@ -1,0 +1,265 @@
+// GroupNorm (+ residual) (+ ReLU) on channels-last 3-D volumes, forward and data
+// gradient: the norm/activation that follows every 3-D conv of the hourglass
+// stacks (upstream convbn_3d; reached from attack/DSGN/pgd_attack.py:308/:336).
+//
+//   y = act( (x - mean_g) * rstd_g * gamma_c + beta_c (+ res) )
+//
+// Roofline: HBM streaming.  fwd = stats pass (read x) + apply pass (read x [,res],
+// write y); bwd = stats pass (read gy, x, y) + apply pass (read gy, x, y, write gx).
+// All reductions are two-stage with a fixed order (per-block partials, then a
+// serial fp64 combine) -> deterministic.  gamma/beta are frozen in an attack, so no
+// parameter gradients are produced.
+#include "common.cuh"
+
+namespace b2 {
+
+constexpr int kGnBlocks = kNumSMs * 2;   // partial blocks per sample
+constexpr int kGnMaxC = 256;
+
+struct GnLayout {
+    int lpr;      // lanes (float4) per row = C/4
+    int rpb;      // rows per block step
+    int threads;  // lpr * rpb
+};
+
+static GnLayout gn_layout(int C) {
+    GnLayout l;
+    l.lpr = C / 4;
+    l.rpb = 256 / l.lpr;
+    if (l.rpb < 1) l.rpb = 1;
+    l.threads = l.lpr * l.rpb;
+    return l;
+}
+
+// ws layout (floats): partial[N][kGnBlocks][2][C]  then  coef[N][3][C]
+__host__ __device__ inline int64_t gn_partial_floats(int N, int C) { return (int64_t)N * kGnBlocks * 2 * C; }
+
+// MODE 0: sums of (x, x^2) per channel.  MODE 1: sums of (gz*x, gz) per channel,
+// gz = gy * (relu ? y > 0 : 1).
+template <int MODE>
+__global__ void gn_partials_kernel(const float4* __restrict__ a, const float4* __restrict__ x,
+                                   const float4* __restrict__ y, float* __restrict__ partial,
+                                   int C, int64_t S, int lpr, int rpb, int relu) {
+    extern __shared__ float4 sh[];  // [2][rpb][lpr]
+    const int n = blockIdx.y;
+    const int lane = threadIdx.x % lpr, r = threadIdx.x / lpr;
+    const int64_t rows_per_block = (S + gridDim.x - 1) / gridDim.x;
+    const int64_t s_begin = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t s_end = min(S, s_begin + rows_per_block);
+    const int64_t base = (int64_t)n * S * lpr;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = p;
+    for (int64_t s = s_begin + r; s < s_end; s += rpb) {
+        int64_t i = base + s * lpr + lane;
+        if (MODE == 0) {
+            float4 v = ldg_stream(x + i);
+            p.x += v.x; p.y += v.y; p.z += v.z; p.w += v.w;
+            q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+        } else {
+            float4 g = __ldg(a + i), v = __ldg(x + i);
+            if (relu) {
+                float4 o = __ldg(y + i);
+                g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
+                g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+            }
+            p.x += g.x * v.x; p.y += g.y * v.y; p.z += g.z * v.z; p.w += g.w * v.w;
+            q.x += g.x; q.y += g.y; q.z += g.z; q.w += g.w;
+        }
+    }
+    sh[r * lpr + lane] = p;
+    sh[(rpb + r) * lpr + lane] = q;
+    __syncthreads();
+    if (r == 0) {
+        float4 sp = make_float4(0.f, 0.f, 0.f, 0.f), sq = sp;
+        for (int k = 0; k < rpb; ++k) {
+            float4 u = sh[k * lpr + lane], w = sh[(rpb + k) * lpr + lane];
+            sp.x += u.x; sp.y += u.y; sp.z += u.z; sp.w += u.w;
+            sq.x += w.x; sq.y += w.y; sq.z += w.z; sq.w += w.w;
+        }
+        float* dst = partial + (((int64_t)n * gridDim.x + blockIdx.x) * 2) * C;
+        *reinterpret_cast<float4*>(dst + lane * 4) = sp;
+        *reinterpret_cast<float4*>(dst + C + lane * 4) = sq;
+    }
+}
+
+// One block per sample, one thread per channel.
+// fwd: stats[n][g] = (mean, rstd); coef[n][0][c] = scale, coef[n][1][c] = shift.
+__global__ void gn_finalize_fwd(const float* __restrict__ partial, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, float* __restrict__ stats,
+                                float* __restrict__ coef, int C, int64_t S, int G, float eps, int nblocks) {
+    __shared__ double s1[kGnMaxC], s2[kGnMaxC];
+    const int n = blockIdx.x, c = threadIdx.x;
+    double a = 0.0, b = 0.0;
+    if (c < C) {
+        for (int k = 0; k < nblocks; ++k) {
+            const float* p = partial + (((int64_t)n * nblocks + k) * 2) * C;
+            a += (double)p[c];
+            b += (double)p[C + c];
+        }
+        s1[c] = a; s2[c] = b;
+    }
+    __syncthreads();
+    if (c < C) {
+        const int cpg = C / G, g = c / cpg;
+        double sum = 0.0, sq = 0.0;
+        for (int j = 0; j < cpg; ++j) { sum += s1[g * cpg + j]; sq += s2[g * cpg + j]; }
+        double m = (double)cpg * (double)S;
+        double mean = sum / m;
+        double var = sq / m - mean * mean;
+        if (var < 0.0) var = 0.0;
+        double rstd = 1.0 / sqrt(var + (double)eps);
+        if (c % cpg == 0) {
+            stats[((int64_t)n * G + g) * 2 + 0] = (float)mean;
+            stats[((int64_t)n * G + g) * 2 + 1] = (float)rstd;
+        }
+        double scale = (double)gamma[c] * rstd;
+        coef[((int64_t)n * 3 + 0) * C + c] = (float)scale;
+        coef[((int64_t)n * 3 + 1) * C + c] = (float)((double)beta[c] - mean * scale);
+    }
+}
+
+// bwd: coef[n][0][c] = gamma_c*rstd_g, coef[n][1][c] = c2_g, coef[n][2][c] = c3_g with
+//   ds = sum_c gamma_c * sum(gz*x), db = sum_c gamma_c * sum(gz)
+//   c2 = (db*mean - ds) * rstd^3 / m ; c3 = -c2*mean - db*rstd/m ; gx = coef0*gz + c2*x + c3
+__global__ void gn_finalize_bwd(const float* __restrict__ partial, const float* __restrict__ gamma,
+                                const float* __restrict__ stats, float* __restrict__ coef, int C,
+                                int64_t S, int G, int nblocks) {
+    __shared__ double s1[kGnMaxC], s2[kGnMaxC];
+    const int n = blockIdx.x, c = threadIdx.x;
+    if (c < C) {
+        double a = 0.0, b = 0.0;
+        for (int k = 0; k < nblocks; ++k) {
+            const float* p = partial + (((int64_t)n * nblocks + k) * 2) * C;
+            a += (double)p[c];
+            b += (double)p[C + c];
+        }
+        s1[c] = a * (double)gamma[c];
+        s2[c] = b * (double)gamma[c];
+    }
+    __syncthreads();
+    if (c < C) {
+        const int cpg = C / G, g = c / cpg;
+        double ds = 0.0, db = 0.0;
+        for (int j = 0; j < cpg; ++j) { ds += s1[g * cpg + j]; db += s2[g * cpg + j]; }
+        double m = (double)cpg * (double)S;
+        double mean = stats[((int64_t)n * G + g) * 2 + 0], rstd = stats[((int64_t)n * G + g) * 2 + 1];
+        double c2 = (db * mean - ds) * rstd * rstd * rstd / m;
+        double c3 = -c2 * mean - db * rstd / m;
+        coef[((int64_t)n * 3 + 0) * C + c] = (float)((double)gamma[c] * rstd);
+        coef[((int64_t)n * 3 + 1) * C + c] = (float)c2;
+        coef[((int64_t)n * 3 + 2) * C + c] = (float)c3;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_fwd(const float4* __restrict__ x, const float4* __restrict__ res, const float* __restrict__ coef,
+             float4* __restrict__ y, int C, int64_t S, int relu) {
+    extern __shared__ float shc[];  // [2][C]
+    const int n = blockIdx.y, lpr = C / 4;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) shc[i] = coef[(int64_t)n * 3 * C + i];
+    __syncthreads();
+    const int64_t total = S * lpr, base = (int64_t)n * total;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int q = (int)(i % lpr) * 4;
+        float4 v = ldg_stream(x + base + i);
+        float4 o;
+        o.x = v.x * shc[q] + shc[C + q];
+        o.y = v.y * shc[q + 1] + shc[C + q + 1];
+        o.z = v.z * shc[q + 2] + shc[C + q + 2];
+        o.w = v.w * shc[q + 3] + shc[C + q + 3];
+        if (res) {
+            float4 r = ldg_stream(res + base + i);
+            o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        y[base + i] = o;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+gn_apply_bwd(const float4* gy, const float4* __restrict__ x, const float4* __restrict__ y,
+             const float* __restrict__ coef, float4* __restrict__ gx, float4* gres, int C,
+             int64_t S, int relu) {
+    extern __shared__ float shc[];  // [3][C]
+    const int n = blockIdx.y, lpr = C / 4;
+    for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) shc[i] = coef[(int64_t)n * 3 * C + i];
+    __syncthreads();
+    const int64_t total = S * lpr, base = (int64_t)n * total;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int q = (int)(i % lpr) * 4;
+        float4 g = ldg_stream(gy + base + i);
+        float4 v = ldg_stream(x + base + i);
+        if (relu) {
+            float4 o = ldg_stream(y + base + i);
+            g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
+            g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
+        }
+        float4 d;
+        d.x = shc[q] * g.x + shc[C + q] * v.x + shc[2 * C + q];
+        d.y = shc[q + 1] * g.y + shc[C + q + 1] * v.y + shc[2 * C + q + 1];
+        d.z = shc[q + 2] * g.z + shc[C + q + 2] * v.z + shc[2 * C + q + 2];
+        d.w = shc[q + 3] * g.w + shc[C + q + 3] * v.w + shc[2 * C + q + 3];
+        if (gres) gres[base + i] = g;   // may alias gy: read above, same index
+        gx[base + i] = d;
+    }
+}
+
+}  // namespace b2
+
+using namespace b2;
+
+extern "C" int64_t b2_groupnorm_workspace_bytes(int N, int C) {
+    return (gn_partial_floats(N, C) + (int64_t)N * 3 * C) * (int64_t)sizeof(float);
+}
+
+static int gn_check(const char* who, int N, int C, int64_t S, int G) {
+    if (C % 4 != 0 || C > kGnMaxC || C < 4) { set_error("%s: C must be a multiple of 4 in [4,%d] (got %d)", who, kGnMaxC, C); return B2_ERR_UNSUPPORTED; }
+    if (G < 1 || C % G != 0) { set_error("%s: G must divide C (C=%d, G=%d)", who, C, G); return B2_ERR_BAD_ARG; }
+    if (N < 0 || S < 0) { set_error("%s: negative size", who); return B2_ERR_BAD_ARG; }
+    return 0;
+}
+
+extern "C" int b2_groupnorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,
+                                float* y, float* stats, int N, int C, int64_t S, int G, float eps,
+                                int relu, void* workspace, void* stream) {
+    B2_REQUIRE(x && gamma && beta && y && stats && workspace, "groupnorm_fwd: null pointer");
+    if (int e = gn_check("groupnorm_fwd", N, C, S, G)) return e;
+    B2_REQUIRE(aligned16(x) && aligned16(y) && (!res || aligned16(res)), "groupnorm_fwd: pointers must be 16B aligned");
+    if (N == 0 || S == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    GnLayout l = gn_layout(C);
+    float* partial = (float*)workspace;
+    float* coef = partial + gn_partial_floats(N, C);
+    int nblocks = (int)(S < kGnBlocks ? S : kGnBlocks);
+    gn_partials_kernel<0><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
+        nullptr, (const float4*)x, nullptr, partial, C, S, l.lpr, l.rpb, 0);
+    gn_finalize_fwd<<<N, kGnMaxC, 0, st>>>(partial, gamma, beta, stats, coef, C, S, G, eps, nblocks);
+    int gx = stream_grid(S * l.lpr, 256 * 4, kNumSMs * 8);
+    gn_apply_fwd<<<dim3(gx, N), 256, 2 * C * sizeof(float), st>>>((const float4*)x, (const float4*)res, coef,
+                                                                  (float4*)y, C, S, relu);
+    return check_launch("groupnorm_fwd");
+}
+
+extern "C" int b2_groupnorm_bwd(const float* gy, const float* x, const float* y, const float* gamma,
+                                const float* stats, float* gx, float* gres, int N, int C, int64_t S,
+                                int G, int relu, void* workspace, void* stream) {
+    B2_REQUIRE(gy && x && gamma && stats && gx && workspace, "groupnorm_bwd: null pointer");
+    B2_REQUIRE(!relu || y, "groupnorm_bwd: relu needs the saved output y");
+    if (int e = gn_check("groupnorm_bwd", N, C, S, G)) return e;
+    B2_REQUIRE(aligned16(gy) && aligned16(x) && aligned16(gx), "groupnorm_bwd: pointers must be 16B aligned");
+    if (N == 0 || S == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    GnLayout l = gn_layout(C);
+    float* partial = (float*)workspace;
+    float* coef = partial + gn_partial_floats(N, C);
+    int nblocks = (int)(S < kGnBlocks ? S : kGnBlocks);
+    gn_partials_kernel<1><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
+        (const float4*)gy, (const float4*)x, (const float4*)y, partial, C, S, l.lpr, l.rpb, relu);
+    gn_finalize_bwd<<<N, kGnMaxC, 0, st>>>(partial, gamma, stats, coef, C, S, G, nblocks);
+    int gxd = stream_grid(S * l.lpr, 256 * 4, kNumSMs * 8);
+    gn_apply_bwd<<<dim3(gxd, N), 256, 3 * C * sizeof(float), st>>>((const float4*)gy, (const float4*)x,
+                                                                   (const float4*)y, coef, (float4*)gx,
+                                                                   (float4*)gres, C, S, relu);
+    return check_launch("groupnorm_bwd");
+}

@@ -1,0 +1,47 @@
+// libb2attack.so: version, error reporting and the conv3d dispatcher.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace b2 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int conv3d_simt_launch(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
+                       int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st);
+int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
+                          int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st);
+
+}  // namespace b2
+
+extern "C" int b2_version(void) { return 100; }  // 0.1.0
+
+extern "C" const char* b2_last_error(void) { return b2::g_err; }
+
+extern "C" int b2_conv3d(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
+                         int Hi, int Wi, int stride, int mode, int impl, void* stream) {
+    B2_REQUIRE(in && wp && out, "conv3d: null pointer");
+    B2_REQUIRE(N >= 0 && Cin > 0 && Cout > 0 && Di > 0 && Hi > 0 && Wi > 0, "conv3d: bad dims");
+    B2_REQUIRE(mode == 0 || mode == 1, "conv3d: mode must be 0 (CONV) or 1 (DECONV)");
+    B2_REQUIRE((mode == 0 && (stride == 1 || stride == 2)) || (mode == 1 && stride == 2),
+               "conv3d: unsupported stride %d for mode %d", stride, mode);
+    int Do, Ho, Wo;
+    if (mode == 0) {
+        Do = (Di - 1) / stride + 1; Ho = (Hi - 1) / stride + 1; Wo = (Wi - 1) / stride + 1;
+    } else {
+        Do = 2 * Di; Ho = 2 * Hi; Wo = 2 * Wi;
+    }
+    if (N == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (impl == 1) return b2::conv3d_simt_launch(in, wp, out, N, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo, stride, mode, st);
+    if (impl == 0) return b2::conv3d_tcgen05_launch(in, wp, out, N, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo, stride, mode, st);
+    b2::set_error("conv3d: unknown impl %d", impl);
+    return B2_ERR_BAD_ARG;
+}

@@ -1,0 +1,462 @@
+"""autograd.Function / functional layer over the C ABI (include/b2attack.h).
+
+Host-side mirror of the operator interface the reference's model reaches:
+``BuildCostVolume`` (upstream dsgn.layers.BuildCostVolume), ``F.grid_sample``
+lifting, ``Conv3d``/``ConvTranspose3d`` + ``GroupNorm`` of the hourglass stacks
+(all behind attack/DSGN/pgd_attack.py:308 forward and :336 backward) and
+``ROIAlign`` (attack/Stereo-RCNN/stereo_rcnn.py:44-45, 110-141).
+
+Every op runs on the CURRENT torch CUDA stream, takes fp32 CUDA tensors, and
+raises RuntimeError on anything else: there is no CPU or PyTorch fallback.
+Volumes are logical NCDHW tensors in ``torch.channels_last_3d`` memory format,
+so they remain drop-in arguments for any stock torch op.
+"""
+import ctypes
+import os
+
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _lib
+from ._lib import check, c_vp
+
+CL3 = torch.channels_last_3d
+CL2 = torch.channels_last
+
+# conv implementation: 0 = tcgen05 (TF32 in, fp32 accumulate), 1 = fp32 SIMT (verification)
+CONV_IMPL = int(os.environ.get("B2_CONV_IMPL", "0"))
+
+
+def set_conv_impl(impl):
+    global CONV_IMPL
+    CONV_IMPL = int(impl)
+
+
+def _stream():
+    return c_vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return c_vp(t.data_ptr()) if t is not None else c_vp(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("eval_driving_safety_b200 ops need CUDA tensors (no CPU fallback); got %s" % t.device)
+        if t.dtype != torch.float32:
+            raise RuntimeError("eval_driving_safety_b200 ops are fp32; got %s" % t.dtype)
+
+
+def cl3(x):
+    """NCDHW logical tensor -> channels-last-3d memory (no copy if already)."""
+    if x.permute(0, 2, 3, 4, 1).is_contiguous():
+        return x
+    return x.contiguous(memory_format=CL3)
+
+
+def cl2(x):
+    if x.permute(0, 2, 3, 1).is_contiguous():
+        return x
+    return x.contiguous(memory_format=CL2)
+
+
+def empty_cl3(n, c, d, h, w, device):
+    return torch.empty((n, d, h, w, c), device=device, dtype=torch.float32).permute(0, 4, 1, 2, 3)
+
+
+def empty_cl2(n, c, h, w, device):
+    return torch.empty((n, h, w, c), device=device, dtype=torch.float32).permute(0, 3, 1, 2)
+
+
+# ---------------------------------------------------------------------------
+# (1) cost volume
+# ---------------------------------------------------------------------------
+class BuildCostVolumeFn(Function):
+    """left,right [N,C,H,W], shifts [N,D] -> cost [N,2C,D,H,W] (channels-last-3d
+    memory when ``channels_last``; plain NCDHW, the upstream layout, otherwise)."""
+
+    @staticmethod
+    def forward(ctx, left, right, shifts, channels_last=True):
+        _need_cuda(left, right, shifts)
+        lib = _lib.load()
+        n, c, h, w = left.shape
+        d = shifts.shape[1]
+        shifts = shifts.contiguous()
+        if channels_last:
+            l, r = cl2(left), cl2(right)
+            cost = empty_cl3(n, 2 * c, d, h, w, left.device)
+        else:
+            l, r = left.contiguous(), right.contiguous()
+            cost = torch.empty((n, 2 * c, d, h, w), device=left.device, dtype=torch.float32)
+        check(lib.b2_cost_volume_fwd(_p(l), _p(r), _p(shifts), _p(cost), n, c, d, h, w,
+                                     1 if channels_last else 0, _stream()), "cost_volume_fwd")
+        ctx.save_for_backward(shifts)
+        ctx.dims = (n, c, d, h, w, channels_last)
+        return cost
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gcost):
+        (shifts,) = ctx.saved_tensors
+        n, c, d, h, w, channels_last = ctx.dims
+        lib = _lib.load()
+        if channels_last:
+            g = cl3(gcost)
+            gl, gr = empty_cl2(n, c, h, w, g.device), empty_cl2(n, c, h, w, g.device)
+        else:
+            g = gcost.contiguous()
+            gl = torch.empty((n, c, h, w), device=g.device, dtype=torch.float32)
+            gr = torch.empty_like(gl)
+        check(lib.b2_cost_volume_bwd(_p(g), _p(shifts), _p(gl), _p(gr), n, c, d, h, w,
+                                     1 if channels_last else 0, _stream()), "cost_volume_bwd")
+        return gl, gr, None, None
+
+
+def build_cost_volume(left, right, shifts, channels_last=True):
+    return BuildCostVolumeFn.apply(left, right, shifts, channels_last)
+
+
+# ---------------------------------------------------------------------------
+# (2) grid_sample lifting
+# ---------------------------------------------------------------------------
+class GridPlan:
+    """CSR 'input cell -> (output voxel, weight)' plan for the deterministic
+    backward; built once per sampling grid (b2_grid_plan_*)."""
+
+    def __init__(self, grid, in_spatial, align_corners):
+        _need_cuda(grid)
+        lib = _lib.load()
+        ndim = grid.shape[-1]
+        assert ndim in (2, 3) and len(in_spatial) == ndim
+        n = grid.shape[0]
+        d, h, w = (1,) + tuple(in_spatial) if ndim == 2 else tuple(in_spatial)
+        grid = grid.contiguous()
+        nvox_per_n = grid[0].numel() // ndim
+        ncell = n * d * h * w
+        counts = torch.zeros(ncell, device=grid.device, dtype=torch.int32)
+        st = _stream()
+        check(lib.b2_grid_plan_count(_p(grid), _p(counts), ndim, n, d, h, w, nvox_per_n,
+                                     int(align_corners), st), "grid_plan_count")
+        row_ptr = torch.zeros(ncell + 1, device=grid.device, dtype=torch.int32)
+        row_ptr[1:] = torch.cumsum(counts, 0, dtype=torch.int32)
+        nnz = int(row_ptr[-1].item())
+        entries = torch.empty((max(nnz, 1), 2), device=grid.device, dtype=torch.int32)
+        counts.zero_()
+        check(lib.b2_grid_plan_fill(_p(grid), _p(row_ptr), _p(counts), _p(entries), ndim, n, d, h, w,
+                                    nvox_per_n, int(align_corners), st), "grid_plan_fill")
+        check(lib.b2_grid_plan_sort(_p(row_ptr), _p(entries), ncell, st), "grid_plan_sort")
+        self.row_ptr, self.entries, self.ncell, self.nnz = row_ptr, entries, ncell, nnz
+        self.ndim, self.in_spatial, self.n = ndim, tuple(in_spatial), n
+
+
+def _gs_fwd(lib, inp, grid, out, out_c, coff, align):
+    n, c = inp.shape[:2]
+    nvox_per_n = grid[0].numel() // grid.shape[-1]
+    if grid.shape[-1] == 3:
+        d, h, w = inp.shape[2:]
+        check(lib.b2_grid_sample3d_fwd(_p(inp), _p(grid), _p(out), n, c, d, h, w, nvox_per_n, out_c, coff,
+                                       int(align), _stream()), "grid_sample3d_fwd")
+    else:
+        h, w = inp.shape[2:]
+        check(lib.b2_grid_sample2d_fwd(_p(inp), _p(grid), _p(out), n, c, h, w, nvox_per_n, out_c, coff,
+                                       int(align), _stream()), "grid_sample2d_fwd")
+
+
+class GridSampleFn(Function):
+    """F.grid_sample(input, grid, 'bilinear', 'zeros', align_corners) for 4-D/5-D
+    inputs; gradient w.r.t. ``input`` only (the grid is calibration, not data)."""
+
+    @staticmethod
+    def forward(ctx, inp, grid, align_corners, plan):
+        _need_cuda(inp, grid)
+        lib = _lib.load()
+        nd = grid.shape[-1]
+        inp = cl3(inp) if nd == 3 else cl2(inp)
+        grid = grid.contiguous()
+        n, c = inp.shape[:2]
+        if nd == 3:
+            out = empty_cl3(n, c, grid.shape[1], grid.shape[2], grid.shape[3], inp.device)
+        else:
+            out = empty_cl2(n, c, grid.shape[1], grid.shape[2], inp.device)
+        _gs_fwd(lib, inp, grid, out, c, 0, align_corners)
+        ctx.plan, ctx.grid, ctx.align, ctx.in_shape = plan, grid, align_corners, tuple(inp.shape)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        lib = _lib.load()
+        plan = ctx.plan or GridPlan(ctx.grid, ctx.in_shape[2:], ctx.align)
+        nd = plan.ndim
+        g = cl3(gout) if nd == 3 else cl2(gout)
+        c = ctx.in_shape[1]
+        gin = empty_cl3(*ctx.in_shape, g.device) if nd == 3 else empty_cl2(*ctx.in_shape, g.device)
+        check(lib.b2_grid_sample_bwd(_p(g), _p(plan.row_ptr), _p(plan.entries), _p(gin), plan.ncell, c, c, 0,
+                                     _stream()), "grid_sample_bwd")
+        return gin, None, None, None
+
+
+def grid_sample(inp, grid, align_corners=False, plan=None):
+    return GridSampleFn.apply(inp, grid, align_corners, plan)
+
+
+class LiftFn(Function):
+    """Frustum -> voxel lifting of DSGN: trilinear sample of the PSV feature and
+    bilinear sample of the image feature written side by side into ONE
+    channels-last voxel tensor [N, C3+C2, Z, Y, X] (no torch.cat round trip)."""
+
+    @staticmethod
+    def forward(ctx, psv, img, grid3, plan3, plan2, align_corners):
+        _need_cuda(psv, img, grid3)
+        lib = _lib.load()
+        psv, img, grid3 = cl3(psv), cl2(img), grid3.contiguous()
+        n, c3 = psv.shape[:2]
+        c2 = img.shape[1]
+        z, y, x = grid3.shape[1:4]
+        grid2 = grid3[..., :2].contiguous().view(n, z * y, x, 2)
+        out = empty_cl3(n, c3 + c2, z, y, x, psv.device)
+        _gs_fwd(lib, psv, grid3, out, c3 + c2, 0, align_corners)
+        _gs_fwd(lib, img, grid2, out, c3 + c2, c3, align_corners)
+        ctx.plans = (plan3 or GridPlan(grid3, psv.shape[2:], align_corners),
+                     plan2 or GridPlan(grid2, img.shape[2:], align_corners))
+        ctx.shapes = (tuple(psv.shape), tuple(img.shape))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        lib = _lib.load()
+        g = cl3(gout)
+        (s3, s2), (p3, p2) = ctx.shapes, ctx.plans
+        ctot = s3[1] + s2[1]
+        g3, g2 = empty_cl3(*s3, g.device), empty_cl2(*s2, g.device)
+        check(lib.b2_grid_sample_bwd(_p(g), _p(p3.row_ptr), _p(p3.entries), _p(g3), p3.ncell, s3[1], ctot, 0,
+                                     _stream()), "grid_sample_bwd(3d)")
+        check(lib.b2_grid_sample_bwd(_p(g), _p(p2.row_ptr), _p(p2.entries), _p(g2), p2.ncell, s2[1], ctot, s3[1],
+                                     _stream()), "grid_sample_bwd(2d)")
+        return g3, g2, None, None, None, None
+
+
+def lift(psv, img, grid3, plan3=None, plan2=None, align_corners=True):
+    return LiftFn.apply(psv, img, grid3, plan3, plan2, align_corners)
+
+
+# ---------------------------------------------------------------------------
+# (3) conv3d / deconv3d (+ data gradients) and GroupNorm
+# ---------------------------------------------------------------------------
+_PACK_CACHE = {}
+
+
+def _packed(weight, kind):
+    """Packed weights wp[27][Cout][Cin] for the gather modes of b2_conv3d.
+    kind: conv_fwd, conv_dgrad_s1, conv_dgrad_s2, deconv_fwd, deconv_dgrad."""
+    key = (weight.data_ptr(), weight._version, kind, tuple(weight.shape))
+    hit = _PACK_CACHE.get(key)
+    if hit is not None:
+        return hit
+    w = weight.detach()
+    if kind == "conv_fwd":            # w [Co,Ci,k]: wp[k][co][ci]
+        wp = w.permute(2, 3, 4, 0, 1)
+    elif kind == "conv_dgrad_s1":     # CONV s1 on gout, wp[k][ci][co] = w[co,ci,flip k]
+        wp = w.flip(2, 3, 4).permute(2, 3, 4, 1, 0)
+    elif kind == "conv_dgrad_s2":     # DECONV on gout, wp[k][ci][co] = w[co,ci,k]
+        wp = w.permute(2, 3, 4, 1, 0)
+    elif kind == "deconv_fwd":        # wt [Ci,Co,k]: DECONV, wp[k][co][ci] = wt[ci,co,k]
+        wp = w.permute(2, 3, 4, 1, 0)
+    elif kind == "deconv_dgrad":      # CONV s2 on gout, wp[k][ci][co] = wt[ci,co,k]
+        wp = w.permute(2, 3, 4, 0, 1)
+    else:
+        raise ValueError(kind)
+    wp = wp.reshape(27, wp.shape[3], wp.shape[4]).contiguous()
+    if len(_PACK_CACHE) > 512:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = wp
+    return wp
+
+
+def _conv_call(x, wp, stride, mode, impl):
+    lib = _lib.load()
+    n, cin, di, hi, wi = x.shape
+    cout = wp.shape[1]
+    assert wp.shape[2] == cin, (wp.shape, cin)
+    if mode == 0:
+        do, ho, wo = (di - 1) // stride + 1, (hi - 1) // stride + 1, (wi - 1) // stride + 1
+    else:
+        do, ho, wo = 2 * di, 2 * hi, 2 * wi
+    out = empty_cl3(n, cout, do, ho, wo, x.device)
+    check(lib.b2_conv3d(_p(x), _p(wp), _p(out), n, cin, cout, di, hi, wi, stride, mode, impl, _stream()),
+          "conv3d(mode=%d,stride=%d,impl=%d)" % (mode, stride, impl))
+    return out
+
+
+class Conv3dFn(Function):
+    """3x3x3, padding 1, bias-free Conv3d (transposed=False, stride 1|2) or
+    ConvTranspose3d(stride 2, output_padding 1) (transposed=True); forward and
+    data gradient.  Weights are frozen in an attack: no weight gradient."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, transposed, impl):
+        _need_cuda(x, weight)
+        if weight.requires_grad:
+            raise RuntimeError("attack path: weights are frozen; call requires_grad_(False) on the model "
+                               "(the reference wastes its wgrad, attack/DSGN/pgd_attack.py:333)")
+        if tuple(weight.shape[2:]) != (3, 3, 3):
+            raise RuntimeError("only 3x3x3 kernels are supported")
+        x = cl3(x)
+        if stride == 2 and any(s % 2 for s in x.shape[2:]) and not transposed:
+            raise RuntimeError("stride-2 conv needs even spatial dims, got %s" % (tuple(x.shape[2:]),))
+        impl = CONV_IMPL if impl is None else impl
+        if transposed:
+            assert stride == 2
+            out = _conv_call(x, _packed(weight, "deconv_fwd"), 2, 1, impl)
+        else:
+            out = _conv_call(x, _packed(weight, "conv_fwd"), stride, 0, impl)
+        ctx.weight, ctx.cfg = weight, (stride, transposed, impl)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        stride, transposed, impl = ctx.cfg
+        g = cl3(gout)
+        if transposed:
+            gin = _conv_call(g, _packed(ctx.weight, "deconv_dgrad"), 2, 0, impl)
+        elif stride == 1:
+            gin = _conv_call(g, _packed(ctx.weight, "conv_dgrad_s1"), 1, 0, impl)
+        else:
+            gin = _conv_call(g, _packed(ctx.weight, "conv_dgrad_s2"), 2, 1, impl)
+        return gin, None, None, None, None
+
+
+def conv3d(x, weight, stride=1, transposed=False, impl=None):
+    return Conv3dFn.apply(x, weight, stride, transposed, impl)
+
+
+class Conv3dC1Fn(Function):
+    """Conv3d(Cin -> 1, k3, p1, bias-free): bandwidth-bound SIMT head."""
+
+    @staticmethod
+    def forward(ctx, x, weight):
+        _need_cuda(x, weight)
+        lib = _lib.load()
+        x = cl3(x)
+        n, cin, d, h, w = x.shape
+        key = (weight.data_ptr(), weight._version, "c1")
+        w1 = _PACK_CACHE.get(key)
+        if w1 is None:
+            w1 = weight.detach()[0].permute(1, 2, 3, 0).reshape(27, cin).contiguous()
+            _PACK_CACHE[key] = w1
+        out = torch.empty((n, 1, d, h, w), device=x.device, dtype=torch.float32)
+        check(lib.b2_conv3d_c1_fwd(_p(x), _p(w1), _p(out), n, cin, d, h, w, _stream()), "conv3d_c1_fwd")
+        ctx.w1, ctx.dims = w1, (n, cin, d, h, w)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        lib = _lib.load()
+        n, cin, d, h, w = ctx.dims
+        g = gout.contiguous()
+        gin = empty_cl3(n, cin, d, h, w, g.device)
+        check(lib.b2_conv3d_c1_dgrad(_p(g), _p(ctx.w1), _p(gin), n, cin, d, h, w, _stream()), "conv3d_c1_dgrad")
+        return gin, None
+
+
+def conv3d_c1(x, weight):
+    return Conv3dC1Fn.apply(x, weight)
+
+
+_WS = {}
+
+
+def _workspace(nbytes, device):
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), device=device, dtype=torch.uint8)
+        _WS[key] = ws
+    return ws
+
+
+class GroupNormActFn(Function):
+    """y = act(GroupNorm(x) (+ res)) on channels-last volumes; data gradient only."""
+
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, groups, eps, relu):
+        _need_cuda(x, res, gamma, beta)
+        lib = _lib.load()
+        x = cl3(x)
+        res = cl3(res) if res is not None else None
+        n, c = x.shape[:2]
+        s = x[0, 0].numel()
+        y = empty_cl3(*x.shape, x.device)
+        stats = torch.empty((n, groups, 2), device=x.device, dtype=torch.float32)
+        ws = _workspace(lib.b2_groupnorm_workspace_bytes(n, c), x.device)
+        gamma, beta = gamma.detach().contiguous(), beta.detach().contiguous()
+        check(lib.b2_groupnorm_fwd(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(stats), n, c, s, groups,
+                                   float(eps), int(relu), _p(ws), _stream()), "groupnorm_fwd")
+        ctx.save_for_backward(x, y, gamma, stats)
+        ctx.cfg = (groups, relu, res is not None)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gy):
+        lib = _lib.load()
+        x, y, gamma, stats = ctx.saved_tensors
+        groups, relu, has_res = ctx.cfg
+        gy = cl3(gy)
+        n, c = x.shape[:2]
+        s = x[0, 0].numel()
+        gx = empty_cl3(*x.shape, x.device)
+        gres = empty_cl3(*x.shape, x.device) if (has_res and relu) else None
+        ws = _workspace(lib.b2_groupnorm_workspace_bytes(n, c), x.device)
+        check(lib.b2_groupnorm_bwd(_p(gy), _p(x), _p(y), _p(gamma), _p(stats), _p(gx), _p(gres), n, c, s, groups,
+                                   int(relu), _p(ws), _stream()), "groupnorm_bwd")
+        if has_res and not relu:
+            gres = gy
+        return gx, gres, None, None, None, None, None
+
+
+def groupnorm_act(x, gamma, beta, groups, eps=1e-5, relu=False, res=None):
+    return GroupNormActFn.apply(x, res, gamma, beta, groups, eps, relu)
+
+
+# ---------------------------------------------------------------------------
+# RoIAlign (Stereo R-CNN, config 5)
+# ---------------------------------------------------------------------------
+class RoIAlignFn(Function):
+    @staticmethod
+    def forward(ctx, feat, rois, pooled, scale):
+        _need_cuda(feat, rois)
+        lib = _lib.load()
+        if feat.shape[0] != 1:
+            raise RuntimeError("roi_align: batch size 1 (as the attack scripts run)")
+        feat, rois = feat.contiguous(), rois.contiguous()
+        r, (_, c, h, w) = rois.shape[0], feat.shape
+        out = torch.empty((r, c, pooled, pooled), device=feat.device, dtype=torch.float32)
+        check(lib.b2_roi_align_fwd(_p(feat), _p(rois), _p(out), r, c, h, w, pooled, float(scale), _stream()),
+              "roi_align_fwd")
+        ctx.save_for_backward(rois)
+        ctx.cfg = (r, c, h, w, pooled, float(scale))
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        lib = _lib.load()
+        (rois,) = ctx.saved_tensors
+        r, c, h, w, pooled, scale = ctx.cfg
+        g = gout.contiguous()
+        gfeat = torch.empty((1, c, h, w), device=g.device, dtype=torch.float32)
+        check(lib.b2_roi_align_bwd(_p(g), _p(rois), _p(gfeat), r, c, h, w, pooled, scale, _stream()),
+              "roi_align_bwd")
+        return gfeat, None, None, None
+
+
+def roi_align(feat, rois, pooled, scale):
+    return RoIAlignFn.apply(feat, rois, pooled, scale)

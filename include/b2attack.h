@@ -1,0 +1,198 @@
+/*
+ * b2attack.h -- C ABI of libb2attack.so: hand-written sm_100a kernels for the
+ * attack hot path of DexterJZ/eval_driving_safety (PGD / FGSM / patch attacks
+ * against DSGN and Stereo R-CNN).
+ *
+ * The reference has no FFI of its own for this path: it is inline PyTorch code
+ * in attack/DSGN/{pgd,patch}_attack.py and attack/Stereo-RCNN/*.py that reaches
+ * ATen kernels and the upstream extensions dsgn._C / model.roi_layers.  Each
+ * entry point below names the reference lines (or upstream op) it replaces.
+ * INTEGRATION.md shows the ctypes / autograd.Function binding a maintainer adds.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes; all tensors fp32, contiguous in the stated layout;
+ *     every pointer is DEVICE memory unless marked "host".
+ *   - the caller owns every buffer including workspaces; the library never
+ *     allocates or frees device memory, never synchronises, and launches on the
+ *     cudaStream_t passed as `void* stream` (graph-capturable).
+ *   - return 0 on success, non-zero (cudaError_t or B2_ERR_*) otherwise; the text
+ *     of the last error on the calling thread is b2_last_error().  Never throws.
+ *   - re-entrant; no global state except cached TMA descriptors (conv3d).
+ */
+#ifndef B2ATTACK_H
+#define B2ATTACK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2_ERR_BAD_ARG   10001
+#define B2_ERR_UNSUPPORTED 10002
+#define B2_ERR_DRIVER    10003
+
+int b2_version(void);
+const char* b2_last_error(void);
+
+/* ------------------------------------------------------------------------- *
+ * (4) Perturbation update -- replaces the ~26 ATen launches of
+ *     attack/DSGN/pgd_attack.py:339-354 (and :196-207 de/normalise) and of
+ *     attack/Stereo-RCNN/pgd_attack.py:177-217 with ONE launch over all sets.
+ *
+ *   v   = denorm ? x*std_c + mean_c : x
+ *   adv = v + alpha*sign(g);  eta = clamp(adv - clean, -eps, eps)
+ *   o   = clamp(clean + eta, lo_c, hi_c);  out = denorm ? (o - mean_c)/std_c : o
+ *
+ * n_sets (<=4) tensors (e.g. left and right image batches) of shape
+ * [n_img, C, hw] each (C <= 4); x/g/clean/out are HOST arrays of n_sets device
+ * pointers.  mean/std/lo/hi: HOST arrays of C floats.  out may alias x.
+ * Bit-exact with the reference's fp32 operation order (no FMA contraction).
+ * ------------------------------------------------------------------------- */
+int b2_pgd_update(const float* const* x, const float* const* g, const float* const* clean,
+                  float* const* out, int n_sets, int n_img, int C, int64_t hw,
+                  float alpha, float eps, int denorm,
+                  const float* mean, const float* std_, const float* lo, const float* hi,
+                  void* stream);
+
+/* L2 variant (north_star; not in the reference, which only has the L-inf clamp at
+ * attack/DSGN/pgd_attack.py:346-347).  Per image: adv = v + alpha*g/||g||2,
+ * eta = (adv-clean)*min(1, eps/||adv-clean||2).  One tensor set [n_img,C,hw].
+ * workspace: b2_pgd_update_l2_workspace_bytes(n_img) bytes.  Deterministic
+ * (fixed-order two-stage reductions). */
+int64_t b2_pgd_update_l2_workspace_bytes(int n_img);
+int b2_pgd_update_l2(const float* x, const float* g, const float* clean, float* out,
+                     int n_img, int C, int64_t hw, float alpha, float eps, int denorm,
+                     const float* mean, const float* std_, const float* lo, const float* hi,
+                     void* workspace, void* stream);
+
+/* Patch blend, attack/DSGN/patch_attack.py:326-333,369-376 (and Stereo-RCNN
+ * patch_attack.py:225-230): img = (1-m)*img + m*pad(patch) with the circular mask
+ * dist((y,x),(cy,cx)) <= radius computed in-kernel (integer dy^2+dx^2 <= r^2 is
+ * exact).  In place on img [n_img,C,H,W]; only the (2r+1)^2 box
+ * is touched.  patch [C,2r+1,2r+1]; centers: HOST int array [n_img][2] = (cy,cx). */
+int b2_patch_apply(float* img, const float* patch, int n_img, int C, int H, int W,
+                   const int* centers, int radius, void* stream);
+
+/* Patch update, attack/DSGN/patch_attack.py:416-430:
+ *   d = clamp(0.5*alpha*(gL[box_L] + gR[box_R]), -eps, eps)
+ *   patch_out = patch - d, then optional per-channel clamp [lo_c,hi_c]
+ *   (attack/Stereo-RCNN/patch_attack.py:272-281; lo/hi HOST arrays or NULL).
+ * If delta_out != NULL the clipped step d is written there and patch is left
+ * untouched (multi-GPU: all-reduce the deltas, then b2_patch_axpy). */
+int b2_patch_update(float* patch, const float* gL, const float* gR, int C, int H, int W,
+                    int cyL, int cxL, int cyR, int cxR, int radius, float alpha, float eps,
+                    const float* lo, const float* hi, float* delta_out, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (1) Plane-sweep cost volume -- replaces upstream dsgn._C
+ *     build_cost_volume_{forward,backward} reached from
+ *     attack/DSGN/pgd_attack.py:308 / :336.
+ * layout 0 (NCDHW, the upstream layout): left/right [N,C,H,W] -> cost [N,2C,D,H,W]
+ * layout 1 (channels-last, the fast internal layout): left/right [N,H,W,C],
+ *          cost [N,D,H,W,2C]; C % 4 == 0.
+ * shifts: device [N,D] plane disparities in feature px (>= 0, fractional ok).
+ * Backward is gather-form (no atomics) and therefore bitwise deterministic.
+ * ------------------------------------------------------------------------- */
+int b2_cost_volume_fwd(const float* left, const float* right, const float* shifts, float* cost,
+                       int N, int C, int D, int H, int W, int layout, void* stream);
+int b2_cost_volume_bwd(const float* gcost, const float* shifts, float* gleft, float* gright,
+                       int N, int C, int D, int H, int W, int layout, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (2) grid_sample lifting (frustum -> voxel), bilinear/trilinear, zeros padding
+ *     -- replaces ATen grid_sampler_{2d,3d}[_backward] reached through
+ *     F.grid_sample inside StereoNet.forward (attack/DSGN/pgd_attack.py:308,336).
+ * Channels-last tensors.  The output may be a channel slice of a wider tensor:
+ * element (voxel v, channel c) lives at out[v*out_cstride + out_coff + c].
+ *   3-D: in [N,D,H,W,C], grid [N,Z,Y,X,3] (x->W, y->H, z->D), out voxels N*Z*Y*X
+ *   2-D: in [N,H,W,C],   grid [N,Ho,Wo,2]
+ * C % 4 == 0 and C <= 128.
+ * ------------------------------------------------------------------------- */
+int b2_grid_sample3d_fwd(const float* in, const float* grid, float* out,
+                         int N, int C, int D, int H, int W, int64_t nvox_per_n,
+                         int out_cstride, int out_coff, int align_corners, void* stream);
+int b2_grid_sample2d_fwd(const float* in, const float* grid, float* out,
+                         int N, int C, int H, int W, int64_t nvox_per_n,
+                         int out_cstride, int out_coff, int align_corners, void* stream);
+
+/* Deterministic backward w.r.t. the input: a CSR "input cell -> (output voxel,
+ * weight)" plan is built once per grid (the grid is fixed by the calibration, so
+ * it amortises over all PGD iterations) and the backward is a pure gather.
+ *   step 1  b2_grid_plan_count : counts[cell] (int32, zero-initialised by caller)
+ *   (caller: exclusive prefix sum counts -> row_ptr[ncell+1])
+ *   step 2  b2_grid_plan_fill  : entries[row_ptr[cell] ...] = (voxel, weight);
+ *           cursor = zeroed int32[ncell] scratch
+ *   step 3  b2_grid_plan_sort  : sort every row by voxel id (fixes summation order)
+ *   bwd     b2_grid_sample_bwd : gin[cell, :] = sum_e w_e * gout[voxel_e, :]
+ * ndim = 2 or 3; for ndim 2 pass D = 1.  cells = N*D*H*W; entries are int2
+ * {voxel (global, n-major), float bits of weight}. */
+int b2_grid_plan_count(const float* grid, int32_t* counts, int ndim, int N, int D, int H, int W,
+                       int64_t nvox_per_n, int align_corners, void* stream);
+int b2_grid_plan_fill(const float* grid, const int32_t* row_ptr, int32_t* cursor, void* entries,
+                      int ndim, int N, int D, int H, int W, int64_t nvox_per_n,
+                      int align_corners, void* stream);
+int b2_grid_plan_sort(const int32_t* row_ptr, void* entries, int64_t ncell, void* stream);
+int b2_grid_sample_bwd(const float* gout, const int32_t* row_ptr, const void* entries, float* gin,
+                       int64_t ncell, int C, int gout_cstride, int gout_coff, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * (3) 3-D convolutions of the hourglass stacks -- replaces cuDNN Conv3d /
+ *     ConvTranspose3d forward and data-gradient reached from
+ *     attack/DSGN/pgd_attack.py:308 / :336 (weights are frozen in an attack, so
+ *     no weight gradient is ever needed).
+ * Channels-last activations [N,D,H,W,C]; 3x3x3 kernel, padding 1; weights
+ * pre-packed as wp[27][Cout][Cin] (tap = (kd*3+kh)*3+kw).
+ *   mode 0 CONV  : out[o] = sum_k in[o*stride + k - 1] . wp[k]      (stride 1|2)
+ *   mode 1 DECONV: out[o] = sum_k [(o+1-k) even] in[(o+1-k)/2] . wp[k]  (stride 2,
+ *                  i.e. ConvTranspose3d(k3,s2,p1,output_padding=1) and the data
+ *                  gradient of a stride-2 conv)
+ * Data gradients are the same two modes with repacked weights (see ops.py).
+ * impl 0 = tcgen05/TMEM/TMA implicit GEMM (TF32 inputs, fp32 accumulate);
+ * impl 1 = fp32 SIMT implicit GEMM (verification mode; any Cin,Cout % 4 == 0).
+ * in dims are the INPUT spatial dims; out dims are derived:
+ *   CONV: (d+2-3)/stride+1 ; DECONV: 2*d.
+ * ------------------------------------------------------------------------- */
+int b2_conv3d(const float* in, const float* wp, float* out, int N, int Cin, int Cout,
+              int Di, int Hi, int Wi, int stride, int mode, int impl, void* stream);
+
+/* Cout == 1 head (classif1's last layer) and its data gradient: bandwidth-bound,
+ * SIMT.  w1 [27][Cin].  fwd: in [N,D,H,W,Cin] -> out [N,D,H,W];
+ * dgrad: gout [N,D,H,W] -> gin [N,D,H,W,Cin]. */
+int b2_conv3d_c1_fwd(const float* in, const float* w1, float* out, int N, int Cin,
+                     int D, int H, int W, void* stream);
+int b2_conv3d_c1_dgrad(const float* gout, const float* w1, float* gin, int N, int Cin,
+                       int D, int H, int W, void* stream);
+
+/* GroupNorm (+ residual add) (+ ReLU) on channels-last 3-D volumes, forward and
+ * data gradient -- the norm/activation that follows every conv3d (upstream
+ * convbn_3d).  y = act(GN(x)*gamma + beta (+ res)).
+ *   stats  [N,G,2] (mean, rstd) written by fwd, read by bwd
+ *   workspace: b2_groupnorm_workspace_bytes(N, C) bytes
+ * bwd: gx (and gres = masked gy when has_res; may alias gy).  y is the saved
+ * forward output (the ReLU mask). */
+int64_t b2_groupnorm_workspace_bytes(int N, int C);
+int b2_groupnorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,
+                     float* y, float* stats, int N, int C, int64_t S, int G, float eps,
+                     int relu, void* workspace, void* stream);
+int b2_groupnorm_bwd(const float* gy, const float* x, const float* y, const float* gamma,
+                     const float* stats, float* gx, float* gres, int N, int C, int64_t S, int G,
+                     int relu, void* workspace, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * RoIAlign forward / deterministic backward (Stereo R-CNN, config 5) -- replaces
+ * upstream model.roi_layers.ROIAlign constructed at
+ * attack/Stereo-RCNN/stereo_rcnn.py:44-45 and dispatched per FPN level at
+ * :110-141.  feat [1,C,H,W] (NCHW, as the upstream op), rois [R,5]
+ * (batch,x1,y1,x2,y2), out [R,C,P,P]; legacy (unaligned) sampling, adaptive
+ * sampling ratio (0).  Backward is gather-form over feature pixels.
+ * ------------------------------------------------------------------------- */
+int b2_roi_align_fwd(const float* feat, const float* rois, float* out, int R, int C, int H, int W,
+                     int P, float scale, void* stream);
+int b2_roi_align_bwd(const float* gout, const float* rois, float* gfeat, int R, int C, int H, int W,
+                     int P, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2ATTACK_H */
