@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- PGD attack iterations/s on KITTI-shaped stereo pairs (BASELINE.json metric).
+
+Workload at N=1: BASELINE.json configs[1] -- 10-iteration L-inf PGD (eps 0.03, alpha eps/4) on a
+batch of 8 synthetic 384x1248 stereo pairs, DSGN-shaped model with seeded random-init weights.
+One "step" = one PGD iteration (forward + backward + fused pixel update) applied to every pair
+of the rank's batch; value = pair-iterations / s over all ranks (weak scaling: 8 pairs per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+``--impl reference`` times the CPU oracle (oracle/, a restatement of the reference's loop: the
+reference itself cannot run, its model lives in the un-vendored DSGN package) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+EPS, ALPHA = 0.03, 0.03 / 4
+H, W = 384, 1248
+PAIRS_PER_GPU = 8
+METRIC, UNIT = "pgd_attack_pair_iterations_per_second", "pair-iterations/s"
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm_gbs=float(p["hbm_gbs"]), bf16_tflops=float(p["bf16_tflops"]),
+                    bf16_tflops_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def make_batch(cfg, pair_ids, pin=False):
+    from eval_driving_safety_b200 import synthetic
+    L, R, D = [], [], []
+    for i in pair_ids:
+        p = synthetic.make_pair(i, H, W)
+        L.append(p["imgL"]); R.append(p["imgR"]); D.append(p["disp_L"])
+    batch = {"imgL": torch.cat(L), "imgR": torch.cat(R), "disp": torch.cat(D)}
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    return batch
+
+
+def run_b200(args):
+    from eval_driving_safety_b200 import attack, dsgn, ops, parallel, synthetic
+    rank, world = parallel.init()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    torch.backends.cudnn.benchmark = True
+    cfg = dsgn.default_cfg()
+    model = dsgn.build_model(cfg, seed=1, device=dev)
+    calib = synthetic.make_calib(1)
+    pair_ids = [rank * PAIRS_PER_GPU + j for j in range(PAIRS_PER_GPU)]
+    host = make_batch(cfg, pair_ids, pin=True)
+    labels = {k: v.to(dev) for k, v in synthetic.make_labels(cfg, 1, 7).items()}
+    mean = torch.tensor(attack.IMAGENET_MEAN, device=dev).view(1, 3, 1, 1)
+    std = torch.tensor(attack.IMAGENET_STD, device=dev).view(1, 3, 1, 1)
+
+    def iteration(xL, xR, cleanL, cleanR, disp):
+        """one PGD iteration of every pair of the batch, in place on xL/xR; returns summed loss"""
+        total = torch.zeros((), device=dev)
+        for j in range(xL.shape[0]):
+            a = xL[j:j + 1].detach().requires_grad_(True)
+            b = xR[j:j + 1].detach().requires_grad_(True)
+            out = model(a, b, calib[0], calib[1], calib[2], calibs_Proj_R=calib[3])
+            loss = dsgn.attack_loss(cfg, out, disp[j:j + 1], labels)
+            gL, gR = torch.autograd.grad(loss, [a, b])
+            attack.pgd_step_pair(xL[j:j + 1], gL.contiguous(), cleanL[j:j + 1], xR[j:j + 1], gR.contiguous(),
+                                 cleanR[j:j + 1], ALPHA, EPS, inplace=True)
+            total += loss.detach()
+        return total
+
+    # ---- resident-input arm ("value") ------------------------------------------------------
+    xL, xR, disp = host["imgL"].to(dev), host["imgR"].to(dev), host["disp"].to(dev)
+    cleanL, cleanR = xL * std + mean, xR * std + mean
+    for _ in range(args.warmup):
+        iteration(xL, xR, cleanL, cleanR, disp)
+    torch.cuda.synchronize()
+    parallel.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = ops.LAUNCH_COUNT
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ops.profile() as prof:
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(args.steps):
+            iteration(xL, xR, cleanL, cleanR, disp)
+        e1.record()
+        torch.cuda.synchronize()
+    parallel.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.LAUNCH_COUNT - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    kern = prof.summary()
+
+    # ---- end-to-end arm ("e2e"): host buffers, H2D + D2H inside every timed step ------------
+    hL, hR = host["imgL"].clone().pin_memory(), host["imgR"].clone().pin_memory()
+    h_clean_L = (host["imgL"] * std.cpu() + mean.cpu()).pin_memory()
+    h_clean_R = (host["imgR"] * std.cpu() + mean.cpu()).pin_memory()
+    h_loss = torch.zeros((), pin_memory=True)
+
+    def e2e_step():
+        dL, dR = hL.to(dev, non_blocking=True), hR.to(dev, non_blocking=True)
+        cL, cR = h_clean_L.to(dev, non_blocking=True), h_clean_R.to(dev, non_blocking=True)
+        dd = host["disp"].to(dev, non_blocking=True)
+        loss = iteration(dL, dR, cL, cR, dd)
+        hL.copy_(dL, non_blocking=True); hR.copy_(dR, non_blocking=True); h_loss.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_warm = min(args.warmup, 3)
+    for _ in range(e2e_warm):
+        e2e_step()
+    parallel.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    h2d = sum(t.numel() * 4 for t in (hL, hR, h_clean_L, h_clean_R, host["disp"]))
+    d2h = (hL.numel() + hR.numel()) * 4 + 4
+
+    # ---- per-pair statistics: the only collective of the path -------------------
+    rows = [parallel.pair_stats(pair_ids[j], [torch.zeros((), device=dev), torch.zeros((), device=dev)],
+                                xL[j:j + 1] * std + mean, cleanL[j:j + 1]) for j in range(PAIRS_PER_GPU)]
+    stats = parallel.gather_stats(rows, PAIRS_PER_GPU * world)
+
+    # max over ranks, device-timed
+    t = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, e2e_ms = t.tolist()
+    if rank != 0:
+        return
+    units = PAIRS_PER_GPU * world * args.steps
+    peaks = measured_peaks()
+    conv = kern.get("conv3d_tcgen05", dict(calls=0, ms=0.0, work=0, per_s=0.0))
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0     # kind::tf32 issues at half the bf16 rate
+    kernels = {}
+    for name, k in sorted(kern.items()):
+        if name.startswith("conv3d_tcgen05") or name.startswith("conv3d_simt"):
+            kernels[name] = {"calls": k["calls"], "ms_total": round(k["ms"], 3), "tflops": round(k["per_s"] / 1e12, 2)}
+        else:
+            kernels[name] = {"calls": k["calls"], "ms_total": round(k["ms"], 3), "gbs": round(k["per_s"] / 1e9, 1),
+                             "frac_hbm": round(k["per_s"] / 1e9 / peaks["hbm_gbs"], 3)}
+    line = {
+        "metric": METRIC, "value": units / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1]: 10-iter L-inf PGD eps=0.03 alpha=eps/4, DSGN-shaped model, "
+                               "8 synthetic 384x1248 stereo pairs per GPU, random-init weights (seed 1)",
+                   "pairs_per_gpu": PAIRS_PER_GPU, "image": [H, W], "psv": [64, 48, 96, 312],
+                   "voxels": [96, 192, 20, 304], "parallelism": "dp%d (pairs sharded, no data-path collective)" % world,
+                   "l2_policy": "per-iteration working set (~10 GB of activations per pair) is far larger than the 126 MB L2"},
+        "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps, "warmup": e2e_warm},
+        "gpu_launches": launches,
+        "roofline": {"kernel": "conv3d_tcgen05_kernel (all 3x3x3 conv/deconv fwd+dgrad launches of the timed region)",
+                     "bound": "tensor", "achieved": conv["per_s"] / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
+                     "frac": conv["per_s"] / 1e12 / tf32_peak if tf32_peak else None, "traffic": None,
+                     "peak_source": "%s bf16_tflops_sustained/2 (TF32 rate; kernel timed inside a long step)" % peaks["source"],
+                     "frac_of_bf16_peak": conv["per_s"] / 1e12 / peaks["bf16_tflops_sustained"],
+                     "launches": conv["calls"], "avg_launch_ms": conv["ms"] / max(conv["calls"], 1),
+                     "share_of_step": conv["ms"] / ms if ms else None},
+        "kernels": kernels,
+        "clocks": clocks,
+        "stats_rows_gathered": int(stats.shape[0]),
+    }
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle on a bounded sample of the same workload
+# ---------------------------------------------------------------------------------------------
+SAMPLE_W = 160          # W-crop of the 384x1248 pair; voxel grid X cropped by the same ratio
+
+
+def sample_cfg():
+    from oracle import dsgn_ref
+    full = dsgn_ref.default_cfg()
+    x_half = 0.2 * 40 / 2            # 40 voxels in X
+    cfg = dsgn_ref.default_cfg(x_range=(-x_half, x_half), spp_pools=(32, 32, 16, 8))
+    vox = lambda c, w: (c.maxdisp // 4) * (H // 4) * (w // 4) + \
+        round((c.z_range[1] - c.z_range[0]) / c.voxel) * round((c.y_range[1] - c.y_range[0]) / c.voxel) * \
+        round((c.x_range[1] - c.x_range[0]) / c.voxel)
+    return cfg, vox(cfg, SAMPLE_W) / vox(full, W)
+
+
+def cpu_sample_iteration(model, cfg, pair, calib, labels):
+    from oracle import attack_ref, dsgn_ref
+    xL, xR = pair["imgL"].clone().requires_grad_(True), pair["imgR"].clone().requires_grad_(True)
+    out = model(xL, xR, *calib[:3], calibs_Proj_R=calib[3])
+    loss = dsgn_ref.attack_loss(cfg, out, pair["disp_L"], labels)
+    gL, gR = torch.autograd.grad(loss, [xL, xR])
+    cl, cr = attack_ref.denormalize(pair["imgL"]), attack_ref.denormalize(pair["imgR"])
+    pair["imgL"] = attack_ref.pgd_step_linf(xL.detach(), gL, cl, ALPHA, EPS)
+    pair["imgR"] = attack_ref.pgd_step_linf(xR.detach(), gR, cr, ALPHA, EPS)
+    return loss.item()
+
+
+def cpu_setup():
+    from eval_driving_safety_b200 import synthetic
+    from oracle import dsgn_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg, frac = sample_cfg()
+    model = dsgn_ref.build_model(cfg, seed=1)
+    for p in model.parameters():
+        p.requires_grad_(False)      # like our arm: no wgrad (the reference wastes it, pgd_attack.py:333)
+    full = synthetic.make_pair(0, H, W)
+    pair = {k: v[..., :SAMPLE_W].contiguous() for k, v in full.items()}
+    calib = synthetic.make_calib(1, cu=SAMPLE_W / 2)
+    labels = dsgn_ref.make_labels(cfg, 1, 7)
+    return model, cfg, pair, calib, labels, frac, cores
+
+
+def cpu_baseline_sample():
+    model, cfg, pair, calib, labels, frac, cores = cpu_setup()
+    t0 = time.perf_counter()
+    cpu_sample_iteration(model, cfg, pair, calib, labels)
+    dt = time.perf_counter() - t0
+    return {"value": frac / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "oracle (pure-PyTorch CPU restatement), 1 PGD iteration on a 384x%d W-crop of pair 0 with the "
+                      "voxel grid cropped alike = %.4f of a full pair's 3-D voxels; %.1f s measured, scaled by that "
+                      "fraction to full-size pair-iterations/s" % (SAMPLE_W, frac, dt)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    model, cfg, pair, calib, labels, frac, cores = cpu_setup()
+    for _ in range(args.warmup):
+        cpu_sample_iteration(model, cfg, pair, calib, labels)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_sample_iteration(model, cfg, pair, calib, labels)
+    dt = time.perf_counter() - t0
+    value = frac * args.steps / dt
+    sample = ("each step = 1 PGD iteration of the CPU oracle on a 384x%d W-crop of one pair (voxel grid cropped alike) "
+              "= %.4f of a full pair's 3-D voxels; value scaled by that fraction to full-size pair-iterations/s"
+              % (SAMPLE_W, frac))
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "BASELINE configs[1] PGD iteration, CPU oracle (the reference's model is in the "
+                               "un-vendored DSGN package and cannot run)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

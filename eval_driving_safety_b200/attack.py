@@ -22,6 +22,7 @@ import torch
 
 from . import _lib
 from ._lib import check, c_vp, f32_array
+from . import ops
 from .ops import _need_cuda, _p, _stream
 
 # attack/DSGN/pgd_attack.py:153-154
@@ -51,11 +52,11 @@ def _pgd_update_sets(xs, gs, cs, outs, alpha, eps, mean, std, lo, hi):
     lo_a, hi_a = f32_array(_chan(lo, c, 0.0)), f32_array(_chan(hi, c, 1.0))
     mean_a = f32_array(_chan(mean, c, 0.0)) if denorm else None
     std_a = f32_array(_chan(std, c, 1.0)) if denorm else None
-    arr = lambda ts: ctypes.cast(_lib.ptr_array(ts), ctypes.POINTER(ctypes.c_void_p))
     keep = [_lib.ptr_array(ts) for ts in (xs, gs, cs, outs)]
     ptrs = [ctypes.cast(k, ctypes.POINTER(ctypes.c_void_p)) for k in keep]
-    check(lib.b2_pgd_update(ptrs[0], ptrs[1], ptrs[2], ptrs[3], len(xs), n, c, h * w, float(alpha), float(eps),
-                            int(denorm), mean_a, std_a, lo_a, hi_a, _stream()), "pgd_update")
+    with ops._op("pgd_update", 1, 16 * len(xs) * n * c * h * w):      # 3 reads + 1 write per element
+        check(lib.b2_pgd_update(ptrs[0], ptrs[1], ptrs[2], ptrs[3], len(xs), n, c, h * w, float(alpha), float(eps),
+                                int(denorm), mean_a, std_a, lo_a, hi_a, _stream()), "pgd_update")
     return outs
 
 

@@ -1,8 +1,370 @@
-// placeholder, replaced by the tcgen05 implicit-GEMM kernel
+// Subsystem (3): 3x3x3 convolutions of the hourglass stacks as an implicit GEMM on
+// the 5th-gen tensor cores (impl = 0 of b2_conv3d).  Replaces cuDNN Conv3d /
+// ConvTranspose3d forward + data gradient reached from
+// attack/DSGN/pgd_attack.py:308 / :336.
+//
+//   GEMM view : M = output voxels (tile = 16 h x 8 w = 128 rows), N = Cout (<= 256, one
+//               tile), K = taps x Cin.  D[M,N] += A[M,K] * B[N,K]^T, TF32 in, fp32 acc.
+//   A operand : never materialised.  For every tap the rows of the A tile are the
+//               SAME 16x8 voxel box shifted by the tap offset, so one tiled TMA load
+//               of a {32 ch, 8 w, 16 h, 1 d, 1 n} box (128B swizzle, zero fill outside
+//               the volume = the conv padding) lands a K-major UMMA tile in smem.
+//               Stride-2 convs use a second tensor map with traversal strides 2;
+//               transposed convs are split into the 8 output-parity classes, each a
+//               unit-stride gather with 1..8 taps.
+//   B operand : packed weights wp[27][Cout][Cin] seen as a 2-D K-major matrix
+//               {Cin, 27*Cout}; TMA box {32, Cout}.
+//   Pipeline  : warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one thread),
+//               warps 2-5 = epilogue (tcgen05.ld -> st.global, one voxel row of
+//               Cout*4 contiguous bytes per thread).  smem ring of full/empty
+//               mbarriers; two TMEM accumulators so the epilogue of tile i overlaps
+//               the MMAs of tile i+1.  Persistent: one CTA per SM, static tile striding.
+#include <cuda.h>
 #include "common.cuh"
+
 namespace b2 {
-int conv3d_tcgen05_launch(const float*, const float*, float*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t) {
-    set_error("conv3d(tcgen05): not built yet");
-    return B2_ERR_UNSUPPORTED;
+
+constexpr int kTcThreads = 192;
+constexpr int kTileH = 16, kTileW = 8;          // 128 voxel rows per tile
+constexpr int kKChunk = 32;                     // floats per K block = one 128B swizzle row
+constexpr int kABytes = 128 * 128;              // A stage: 128 rows x 128 B
+constexpr int kMaxStages = 8;
+
+struct TcParams {
+    int N, Cin, Cout;
+    int Dt, Ht, Wt;            // extents of the tile grid space (conv: output dims; deconv: input dims)
+    int Do, Ho, Wo;            // output dims
+    int mode;                  // 0 conv s1, 1 conv s2, 2 deconv s2
+    int tiles_w, tiles_h;
+    int kchunks;               // Cin / 32
+    int stages;
+    int stage_bytes;           // kABytes + Cout*128
+    int tmem_cols;             // power of two >= 2*Cout
+    long long total_tiles;
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1,
+                                            int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128B-swizzled smem matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start>>4 [0,14) | LBO>>4 [16,30) (=1, unused for swizzled K-major) | SBO>>4 [32,46) (1024 B between
+// 8-row groups) | version=1 [46,48) | layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// cute::UMMA::InstrDescriptor: c_format F32=1 [4,6) | a,b format TF32=2 [7,10),[10,13) | K-major both |
+// n_dim = N>>3 [17,23) | m_dim = M>>4 [24,29)
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- tile / step decode
+struct TileCoord { int cls, n, d, h0, w0; };
+
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, long long t) {
+    TileCoord c;
+    c.w0 = (int)(t % p.tiles_w) * kTileW; t /= p.tiles_w;
+    c.h0 = (int)(t % p.tiles_h) * kTileH; t /= p.tiles_h;
+    c.d = (int)(t % p.Dt); t /= p.Dt;
+    c.n = (int)(t % p.N); t /= p.N;
+    c.cls = (int)t;
+    return c;
+}
+__device__ __forceinline__ int tile_taps(const TcParams& p, int cls) {
+    if (p.mode != 2) return 27;
+    return (1 + (cls & 1)) * (1 + ((cls >> 1) & 1)) * (1 + ((cls >> 2) & 1));
+}
+// deconv: parity p along one axis, j-th tap of that axis -> (k, input shift)
+__device__ __forceinline__ void deconv_axis(int par, int j, int& k, int& shift) {
+    if (par == 0) { k = 1; shift = 0; }
+    else if (j == 0) { k = 0; shift = 1; }
+    else { k = 2; shift = 0; }
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                      float* __restrict__ out, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;     // 128B swizzle needs 1024 B alignment
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + 2 + a); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {   // whole warp: allocate TMEM (2 accumulators of Cout fp32 columns)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one thread) =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t tx = (uint32_t)p.stage_bytes;
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                TileCoord tc = decode_tile(p, t);
+                const int ntaps = tile_taps(p, tc.cls);
+                const int pw = tc.cls & 1, ph = (tc.cls >> 1) & 1, pd = (tc.cls >> 2) & 1;
+                for (int tap_i = 0; tap_i < ntaps; ++tap_i) {
+                    int aw, ah, ad, tap;
+                    if (p.mode == 0) {
+                        int kd = tap_i / 9, kh = (tap_i / 3) % 3, kw = tap_i % 3;
+                        aw = tc.w0 + kw - 1; ah = tc.h0 + kh - 1; ad = tc.d + kd - 1; tap = tap_i;
+                    } else if (p.mode == 1) {
+                        int kd = tap_i / 9, kh = (tap_i / 3) % 3, kw = tap_i % 3;
+                        aw = 2 * tc.w0 + kw - 1; ah = 2 * tc.h0 + kh - 1; ad = 2 * tc.d + kd - 1; tap = tap_i;
+                    } else {
+                        int nw = 1 + pw, nh = 1 + ph;
+                        int jw = tap_i % nw, jh = (tap_i / nw) % nh, jd = tap_i / (nw * nh);
+                        int kw, kh, kd, sw, sh, sd;
+                        deconv_axis(pw, jw, kw, sw); deconv_axis(ph, jh, kh, sh); deconv_axis(pd, jd, kd, sd);
+                        aw = tc.w0 + sw; ah = tc.h0 + sh; ad = tc.d + sd; tap = (kd * 3 + kh) * 3 + kw;
+                    }
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        mbar_expect_tx(full_bar(stage), tx);
+                        uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                        tma_load_5d(sa, &map_a, full_bar(stage), kc * kKChunk, aw, ah, ad, tc.n);
+                        tma_load_2d(sa + kABytes, &map_b, full_bar(stage), kc * kKChunk, tap * p.Cout);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(128, p.Cout);
+            int stage = 0; uint32_t phase = 0;
+            long long it = 0;
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+                const int acc = (int)(it & 1);
+                const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1);        // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.Cout);
+                TileCoord tc = decode_tile(p, t);
+                const int nsteps = tile_taps(p, tc.cls) * p.kchunks;
+                for (int s = 0; s < nsteps; ++s) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                    uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kKChunk / 8; ++k) {
+                        // +32 B per K step inside the 128B swizzle row: +2 in the (addr >> 4) field
+                        umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (s | k) != 0);
+                    }
+                    umma_commit(empty_bar(stage));                // frees the smem slot when the MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));                      // accumulator ready for the epilogue
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (4 warps, one voxel row per thread) =====================
+        const int lane_grp = warp & 3;                            // TMEM lanes [32*lane_grp, +32)
+        const int m = lane_grp * 32 + lane;
+        const int hl = m / kTileW, wl = m % kTileW;
+        long long it = 0;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const int acc = (int)(it & 1);
+            const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+            TileCoord tc = decode_tile(p, t);
+            const int h = tc.h0 + hl, w = tc.w0 + wl;
+            const bool ok = h < p.Ht && w < p.Wt;
+            long long vox;
+            if (p.mode == 2) {
+                int od = 2 * tc.d + ((tc.cls >> 2) & 1), oh = 2 * h + ((tc.cls >> 1) & 1), ow = 2 * w + (tc.cls & 1);
+                vox = (((long long)tc.n * p.Do + od) * p.Ho + oh) * p.Wo + ow;
+            } else {
+                vox = (((long long)tc.n * p.Do + tc.d) * p.Ho + h) * p.Wo + w;
+            }
+            float* orow = out + vox * p.Cout;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.Cout);
+            for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c0, r);
+                tmem_ld_wait();
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                               __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                        *reinterpret_cast<float4*>(orow + c0 + 4 * j) = v;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)ptr;
+    }
+    return fn;
+}
+
+int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
+                          int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st) {
+    if (Cin % 32 != 0 || Cout % 32 != 0 || Cout > 256 || Cout < 32) {
+        set_error("conv3d(tcgen05): needs Cin %% 32 == 0 and Cout in {32,64,...,256} (got %d -> %d); "
+                  "use impl=1 for other widths", Cin, Cout);
+        return B2_ERR_UNSUPPORTED;
+    }
+    EncodeTiledFn encode = get_encode();
+    if (!encode) { set_error("conv3d(tcgen05): cuTensorMapEncodeTiled not available from the driver"); return B2_ERR_DRIVER; }
+
+    TcParams p{};
+    p.N = N; p.Cin = Cin; p.Cout = Cout; p.Do = Do; p.Ho = Ho; p.Wo = Wo;
+    p.mode = (mode == 1) ? 2 : (stride == 2 ? 1 : 0);
+    if (p.mode == 2) { p.Dt = Di; p.Ht = Hi; p.Wt = Wi; } else { p.Dt = Do; p.Ht = Ho; p.Wt = Wo; }
+    p.tiles_w = (p.Wt + kTileW - 1) / kTileW;
+    p.tiles_h = (p.Ht + kTileH - 1) / kTileH;
+    p.kchunks = Cin / kKChunk;
+    p.stage_bytes = kABytes + Cout * 128;
+    p.stages = (200 * 1024) / p.stage_bytes;
+    if (p.stages > kMaxStages) p.stages = kMaxStages;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 2 * Cout) p.tmem_cols *= 2;
+    p.total_tiles = (long long)(p.mode == 2 ? 8 : 1) * N * p.Dt * p.tiles_h * p.tiles_w;
+
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)N};
+        cuuint64_t gstr[4] = {(cuuint64_t)Cin * 4, (cuuint64_t)Wi * Cin * 4, (cuuint64_t)Hi * Wi * Cin * 4,
+                              (cuuint64_t)Di * Hi * Wi * Cin * 4};
+        const cuuint32_t s = (p.mode == 1) ? 2 : 1;
+        // traversal box; with element stride s the box lands ceil(box/s) elements per dim in smem
+        cuuint32_t box[5] = {(cuuint32_t)kKChunk, (cuuint32_t)kTileW * s, (cuuint32_t)kTileH * s, s, 1};
+        cuuint32_t estr[5] = {1, s, s, s, 1};
+        CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in, gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3d(tcgen05): cuTensorMapEncodeTiled(A) failed: %d", (int)r); return B2_ERR_DRIVER; }
+    }
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * Cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)Cin * 4};
+        cuuint32_t box[2] = {(cuuint32_t)kKChunk, (cuuint32_t)Cout};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wp, gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3d(tcgen05): cuTensorMapEncodeTiled(B) failed: %d", (int)r); return B2_ERR_DRIVER; }
+    }
+
+    const int smem = p.stages * p.stage_bytes + 1024;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(conv3d_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_error("conv3d(tcgen05): cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return (int)e; }
+        attr_smem = smem;
+    }
+    int grid = (int)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
+    conv3d_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p);
+    return check_launch("conv3d(tcgen05)");
+}
+
+}  // namespace b2

@@ -13,6 +13,7 @@ so they remain drop-in arguments for any stock torch op.
 """
 import ctypes
 import os
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -35,6 +36,58 @@ def set_conv_impl(impl):
 
 def _stream():
     return c_vp(torch.cuda.current_stream().cuda_stream)
+
+
+# -- launch accounting / live kernel timing (bench.py) -------------------------
+LAUNCH_COUNT = 0          # kernels of libb2attack.so launched so far
+_PROFILE = None           # name -> [(start_event, end_event, work)] while profiling
+
+
+class _op:
+    """Counts the kernels an entry point launches and, while ``profile()`` is active,
+    brackets it with CUDA events on the launching (= current torch) stream.  ``work`` is
+    the ALGORITHMIC byte (or flop) count of the call, see DESIGN.md."""
+
+    def __init__(self, name, nlaunch, work=0):
+        self.name, self.nlaunch, self.work = name, nlaunch, work
+
+    def __enter__(self):
+        if _PROFILE is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        global LAUNCH_COUNT
+        LAUNCH_COUNT += self.nlaunch
+        if _PROFILE is not None and exc[0] is None:
+            self.e1.record()
+            _PROFILE.setdefault(self.name, []).append((self.e0, self.e1, self.work))
+        return False
+
+
+class profile:
+    """with ops.profile() as prof: ... ; prof.summary() -> {name: dict(calls, ms, work, per_s)}"""
+
+    def __enter__(self):
+        global _PROFILE
+        _PROFILE = self.records = {}
+        return self
+
+    def __exit__(self, *exc):
+        global _PROFILE
+        _PROFILE = None
+        return False
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, recs in self.records.items():
+            ms = sum(e0.elapsed_time(e1) for e0, e1, _ in recs)
+            work = sum(w for _, _, w in recs)
+            out[name] = dict(calls=len(recs), ms=ms, work=work, per_s=(work / (ms * 1e-3) if ms > 0 else 0.0))
+        return out
 
 
 def _p(t):
@@ -92,8 +145,9 @@ class BuildCostVolumeFn(Function):
         else:
             l, r = left.contiguous(), right.contiguous()
             cost = torch.empty((n, 2 * c, d, h, w), device=left.device, dtype=torch.float32)
-        check(lib.b2_cost_volume_fwd(_p(l), _p(r), _p(shifts), _p(cost), n, c, d, h, w,
-                                     1 if channels_last else 0, _stream()), "cost_volume_fwd")
+        with _op("cost_volume_fwd", 1, 4 * (2 * n * c * h * w + cost.numel())):
+            check(lib.b2_cost_volume_fwd(_p(l), _p(r), _p(shifts), _p(cost), n, c, d, h, w,
+                                         1 if channels_last else 0, _stream()), "cost_volume_fwd")
         ctx.save_for_backward(shifts)
         ctx.dims = (n, c, d, h, w, channels_last)
         return cost
@@ -111,8 +165,9 @@ class BuildCostVolumeFn(Function):
             g = gcost.contiguous()
             gl = torch.empty((n, c, h, w), device=g.device, dtype=torch.float32)
             gr = torch.empty_like(gl)
-        check(lib.b2_cost_volume_bwd(_p(g), _p(shifts), _p(gl), _p(gr), n, c, d, h, w,
-                                     1 if channels_last else 0, _stream()), "cost_volume_bwd")
+        with _op("cost_volume_bwd", 1, 4 * (2 * n * c * h * w + g.numel())):
+            check(lib.b2_cost_volume_bwd(_p(g), _p(shifts), _p(gl), _p(gr), n, c, d, h, w,
+                                         1 if channels_last else 0, _stream()), "cost_volume_bwd")
         return gl, gr, None, None
 
 
@@ -156,14 +211,18 @@ class GridPlan:
 def _gs_fwd(lib, inp, grid, out, out_c, coff, align):
     n, c = inp.shape[:2]
     nvox_per_n = grid[0].numel() // grid.shape[-1]
+    # algorithmic bytes: read input once + grid, write the sampled channels
+    work = 4 * (inp.numel() + grid.numel() + n * nvox_per_n * c)
     if grid.shape[-1] == 3:
         d, h, w = inp.shape[2:]
-        check(lib.b2_grid_sample3d_fwd(_p(inp), _p(grid), _p(out), n, c, d, h, w, nvox_per_n, out_c, coff,
-                                       int(align), _stream()), "grid_sample3d_fwd")
+        with _op("grid_sample3d_fwd", 1, work):
+            check(lib.b2_grid_sample3d_fwd(_p(inp), _p(grid), _p(out), n, c, d, h, w, nvox_per_n, out_c, coff,
+                                           int(align), _stream()), "grid_sample3d_fwd")
     else:
         h, w = inp.shape[2:]
-        check(lib.b2_grid_sample2d_fwd(_p(inp), _p(grid), _p(out), n, c, h, w, nvox_per_n, out_c, coff,
-                                       int(align), _stream()), "grid_sample2d_fwd")
+        with _op("grid_sample2d_fwd", 1, work):
+            check(lib.b2_grid_sample2d_fwd(_p(inp), _p(grid), _p(out), n, c, h, w, nvox_per_n, out_c, coff,
+                                           int(align), _stream()), "grid_sample2d_fwd")
 
 
 class GridSampleFn(Function):
@@ -195,8 +254,9 @@ class GridSampleFn(Function):
         g = cl3(gout) if nd == 3 else cl2(gout)
         c = ctx.in_shape[1]
         gin = empty_cl3(*ctx.in_shape, g.device) if nd == 3 else empty_cl2(*ctx.in_shape, g.device)
-        check(lib.b2_grid_sample_bwd(_p(g), _p(plan.row_ptr), _p(plan.entries), _p(gin), plan.ncell, c, c, 0,
-                                     _stream()), "grid_sample_bwd")
+        with _op("grid_sample%dd_bwd" % nd, 1, 4 * (g.numel() + gin.numel()) + 8 * plan.nnz + 4 * plan.ncell):
+            check(lib.b2_grid_sample_bwd(_p(g), _p(plan.row_ptr), _p(plan.entries), _p(gin), plan.ncell, c, c, 0,
+                                         _stream()), "grid_sample_bwd")
         return gin, None, None, None
 
 
@@ -234,10 +294,13 @@ class LiftFn(Function):
         (s3, s2), (p3, p2) = ctx.shapes, ctx.plans
         ctot = s3[1] + s2[1]
         g3, g2 = empty_cl3(*s3, g.device), empty_cl2(*s2, g.device)
-        check(lib.b2_grid_sample_bwd(_p(g), _p(p3.row_ptr), _p(p3.entries), _p(g3), p3.ncell, s3[1], ctot, 0,
-                                     _stream()), "grid_sample_bwd(3d)")
-        check(lib.b2_grid_sample_bwd(_p(g), _p(p2.row_ptr), _p(p2.entries), _p(g2), p2.ncell, s2[1], ctot, s3[1],
-                                     _stream()), "grid_sample_bwd(2d)")
+        nv = g.numel() // ctot
+        with _op("grid_sample3d_bwd", 1, 4 * (nv * s3[1] + g3.numel()) + 8 * p3.nnz + 4 * p3.ncell):
+            check(lib.b2_grid_sample_bwd(_p(g), _p(p3.row_ptr), _p(p3.entries), _p(g3), p3.ncell, s3[1], ctot, 0,
+                                         _stream()), "grid_sample_bwd(3d)")
+        with _op("grid_sample2d_bwd", 1, 4 * (nv * s2[1] + g2.numel()) + 8 * p2.nnz + 4 * p2.ncell):
+            check(lib.b2_grid_sample_bwd(_p(g), _p(p2.row_ptr), _p(p2.entries), _p(g2), p2.ncell, s2[1], ctot, s3[1],
+                                         _stream()), "grid_sample_bwd(2d)")
         return g3, g2, None, None, None, None
 
 
@@ -254,10 +317,10 @@ _PACK_CACHE = {}
 def _packed(weight, kind):
     """Packed weights wp[27][Cout][Cin] for the gather modes of b2_conv3d.
     kind: conv_fwd, conv_dgrad_s1, conv_dgrad_s2, deconv_fwd, deconv_dgrad."""
-    key = (weight.data_ptr(), weight._version, kind, tuple(weight.shape))
+    key = (id(weight), kind)
     hit = _PACK_CACHE.get(key)
-    if hit is not None:
-        return hit
+    if hit is not None and hit[0]() is weight and hit[1] == (weight._version, weight.data_ptr()):
+        return hit[2]
     w = weight.detach()
     if kind == "conv_fwd":            # w [Co,Ci,k]: wp[k][co][ci]
         wp = w.permute(2, 3, 4, 0, 1)
@@ -272,10 +335,16 @@ def _packed(weight, kind):
     else:
         raise ValueError(kind)
     wp = wp.reshape(27, wp.shape[3], wp.shape[4]).contiguous()
-    if len(_PACK_CACHE) > 512:
-        _PACK_CACHE.clear()
-    _PACK_CACHE[key] = wp
+    _cache_put(key, weight, wp)
     return wp
+
+
+def _cache_put(key, weight, packed):
+    # entries are validated by identity (weakref) + version + storage address, so a freed
+    # tensor whose id/address is reused can never produce a stale hit
+    if len(_PACK_CACHE) > 1024:
+        _PACK_CACHE.clear()
+    _PACK_CACHE[key] = (weakref.ref(weight), (weight._version, weight.data_ptr()), packed)
 
 
 def _conv_call(x, wp, stride, mode, impl):
@@ -288,8 +357,12 @@ def _conv_call(x, wp, stride, mode, impl):
     else:
         do, ho, wo = 2 * di, 2 * hi, 2 * wi
     out = empty_cl3(n, cout, do, ho, wo, x.device)
-    check(lib.b2_conv3d(_p(x), _p(wp), _p(out), n, cin, cout, di, hi, wi, stride, mode, impl, _stream()),
-          "conv3d(mode=%d,stride=%d,impl=%d)" % (mode, stride, impl))
+    # algorithmic flops: 2*Cin*Cout*27 per output voxel for CONV; a transposed conv touches
+    # 27/8 taps per output voxel on average (= 2*Cin*Cout*27 per INPUT voxel)
+    vox = n * do * ho * wo if mode == 0 else n * di * hi * wi
+    with _op("conv3d_tcgen05" if impl == 0 else "conv3d_simt", 1, 2 * cin * cout * 27 * vox):
+        check(lib.b2_conv3d(_p(x), _p(wp), _p(out), n, cin, cout, di, hi, wi, stride, mode, impl, _stream()),
+              "conv3d(mode=%d,stride=%d,impl=%d)" % (mode, stride, impl))
     return out
 
 
@@ -345,13 +418,16 @@ class Conv3dC1Fn(Function):
         lib = _lib.load()
         x = cl3(x)
         n, cin, d, h, w = x.shape
-        key = (weight.data_ptr(), weight._version, "c1")
-        w1 = _PACK_CACHE.get(key)
-        if w1 is None:
+        key = (id(weight), "c1")
+        hit = _PACK_CACHE.get(key)
+        if hit is not None and hit[0]() is weight and hit[1] == (weight._version, weight.data_ptr()):
+            w1 = hit[2]
+        else:
             w1 = weight.detach()[0].permute(1, 2, 3, 0).reshape(27, cin).contiguous()
-            _PACK_CACHE[key] = w1
+            _cache_put(key, weight, w1)
         out = torch.empty((n, 1, d, h, w), device=x.device, dtype=torch.float32)
-        check(lib.b2_conv3d_c1_fwd(_p(x), _p(w1), _p(out), n, cin, d, h, w, _stream()), "conv3d_c1_fwd")
+        with _op("conv3d_c1_fwd", 1, 4 * (x.numel() + out.numel())):
+            check(lib.b2_conv3d_c1_fwd(_p(x), _p(w1), _p(out), n, cin, d, h, w, _stream()), "conv3d_c1_fwd")
         ctx.w1, ctx.dims = w1, (n, cin, d, h, w)
         return out
 
@@ -362,7 +438,8 @@ class Conv3dC1Fn(Function):
         n, cin, d, h, w = ctx.dims
         g = gout.contiguous()
         gin = empty_cl3(n, cin, d, h, w, g.device)
-        check(lib.b2_conv3d_c1_dgrad(_p(g), _p(ctx.w1), _p(gin), n, cin, d, h, w, _stream()), "conv3d_c1_dgrad")
+        with _op("conv3d_c1_dgrad", 1, 4 * (g.numel() + gin.numel())):
+            check(lib.b2_conv3d_c1_dgrad(_p(g), _p(ctx.w1), _p(gin), n, cin, d, h, w, _stream()), "conv3d_c1_dgrad")
         return gin, None
 
 
@@ -397,8 +474,9 @@ class GroupNormActFn(Function):
         stats = torch.empty((n, groups, 2), device=x.device, dtype=torch.float32)
         ws = _workspace(lib.b2_groupnorm_workspace_bytes(n, c), x.device)
         gamma, beta = gamma.detach().contiguous(), beta.detach().contiguous()
-        check(lib.b2_groupnorm_fwd(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(stats), n, c, s, groups,
-                                   float(eps), int(relu), _p(ws), _stream()), "groupnorm_fwd")
+        with _op("groupnorm_fwd", 3, 4 * x.numel() * (3 + (res is not None))):
+            check(lib.b2_groupnorm_fwd(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(stats), n, c, s, groups,
+                                       float(eps), int(relu), _p(ws), _stream()), "groupnorm_fwd")
         ctx.save_for_backward(x, y, gamma, stats)
         ctx.cfg = (groups, relu, res is not None)
         return y
@@ -415,8 +493,9 @@ class GroupNormActFn(Function):
         gx = empty_cl3(*x.shape, x.device)
         gres = empty_cl3(*x.shape, x.device) if (has_res and relu) else None
         ws = _workspace(lib.b2_groupnorm_workspace_bytes(n, c), x.device)
-        check(lib.b2_groupnorm_bwd(_p(gy), _p(x), _p(y), _p(gamma), _p(stats), _p(gx), _p(gres), n, c, s, groups,
-                                   int(relu), _p(ws), _stream()), "groupnorm_bwd")
+        with _op("groupnorm_bwd", 3, 4 * x.numel() * (5 + 2 * int(relu) + (gres is not None))):
+            check(lib.b2_groupnorm_bwd(_p(gy), _p(x), _p(y), _p(gamma), _p(stats), _p(gx), _p(gres), n, c, s, groups,
+                                       int(relu), _p(ws), _stream()), "groupnorm_bwd")
         if has_res and not relu:
             gres = gy
         return gx, gres, None, None, None, None, None
@@ -439,8 +518,9 @@ class RoIAlignFn(Function):
         feat, rois = feat.contiguous(), rois.contiguous()
         r, (_, c, h, w) = rois.shape[0], feat.shape
         out = torch.empty((r, c, pooled, pooled), device=feat.device, dtype=torch.float32)
-        check(lib.b2_roi_align_fwd(_p(feat), _p(rois), _p(out), r, c, h, w, pooled, float(scale), _stream()),
-              "roi_align_fwd")
+        with _op("roi_align_fwd", 1, 4 * (feat.numel() + out.numel())):
+            check(lib.b2_roi_align_fwd(_p(feat), _p(rois), _p(out), r, c, h, w, pooled, float(scale), _stream()),
+                  "roi_align_fwd")
         ctx.save_for_backward(rois)
         ctx.cfg = (r, c, h, w, pooled, float(scale))
         return out
@@ -453,8 +533,9 @@ class RoIAlignFn(Function):
         r, c, h, w, pooled, scale = ctx.cfg
         g = gout.contiguous()
         gfeat = torch.empty((1, c, h, w), device=g.device, dtype=torch.float32)
-        check(lib.b2_roi_align_bwd(_p(g), _p(rois), _p(gfeat), r, c, h, w, pooled, scale, _stream()),
-              "roi_align_bwd")
+        with _op("roi_align_bwd", 1, 4 * (g.numel() + gfeat.numel())):
+            check(lib.b2_roi_align_bwd(_p(g), _p(rois), _p(gfeat), r, c, h, w, pooled, scale, _stream()),
+                  "roi_align_bwd")
         return gfeat, None, None, None
 
 

@@ -177,7 +177,7 @@ def build_cost_volume(left, right, shifts):
     [N,D] (feature px, >= 0) -> [N,2C,D,H,W]."""
     n, c, h, w = left.shape
     d = shifts.shape[1]
-    cols = torch.arange(w, dtype=torch.float32, device=left.device)
+    cols = torch.arange(w, dtype=left.dtype, device=left.device)
     planes = []
     for i in range(d):
         s = shifts[:, i]
@@ -251,7 +251,7 @@ class StereoNetRef(nn.Module):
 
     # -- stages (split so tests can compare intermediates) ------------------
     def psv_stage(self, featL, featR, fu, baseline):
-        shifts = plane_shifts(self.cfg, fu, baseline)
+        shifts = plane_shifts(self.cfg, fu, baseline).to(featL.dtype)
         cost = build_cost_volume(featL, featR, shifts)
         cost0 = self.dres0(cost)
         cost0 = self.dres1(cost0) + cost0
@@ -264,11 +264,11 @@ class StereoNetRef(nn.Module):
         up = F.interpolate(cost1, [cfg.maxdisp, img_hw[0], img_hw[1]], mode='trilinear',
                            align_corners=False)
         prob = F.softmax(up.squeeze(1), 1)
-        z = full_depths(cfg).view(1, -1, 1, 1)
+        z = full_depths(cfg).view(1, -1, 1, 1).to(cost1.dtype)
         return (prob * z).sum(1)
 
     def lift(self, out, rpn_feat, proj):
-        grid = lifting_grid(self.cfg, proj, out.shape[-2:])
+        grid = lifting_grid(self.cfg, proj, out.shape[-2:]).to(out.dtype)
         vox = F.grid_sample(out, grid, mode='bilinear', padding_mode='zeros', align_corners=True)
         n, zz, yy, xx, _ = grid.shape
         g2 = grid[..., :2].reshape(n, zz * yy, xx, 2)

@@ -1,0 +1,164 @@
+"""GPU end-to-end parity: the B200 StereoNet path (sm_100a kernels) against the CPU
+oracle on the same seeded synthetic pair and weights -- cost volume, outputs, input
+gradient, K-iteration PGD perturbation and its sign pattern (north_star)."""
+import pytest
+import torch
+
+from helpers import max_err, rel_err
+from oracle import attack_ref as A
+from oracle import dsgn_ref as R
+
+pytestmark = pytest.mark.gpu
+
+H, W = 32, 64
+
+
+def _setup(affine):
+    from eval_driving_safety_b200 import dsgn, synthetic
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    cfg_r, cfg_p = R.tiny_cfg(), dsgn.tiny_cfg()
+    ref = R.build_model(cfg_r, seed=1)
+    if affine:
+        # non-trivial norm parameters so that the affine path of our GroupNorm kernels is exercised
+        g = torch.Generator().manual_seed(5)
+        for m in ref.modules():
+            if isinstance(m, torch.nn.GroupNorm):
+                m.weight.data = 0.5 + torch.rand(m.weight.shape, generator=g)
+                m.bias.data = 0.1 * torch.randn(m.bias.shape, generator=g)
+    model = dsgn.StereoNet(cfg_p)
+    model.load_state_dict(ref.state_dict())
+    model = model.freeze().cuda()
+    pair = synthetic.make_pair(0, H, W, max_depth=8.4)
+    calib = synthetic.make_calib(1, scale=H / 384, cu=W / 2, cv=H / 2)
+    labels = R.make_labels(cfg_r, 1, 7)
+    return dict(cfg_r=cfg_r, cfg_p=cfg_p, ref=ref, model=model, pair=pair, calib=calib, labels=labels)
+
+
+@pytest.fixture(scope="module")
+def setup_affine(built_lib):
+    """Stage-level tests of OUR kernels: perturbed GroupNorm affine parameters."""
+    return _setup(True)
+
+
+@pytest.fixture(scope="module")
+def setup(built_lib):
+    """Whole-model tests: seeded default init.  (With perturbed 2-D GroupNorm affine
+    parameters the stock torch CUDA 2-D extractor alone differs from its own CPU
+    result by ~1e-2 in the input gradient on this tiny config -- measured, fp64
+    arbiter, tools/diag1.py -- which would mask what these tests are about.)"""
+    return _setup(False)
+
+
+def _ref_grads(s, xL, xR):
+    xL, xR = xL.clone().requires_grad_(True), xR.clone().requires_grad_(True)
+    out = s["ref"](xL, xR, *s["calib"][:3], calibs_Proj_R=s["calib"][3])
+    loss = R.attack_loss(s["cfg_r"], out, s["pair"]["disp_L"], s["labels"])
+    gL, gR = torch.autograd.grad(loss, [xL, xR])
+    return out, loss, gL, gR
+
+
+def _gpu_grads(s, xL, xR, impl):
+    from eval_driving_safety_b200 import dsgn, ops
+    ops.set_conv_impl(impl)
+    xL, xR = xL.cuda().requires_grad_(True), xR.cuda().requires_grad_(True)
+    out = s["model"](xL, xR, *s["calib"][:3], calibs_Proj_R=s["calib"][3])
+    labels = {k: v.cuda() for k, v in s["labels"].items()}
+    loss = dsgn.attack_loss(s["cfg_p"], out, s["pair"]["disp_L"].cuda(), labels)
+    gL, gR = torch.autograd.grad(loss, [xL, xR])
+    return out, loss, gL, gR
+
+
+def test_stage_parity_fp32_path(setup_affine):
+    """Verification mode (fp32 SIMT convs): every stage against the oracle."""
+    from eval_driving_safety_b200 import ops
+    s = setup_affine
+    ops.set_conv_impl(1)
+    xL, xR = s["pair"]["imgL"], s["pair"]["imgR"]
+    with torch.no_grad():
+        fL, rL = s["ref"].feature_extraction(xL)
+        fR, _ = s["ref"].feature_extraction(xR)
+        cost_r, out_r, cost1_r = s["ref"].psv_stage(fL, fR, s["calib"][0], s["calib"][1])
+        gL_, rLg = s["model"].feature_extraction(xL.cuda())
+        gR_, _ = s["model"].feature_extraction(xR.cuda())
+        assert rel_err(gL_.cpu(), fL) < 1e-4
+        # same features into both cost volumes -> bit-exact cost volume
+        cost_g, out_g, cost1_g = s["model"].psv_stage(fL.cuda(), fR.cuda(), s["calib"][0], s["calib"][1])
+        assert torch.equal(cost_g.cpu(), cost_r)
+        assert rel_err(out_g.cpu(), out_r) < 1e-4 and rel_err(cost1_g.cpu(), cost1_r) < 1e-4
+        vox_r = s["ref"].lift(out_r, rL, s["calib"][2])
+        vox_g = s["model"].lift(out_r.cuda(), rL.cuda(), s["calib"][2])
+        assert max_err(vox_g.cpu(), vox_r) < 1e-5
+        heads_r = s["ref"].bev_stage(vox_r)
+        heads_g = s["model"].bev_stage(vox_r.cuda())
+        for a, b in zip(heads_g, heads_r):
+            assert rel_err(a.cpu(), b) < 1e-4
+
+
+@pytest.mark.parametrize("impl,tol_out,tol_grad,min_agree", [(1, 1e-4, 5e-3, 0.999), (0, 5e-2, 0.15, 0.99)])
+def test_outputs_and_input_gradient(setup, impl, tol_out, tol_grad, min_agree):
+    """impl 1 = fp32 verification path (measured 1e-5 gradient error); impl 0 = tcgen05 TF32 path.
+    Stated TF32 tolerance: each conv carries ~8e-4 relative error (10-bit mantissa, measured against
+    the fp32 kernel); through the ~20 convs + GroupNorms of this tiny volume that is 6e-2 on the
+    input gradient (measured) -- bound 0.15; sign pattern must agree on >= 99 % of the pixels whose
+    |gradient| exceeds 1 % of the maximum."""
+    s = setup
+    out_r, loss_r, gL_r, gR_r = _ref_grads(s, s["pair"]["imgL"], s["pair"]["imgR"])
+    out_g, loss_g, gL_g, gR_g = _gpu_grads(s, s["pair"]["imgL"], s["pair"]["imgR"], impl)
+    for k in ("depth_preds", "bbox_cls", "bbox_reg", "bbox_centerness"):
+        assert out_g[k].shape == out_r[k].shape
+        assert rel_err(out_g[k].cpu(), out_r[k]) < tol_out, k
+    assert abs(loss_g.item() - loss_r.item()) < tol_out * abs(loss_r.item()) * 10
+    assert rel_err(gL_g.cpu(), gL_r) < tol_grad and rel_err(gR_g.cpu(), gR_r) < tol_grad
+    # sign pattern outside near-zero gradients (tau = 1e-2 * max |g|)
+    for gg, gr in ((gL_g.cpu(), gL_r), (gR_g.cpu(), gR_r)):
+        big = gr.abs() > 1e-2 * gr.abs().max()
+        agree = (gg.sign() == gr.sign())[big].float().mean().item()
+        assert agree >= min_agree, agree
+
+
+@pytest.mark.parametrize("impl", [0, 1])
+def test_our_stages_backward_is_bitwise_deterministic(setup_affine, impl):
+    """Cost volume + both 3-D hourglass stacks + lifting, forward and backward twice: identical
+    bits (gather-form backwards, fixed-order reductions).  The stock torch ops around them
+    (trilinear upsample backward etc.) use atomics and are outside this claim."""
+    from eval_driving_safety_b200 import dsgn, ops
+    s = setup_affine
+    ops.set_conv_impl(impl)
+    g = torch.Generator().manual_seed(3)
+    fL, fR, rL = (torch.randn(1, 32, 8, 16, generator=g).cuda() for _ in range(3))
+    res = []
+    for _ in range(2):
+        a, b, r = fL.clone().requires_grad_(True), fR.clone().requires_grad_(True), rL.clone().requires_grad_(True)
+        cost, out, cost1 = s["model"].psv_stage(a, b, s["calib"][0], s["calib"][1])
+        vox = s["model"].lift(out, r, s["calib"][2])
+        v = dsgn.run_convbn_3d(s["model"].rpn3d_conv[0], vox, relu=True)
+        v = s["model"].rpn3d_hg(v, res=v)
+        res.append(torch.autograd.grad(v.square().sum() + cost1.square().sum(), [a, b, r]) + (v.detach(),))
+    for x, y in zip(*res):
+        assert torch.equal(x, y)
+
+
+def test_pgd_attack_final_perturbation(setup):
+    """3-iteration L-inf PGD (eps 0.03, alpha eps/4): oracle loop vs product loop."""
+    from eval_driving_safety_b200 import attack, dsgn, ops
+    s = setup
+    ops.set_conv_impl(1)
+    eps, alpha, K = 0.03, 0.03 / 4, 3
+    xL, xR = s["pair"]["imgL"].clone(), s["pair"]["imgR"].clone()
+    cleanL, cleanR = A.denormalize(xL), A.denormalize(xR)
+    for _ in range(K):
+        _, _, gL, gR = _ref_grads(s, xL, xR)
+        xL = A.pgd_step_linf(xL, gL, cleanL, alpha, eps)
+        xR = A.pgd_step_linf(xR, gR, cleanR, alpha, eps)
+    labels = {k: v.cuda() for k, v in s["labels"].items()}
+    disp = s["pair"]["disp_L"].cuda()
+    loss_fn = lambda out: dsgn.attack_loss(s["cfg_p"], out, disp, labels)
+    aL, aR, losses = attack.pgd_attack(s["model"], loss_fn, s["pair"]["imgL"].cuda(), s["pair"]["imgR"].cuda(),
+                                       s["calib"], K, alpha, eps)
+    dL_ref, dL = A.denormalize(xL) - cleanL, A.denormalize(aL.cpu()) - cleanL
+    assert dL.abs().max() <= eps + 1e-6
+    # perturbation entries are multiples of alpha: identical wherever every iteration's sign agreed
+    same = ((dL - dL_ref).abs() < 1e-6).float().mean().item()
+    assert same > 0.98, same
+    assert losses.shape == (K,)

@@ -1,0 +1,262 @@
+"""GPU parity of the volume kernels through the C ABI against the oracle's stock
+torch ops on CPU: cost volume (subsystem 1), grid_sample lifting (2), conv3d /
+deconv3d / GroupNorm (3), RoIAlign (config 5)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import max_err, rel_err
+from oracle import attack_ref as A
+from oracle import dsgn_ref as R
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops(built_lib):
+    from eval_driving_safety_b200 import ops
+    return ops
+
+
+# ---------------------------------------------------------------- cost volume
+@pytest.mark.parametrize("channels_last", [True, False])
+@pytest.mark.parametrize("dims", [(1, 4, 6, 8, 16), (2, 32, 12, 24, 78), (1, 8, 5, 3, 7)])
+def test_cost_volume_fwd_bwd(ops, dims, channels_last):
+    n, c, d, h, w = dims
+    g = torch.Generator().manual_seed(sum(dims))
+    l = torch.randn(n, c, h, w, generator=g, requires_grad=True)
+    r = torch.randn(n, c, h, w, generator=g, requires_grad=True)
+    shifts = torch.rand(n, d, generator=g) * (w + 2)
+    shifts[:, 0] = 0.0
+    shifts[:, 1] = 3.0                                   # integer shift
+    ref = R.build_cost_volume(l, r, shifts)
+    gy = torch.randn(ref.shape, generator=g)
+    gl_ref, gr_ref = torch.autograd.grad(ref, [l, r], gy)
+    lc, rc = l.detach().cuda().requires_grad_(True), r.detach().cuda().requires_grad_(True)
+    out = ops.build_cost_volume(lc, rc, shifts.cuda(), channels_last)
+    assert out.shape == ref.shape
+    assert torch.equal(out.cpu(), ref)                   # fp32 copy/lerp with the oracle's op order: bit-exact
+    gl, gr = torch.autograd.grad(out, [lc, rc], gy.cuda())
+    assert max_err(gl.cpu(), gl_ref) < 1e-5 and max_err(gr.cpu(), gr_ref) < 1e-5   # sum over planes, order differs
+    gl2, gr2 = torch.autograd.grad(ops.build_cost_volume(lc, rc, shifts.cuda(), channels_last), [lc, rc], gy.cuda())
+    assert torch.equal(gl, gl2) and torch.equal(gr, gr2)                            # deterministic
+
+
+def test_cost_volume_kitti_size_properties(ops):
+    """Full size (368 MB): linearity + PSMNet integer-shift identity, size-independent checks."""
+    from eval_driving_safety_b200 import dsgn, synthetic
+    cfg = dsgn.default_cfg()
+    fu, b, _, _ = synthetic.make_calib(1)
+    shifts = dsgn.plane_shifts(cfg, fu, b).cuda()
+    g = torch.Generator().manual_seed(1)
+    l, r = torch.randn(1, 32, 96, 312, generator=g).cuda(), torch.randn(1, 32, 96, 312, generator=g).cuda()
+    c1 = ops.build_cost_volume(l, r, shifts)
+    assert c1.shape == (1, 64, 48, 96, 312)
+    c2 = ops.build_cost_volume(2 * l, 2 * r, shifts)
+    assert torch.equal(c2, 2 * c1)
+    ish = torch.floor(shifts)
+    ci = ops.build_cost_volume(l, r, ish)
+    d = 17
+    s = int(ish[0, d])
+    assert torch.equal(ci[0, :32, d, :, s:], l[0, :, :, s:]) and torch.equal(ci[0, 32:, d, :, s:], r[0, :, :, :312 - s])
+    assert ci[0, :, d, :, :s].abs().max() == 0
+
+
+# ---------------------------------------------------------------- grid sample
+@pytest.mark.parametrize("align", [True, False])
+def test_grid_sample3d_fwd_bwd(ops, align):
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(2, 64, 6, 9, 11, generator=g, requires_grad=True)
+    grid = (torch.rand(2, 7, 5, 13, 3, generator=g) * 2.6 - 1.3)        # some samples out of range
+    grid[0, 0, 0, 0] = torch.tensor([-1.0, 1.0, 0.0])
+    ref = F.grid_sample(x, grid, mode='bilinear', padding_mode='zeros', align_corners=align)
+    gy = torch.randn(ref.shape, generator=g)
+    (gx_ref,) = torch.autograd.grad(ref, x, gy)
+    xc = x.detach().cuda().requires_grad_(True)
+    out = ops.grid_sample(xc, grid.cuda(), align)
+    ok = ~torch.isnan(ref)
+    assert max_err(out.cpu()[ok], ref[ok]) < 1e-5
+    (gx,) = torch.autograd.grad(out, xc, gy.cuda())
+    assert max_err(gx.cpu(), torch.nan_to_num(gx_ref)) < 1e-4
+    (gx2,) = torch.autograd.grad(ops.grid_sample(xc, grid.cuda(), align), xc, gy.cuda())
+    assert torch.equal(gx, gx2)                                          # deterministic backward
+
+
+def test_grid_sample2d_and_lift(ops):
+    g = torch.Generator().manual_seed(4)
+    img = torch.randn(1, 32, 10, 14, generator=g, requires_grad=True)
+    psv = torch.randn(1, 64, 5, 10, 14, generator=g, requires_grad=True)
+    grid3 = torch.rand(1, 6, 4, 9, 3, generator=g) * 2.4 - 1.2
+    grid2 = grid3[..., :2].reshape(1, 24, 9, 2)
+    ref2 = F.grid_sample(img, grid2, mode='bilinear', padding_mode='zeros', align_corners=True)
+    out2 = ops.grid_sample(img.detach().cuda(), grid2.cuda(), True)
+    assert max_err(out2.cpu(), ref2) < 1e-5
+    ref = torch.cat([F.grid_sample(psv, grid3, mode='bilinear', padding_mode='zeros', align_corners=True),
+                     ref2.view(1, 32, 6, 4, 9)], 1)
+    gy = torch.randn(ref.shape, generator=g)
+    gp_ref, gi_ref = torch.autograd.grad(ref, [psv, img], gy)
+    pc, ic = psv.detach().cuda().requires_grad_(True), img.detach().cuda().requires_grad_(True)
+    out = ops.lift(pc, ic, grid3.cuda())
+    assert out.shape == ref.shape and max_err(out.cpu(), ref) < 1e-5
+    gp, gi = torch.autograd.grad(out, [pc, ic], gy.cuda())
+    assert max_err(gp.cpu(), gp_ref) < 1e-4 and max_err(gi.cpu(), gi_ref) < 1e-4
+
+
+# ---------------------------------------------------------------- conv3d
+CONV_CASES = [  # (cin, cout, stride, transposed, spatial)
+    (64, 64, 1, False, (4, 6, 8)), (96, 64, 1, False, (4, 4, 8)), (128, 128, 1, False, (2, 4, 6)),
+    (64, 128, 2, False, (4, 6, 8)), (128, 128, 2, False, (4, 4, 4)),
+    (128, 128, 2, True, (2, 3, 4)), (128, 64, 2, True, (2, 2, 6)), (8, 12, 1, False, (3, 5, 7))]
+
+
+def _conv_ref(x, w, stride, transposed):
+    if transposed:
+        return F.conv_transpose3d(x, w, None, 2, 1, output_padding=1)
+    return F.conv3d(x, w, None, stride, 1)
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv3d_simt_fwd_dgrad(ops, case):
+    cin, cout, stride, transposed, sp = case
+    g = torch.Generator().manual_seed(cin + cout + stride)
+    x = torch.randn(2, cin, *sp, generator=g, requires_grad=True)
+    w = torch.randn((cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3), generator=g) * 0.05
+    ref = _conv_ref(x, w, stride, transposed)
+    gy = torch.randn(ref.shape, generator=g)
+    (gx_ref,) = torch.autograd.grad(ref, x, gy)
+    xc = x.detach().cuda().requires_grad_(True)
+    out = ops.conv3d(xc, w.cuda(), stride, transposed, impl=1)
+    assert out.shape == ref.shape
+    assert rel_err(out.cpu(), ref) < 1e-4        # fp32 both sides, K up to 3456, different summation order
+    (gx,) = torch.autograd.grad(out, xc, gy.cuda())
+    assert rel_err(gx.cpu(), gx_ref) < 1e-4
+
+
+def test_conv3d_c1_and_groupnorm(ops):
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(2, 64, 4, 6, 10, generator=g, requires_grad=True)
+    w = torch.randn(1, 64, 3, 3, 3, generator=g) * 0.1
+    ref = F.conv3d(x, w, None, 1, 1)
+    gy = torch.randn(ref.shape, generator=g)
+    (gx_ref,) = torch.autograd.grad(ref, x, gy)
+    xc = x.detach().cuda().requires_grad_(True)
+    out = ops.conv3d_c1(xc, w.cuda())
+    assert rel_err(out.cpu(), ref) < 1e-5
+    (gx,) = torch.autograd.grad(out, xc, gy.cuda())
+    assert rel_err(gx.cpu(), gx_ref) < 1e-5
+
+
+@pytest.mark.parametrize("c,relu,has_res", [(64, True, False), (64, False, True), (128, True, True), (64, False, False)])
+def test_groupnorm_act(ops, c, relu, has_res):
+    g = torch.Generator().manual_seed(c + relu)
+    x = (torch.randn(2, c, 3, 5, 7, generator=g) * 2 + 0.5).requires_grad_(True)
+    res = torch.randn(2, c, 3, 5, 7, generator=g).requires_grad_(True) if has_res else None
+    gamma, beta = torch.rand(c, generator=g) + 0.5, torch.randn(c, generator=g)
+    y = F.group_norm(x, 32, gamma, beta, 1e-5)
+    if has_res:
+        y = y + res
+    if relu:
+        y = F.relu(y)
+    gy = torch.randn(y.shape, generator=g)
+    grads_ref = torch.autograd.grad(y, [x] + ([res] if has_res else []), gy)
+    xc = x.detach().cuda().requires_grad_(True)
+    rc = res.detach().cuda().requires_grad_(True) if has_res else None
+    out = ops.groupnorm_act(xc, gamma.cuda(), beta.cuda(), 32, 1e-5, relu, rc)
+    assert max_err(out.cpu(), y) < 2e-5
+    grads = torch.autograd.grad(out, [xc] + ([rc] if has_res else []), gy.cuda())
+    for a, b in zip(grads, grads_ref):
+        assert max_err(a.cpu(), b) < 5e-5
+    grads2 = torch.autograd.grad(ops.groupnorm_act(xc, gamma.cuda(), beta.cuda(), 32, 1e-5, relu, rc),
+                                 [xc] + ([rc] if has_res else []), gy.cuda())
+    assert all(torch.equal(a, b) for a, b in zip(grads, grads2))
+
+
+# ---------------------------------------------------------------- RoIAlign
+@pytest.mark.parametrize("pooled", [7, 14])
+def test_roi_align_vs_torchvision(ops, pooled):
+    from torchvision.ops import roi_align
+    g = torch.Generator().manual_seed(21)
+    feat = torch.randn(1, 16, 38, 125, generator=g, requires_grad=True)
+    x1, y1 = torch.rand(24, generator=g) * 1700, torch.rand(24, generator=g) * 500
+    rois = torch.stack([torch.zeros(24), x1, y1, x1 + torch.rand(24, generator=g) * 400 + 1,
+                        y1 + torch.rand(24, generator=g) * 200 + 1], 1)
+    rois[0] = torch.tensor([0, -30.0, -20.0, 50.0, 40.0])            # partially outside
+    rois[1] = torch.tensor([0, 1900.0, 560.0, 2100.0, 650.0])        # beyond the far edges
+    scale = 38 / 600
+    ref = roi_align(feat, rois, (pooled, pooled), scale, 0, False)
+    gy = torch.randn(ref.shape, generator=g)
+    (gf_ref,) = torch.autograd.grad(ref, feat, gy)
+    fc = feat.detach().cuda().requires_grad_(True)
+    out = ops.roi_align(fc, rois.cuda(), pooled, scale)
+    assert max_err(out.cpu(), ref) < 1e-4
+    (gf,) = torch.autograd.grad(out, fc, gy.cuda())
+    assert max_err(gf.cpu(), gf_ref) < 1e-4
+    (gf2,) = torch.autograd.grad(ops.roi_align(fc, rois.cuda(), pooled, scale), fc, gy.cuda())
+    assert torch.equal(gf, gf2)
+
+
+def test_pyramid_roi_dispatch_matches_oracle(ops):
+    """FPN level dispatch of attack/Stereo-RCNN/stereo_rcnn.py:110-141 through our RoIAlign."""
+    from eval_driving_safety_b200 import stereo_rcnn
+    g = torch.Generator().manual_seed(22)
+    sizes = [(150, 497), (75, 249), (38, 125), (19, 63)]
+    feats = [torch.randn(1, 8, h, w, generator=g) for h, w in sizes]
+    x1, y1 = torch.rand(40, generator=g) * 1500, torch.rand(40, generator=g) * 400
+    w = torch.exp(torch.rand(40, generator=g) * 6.0) + 2
+    h = torch.exp(torch.rand(40, generator=g) * 5.0) + 2
+    rois = torch.stack([torch.zeros(40), x1, y1, x1 + w, y1 + h], 1)
+    ref = A.pyramid_roi_feat(feats, rois, 600.0, 7)
+    out = stereo_rcnn.pyramid_roi_feat([f.cuda() for f in feats], rois.cuda(), 600.0, 7)
+    assert max_err(out.cpu(), ref) < 1e-5
+
+
+# ---------------------------------------------------------------- conv3d, tensor-core path
+TC_CASES = [c for c in CONV_CASES if c[0] % 32 == 0 and c[1] % 32 == 0] + [
+    (64, 64, 1, False, (3, 20, 19)), (64, 96, 1, False, (2, 5, 9)), (64, 128, 2, False, (6, 36, 20)),
+    (128, 64, 2, True, (3, 18, 10))]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv3d_tcgen05_fwd_dgrad(ops, case):
+    """tcgen05/TMEM/TMA implicit GEMM against torch CPU fp32.  Tolerance: TF32 operands (10-bit
+    mantissa, truncation) with fp32 accumulation -> ~8e-4 relative (measured); bound 3e-3."""
+    cin, cout, stride, transposed, sp = case
+    g = torch.Generator().manual_seed(cin + cout + stride + sp[1])
+    x = torch.randn(2, cin, *sp, generator=g, requires_grad=True)
+    w = torch.randn((cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3), generator=g) * 0.05
+    ref = _conv_ref(x, w, stride, transposed)
+    gy = torch.randn(ref.shape, generator=g)
+    (gx_ref,) = torch.autograd.grad(ref, x, gy)
+    xc = x.detach().cuda().requires_grad_(True)
+    out = ops.conv3d(xc, w.cuda(), stride, transposed, impl=0)
+    assert out.shape == ref.shape and rel_err(out.cpu(), ref) < 3e-3
+    (gx,) = torch.autograd.grad(out, xc, gy.cuda())
+    assert rel_err(gx.cpu(), gx_ref) < 3e-3
+    out2 = ops.conv3d(xc, w.cuda(), stride, transposed, impl=0)
+    assert torch.equal(out, out2)
+
+
+def test_conv3d_tcgen05_rejects_unsupported_widths(ops):
+    x, w = torch.randn(1, 8, 4, 4, 4).cuda(), torch.randn(12, 8, 3, 3, 3).cuda()
+    with pytest.raises(RuntimeError, match="impl=1"):
+        ops.conv3d(x, w, 1, False, impl=0)
+    w.requires_grad_(True)
+    with pytest.raises(RuntimeError, match="frozen"):
+        ops.conv3d(x, w, 1, False, impl=1)
+
+
+def test_conv3d_kitti_size_tcgen05_vs_fp32_kernel(ops):
+    """Full PSV size [1,64,48,96,312] (318 GFLOP): tensor-core path against the fp32 SIMT kernel,
+    plus linearity (size-independent property)."""
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(1, 48, 96, 312, 64, generator=g).cuda().permute(0, 4, 1, 2, 3)
+    w = (torch.randn(64, 64, 3, 3, 3, generator=g) * 0.03).cuda()
+    a = ops.conv3d(x, w, 1, False, impl=0)
+    b = ops.conv3d(x, w, 1, False, impl=1)
+    assert rel_err(a, b) < 3e-3
+    assert torch.equal(ops.conv3d(2 * x, w, 1, False, impl=0), 2 * a)     # power-of-two scaling is exact
+    xs = torch.randn(1, 24, 48, 156, 128, generator=g).cuda().permute(0, 4, 1, 2, 3)
+    wt = (torch.randn(128, 64, 3, 3, 3, generator=g) * 0.03).cuda()
+    assert rel_err(ops.conv3d(xs, wt, 2, True, impl=0), ops.conv3d(xs, wt, 2, True, impl=1)) < 3e-3
+    w2 = (torch.randn(128, 64, 3, 3, 3, generator=g) * 0.03).cuda()
+    assert rel_err(ops.conv3d(x, w2, 2, False, impl=0), ops.conv3d(x, w2, 2, False, impl=1)) < 3e-3
