@@ -81,23 +81,41 @@ __global__ void gn_partials_kernel(const float4* __restrict__ a, const float4* _
     }
 }
 
-// One block per sample, one thread per channel.
-// fwd: stats[n][g] = (mean, rstd); coef[n][0][c] = scale, coef[n][1][c] = shift.
-__global__ void gn_finalize_fwd(const float* __restrict__ partial, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, float* __restrict__ stats,
-                                float* __restrict__ coef, int C, int64_t S, int G, float eps, int nblocks) {
-    __shared__ double s1[kGnMaxC], s2[kGnMaxC];
-    const int n = blockIdx.x, c = threadIdx.x;
+// Sum the per-block partials of channel c: kGnLanes threads per channel each add every
+// kGnLanes-th partial in order, then the lanes are combined in lane order -> fixed order.
+constexpr int kGnLanes = 4;       // kGnMaxC * kGnLanes = 1024 threads
+
+__device__ __forceinline__ void gn_sum_partials(const float* __restrict__ partial, int n, int nblocks, int C,
+                                                double* s1, double* s2, double (*sh)[2][kGnMaxC]) {
+    const int c = threadIdx.x % kGnMaxC, l = threadIdx.x / kGnMaxC;
     double a = 0.0, b = 0.0;
     if (c < C) {
-        for (int k = 0; k < nblocks; ++k) {
+        for (int k = l; k < nblocks; k += kGnLanes) {
             const float* p = partial + (((int64_t)n * nblocks + k) * 2) * C;
-            a += (double)p[c];
-            b += (double)p[C + c];
+            a += (double)__ldg(p + c);
+            b += (double)__ldg(p + C + c);
         }
-        s1[c] = a; s2[c] = b;
+    }
+    sh[l][0][c] = a; sh[l][1][c] = b;
+    __syncthreads();
+    if (l == 0 && c < C) {
+        double ta = 0.0, tb = 0.0;
+        for (int j = 0; j < kGnLanes; ++j) { ta += sh[j][0][c]; tb += sh[j][1][c]; }
+        s1[c] = ta; s2[c] = tb;
     }
     __syncthreads();
+}
+
+// One block per sample, kGnLanes threads per channel.
+// fwd: stats[n][g] = (mean, rstd); coef[n][0][c] = scale, coef[n][1][c] = shift.
+__global__ void __launch_bounds__(kGnMaxC * kGnLanes)
+gn_finalize_fwd(const float* __restrict__ partial, const float* __restrict__ gamma,
+                const float* __restrict__ beta, float* __restrict__ stats,
+                float* __restrict__ coef, int C, int64_t S, int G, float eps, int nblocks) {
+    __shared__ double s1[kGnMaxC], s2[kGnMaxC];
+    __shared__ double sh[kGnLanes][2][kGnMaxC];
+    const int n = blockIdx.x, c = threadIdx.x;
+    gn_sum_partials(partial, n, nblocks, C, s1, s2, sh);
     if (c < C) {
         const int cpg = C / G, g = c / cpg;
         double sum = 0.0, sq = 0.0;
@@ -120,21 +138,15 @@ __global__ void gn_finalize_fwd(const float* __restrict__ partial, const float* 
 // bwd: coef[n][0][c] = gamma_c*rstd_g, coef[n][1][c] = c2_g, coef[n][2][c] = c3_g with
 //   ds = sum_c gamma_c * sum(gz*x), db = sum_c gamma_c * sum(gz)
 //   c2 = (db*mean - ds) * rstd^3 / m ; c3 = -c2*mean - db*rstd/m ; gx = coef0*gz + c2*x + c3
-__global__ void gn_finalize_bwd(const float* __restrict__ partial, const float* __restrict__ gamma,
-                                const float* __restrict__ stats, float* __restrict__ coef, int C,
-                                int64_t S, int G, int nblocks) {
+__global__ void __launch_bounds__(kGnMaxC * kGnLanes)
+gn_finalize_bwd(const float* __restrict__ partial, const float* __restrict__ gamma,
+                const float* __restrict__ stats, float* __restrict__ coef, int C,
+                int64_t S, int G, int nblocks) {
     __shared__ double s1[kGnMaxC], s2[kGnMaxC];
+    __shared__ double sh[kGnLanes][2][kGnMaxC];
     const int n = blockIdx.x, c = threadIdx.x;
-    if (c < C) {
-        double a = 0.0, b = 0.0;
-        for (int k = 0; k < nblocks; ++k) {
-            const float* p = partial + (((int64_t)n * nblocks + k) * 2) * C;
-            a += (double)p[c];
-            b += (double)p[C + c];
-        }
-        s1[c] = a * (double)gamma[c];
-        s2[c] = b * (double)gamma[c];
-    }
+    gn_sum_partials(partial, n, nblocks, C, s1, s2, sh);
+    if (c < C) { s1[c] *= (double)gamma[c]; s2[c] *= (double)gamma[c]; }
     __syncthreads();
     if (c < C) {
         const int cpg = C / G, g = c / cpg;
@@ -234,7 +246,7 @@ extern "C" int b2_groupnorm_fwd(const float* x, const float* res, const float* g
     int nblocks = (int)(S < kGnBlocks ? S : kGnBlocks);
     gn_partials_kernel<0><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
         nullptr, (const float4*)x, nullptr, partial, C, S, l.lpr, l.rpb, 0);
-    gn_finalize_fwd<<<N, kGnMaxC, 0, st>>>(partial, gamma, beta, stats, coef, C, S, G, eps, nblocks);
+    gn_finalize_fwd<<<N, kGnMaxC * kGnLanes, 0, st>>>(partial, gamma, beta, stats, coef, C, S, G, eps, nblocks);
     int gx = stream_grid(S * l.lpr, 256 * 4, kNumSMs * 8);
     gn_apply_fwd<<<dim3(gx, N), 256, 2 * C * sizeof(float), st>>>((const float4*)x, (const float4*)res, coef,
                                                                   (float4*)y, C, S, relu);
@@ -256,7 +268,7 @@ extern "C" int b2_groupnorm_bwd(const float* gy, const float* x, const float* y,
     int nblocks = (int)(S < kGnBlocks ? S : kGnBlocks);
     gn_partials_kernel<1><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
         (const float4*)gy, (const float4*)x, (const float4*)y, partial, C, S, l.lpr, l.rpb, relu);
-    gn_finalize_bwd<<<N, kGnMaxC, 0, st>>>(partial, gamma, stats, coef, C, S, G, nblocks);
+    gn_finalize_bwd<<<N, kGnMaxC * kGnLanes, 0, st>>>(partial, gamma, stats, coef, C, S, G, nblocks);
     int gxd = stream_grid(S * l.lpr, 256 * 4, kNumSMs * 8);
     gn_apply_bwd<<<dim3(gxd, N), 256, 3 * C * sizeof(float), st>>>((const float4*)gy, (const float4*)x,
                                                                    (const float4*)y, coef, (float4*)gx,

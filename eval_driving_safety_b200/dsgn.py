@@ -66,6 +66,14 @@ def run_convbn_3d(seq, x, relu=False, res=None):
     return ops.groupnorm_act(y, norm.weight, norm.bias, norm.num_groups, norm.eps, relu=relu, res=res)
 
 
+def run_convbn_2d(seq, x, relu=False, res=None):
+    """cuDNN conv2d (channels-last) -> our GroupNorm (+res) (+ReLU) kernel.
+    ``seq`` = Sequential(Conv2d, GroupNorm)."""
+    conv, norm = seq[0], seq[1]
+    y = conv(x)
+    return ops.groupnorm_act(y, norm.weight, norm.bias, norm.num_groups, norm.eps, relu=relu, res=res)
+
+
 class BasicBlock(nn.Module):
     def __init__(self, cfg, cin, cout, stride, dilation):
         super().__init__()
@@ -76,10 +84,40 @@ class BasicBlock(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), _gn(cfg, cout))
 
     def forward(self, x):
-        out = self.conv2(self.conv1(x))
-        if self.downsample is not None:
-            x = self.downsample(x)
-        return out + x
+        out = run_convbn_2d(self.conv1[0], x, relu=True)
+        short = x if self.downsample is None else run_convbn_2d(self.downsample, x)
+        return run_convbn_2d(self.conv2, out, relu=False, res=short)      # GN(conv2) + shortcut, one pass
+
+
+_INTERP_CACHE = {}
+
+
+def _interp_matrix(n_in, n_out, device):
+    """[n_out, n_in] bilinear (align_corners=False) interpolation matrix, ATen's
+    area_pixel_compute_source_index rule: src = (dst + .5) * in/out - .5, clamped at 0."""
+    key = (n_in, n_out, str(device))
+    m = _INTERP_CACHE.get(key)
+    if m is None:
+        dst = torch.arange(n_out, dtype=torch.float32)
+        src = ((dst + 0.5) * (n_in / n_out) - 0.5).clamp_min(0.0)
+        i0 = src.floor().long().clamp_max(n_in - 1)
+        i1 = (i0 + 1).clamp_max(n_in - 1)
+        w1 = src - i0.float()
+        m = torch.zeros(n_out, n_in)
+        m.scatter_add_(1, i0.view(-1, 1), (1 - w1).view(-1, 1))
+        m.scatter_add_(1, i1.view(-1, 1), w1.view(-1, 1))
+        m = m.to(device)
+        _INTERP_CACHE[key] = m
+    return m
+
+
+def upsample_bilinear_matmul(x, size):
+    """F.interpolate(x, size, 'bilinear', align_corners=False) as two small GEMMs: the SPP maps
+    are tiny (1x4 .. 12x39), and ATen's upsample backward serialises on atomics there (7.6 ms per
+    iteration measured); the GEMM form is deterministic and ~100x faster in backward."""
+    ah = _interp_matrix(x.shape[-2], size[0], x.device)
+    aw = _interp_matrix(x.shape[-1], size[1], x.device)
+    return torch.matmul(torch.matmul(ah, x), aw.t())
 
 
 class FeatureExtraction(nn.Module):
@@ -110,14 +148,34 @@ class FeatureExtraction(nn.Module):
         return nn.Sequential(*layers)
 
     def forward(self, x):
-        out = self.layer1(self.firstconv(x))
+        x = x.contiguous(memory_format=torch.channels_last)
+        out = x
+        for i in (0, 2, 4):
+            out = run_convbn_2d(self.firstconv[i], out, relu=True)
+        out = self.layer1(out)
         raw = self.layer2(out)
         skip = self.layer4(self.layer3(raw))
         size = skip.shape[-2:]
-        cat = [raw, skip] + [F.interpolate(br(skip), size, mode='bilinear', align_corners=False)
-                             for br in self.branches]
-        cat = torch.cat(cat, 1)
-        return self.lastconv(cat), self.rpnconv(cat)
+        # SPP: the pools are nested (every window size is a multiple of the smallest), so pool
+        # once by the smallest and re-pool that -- same windows, no 64x64-wide serial loops
+        pools = [br[0].kernel_size if isinstance(br[0].kernel_size, int) else br[0].kernel_size[0]
+                 for br in self.branches]
+        base = min(pools)
+        cat = [raw, skip]
+        if all(p % base == 0 for p in pools):
+            pooled0 = F.avg_pool2d(skip, base, base)
+            for br, p in zip(self.branches, pools):
+                y = pooled0 if p == base else F.avg_pool2d(pooled0, p // base, p // base)
+                y = run_convbn_2d(br[1], y, relu=True)
+                cat.append(upsample_bilinear_matmul(y, size))
+        else:
+            for br in self.branches:
+                y = run_convbn_2d(br[1], br[0](skip), relu=True)
+                cat.append(upsample_bilinear_matmul(y, size))
+        cat = torch.cat(cat, 1).contiguous(memory_format=torch.channels_last)
+        f = self.lastconv[2](run_convbn_2d(self.lastconv[0], cat, relu=True))
+        r = self.rpnconv[2](run_convbn_2d(self.rpnconv[0], cat, relu=True))
+        return f, r
 
 
 class Hourglass3d(nn.Module):
@@ -217,6 +275,10 @@ class StereoNet(nn.Module):
     def freeze(self):
         for p in self.parameters():
             p.requires_grad_(False)
+        # 2-D parts run channels-last end to end (cuDNN NHWC kernels, our GroupNorm kernel)
+        for m in self.modules():
+            if isinstance(m, nn.Conv2d):
+                m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
         return self.eval()
 
     def load_state_dict(self, state_dict, strict=True, **kw):
@@ -273,8 +335,9 @@ class StereoNet(nn.Module):
         v = self.rpn3d_hg(v, res=v)
         v = F.avg_pool3d(v, (1, cfg.y_pool, 1))
         n, c, zz, yy, xx = v.shape
-        bev = v.permute(0, 1, 3, 2, 4).reshape(n, c * yy, zz, xx)
-        bev = self.bev_conv(bev)
+        bev = v.permute(0, 1, 3, 2, 4).reshape(n, c * yy, zz, xx).contiguous(memory_format=torch.channels_last)
+        bev = run_convbn_2d(self.bev_conv[0], bev, relu=True)
+        bev = run_convbn_2d(self.bev_conv[2], bev, relu=True)
         return self.bbox_cls(bev), self.bbox_reg(bev), self.bbox_centerness(bev)
 
     def forward(self, imgL, imgR, calibs_fu, calibs_baseline, calibs_Proj, calibs_Proj_R=None):

@@ -459,18 +459,26 @@ def _workspace(nbytes, device):
     return ws
 
 
+def _cl(x):
+    return cl3(x) if x.dim() == 5 else cl2(x)
+
+
+def _empty_cl_like(x):
+    return empty_cl3(*x.shape, x.device) if x.dim() == 5 else empty_cl2(*x.shape, x.device)
+
+
 class GroupNormActFn(Function):
-    """y = act(GroupNorm(x) (+ res)) on channels-last volumes; data gradient only."""
+    """y = act(GroupNorm(x) (+ res)) on channels-last 3-D volumes or 2-D maps; data gradient only."""
 
     @staticmethod
     def forward(ctx, x, res, gamma, beta, groups, eps, relu):
         _need_cuda(x, res, gamma, beta)
         lib = _lib.load()
-        x = cl3(x)
-        res = cl3(res) if res is not None else None
+        x = _cl(x)
+        res = _cl(res) if res is not None else None
         n, c = x.shape[:2]
         s = x[0, 0].numel()
-        y = empty_cl3(*x.shape, x.device)
+        y = _empty_cl_like(x)
         stats = torch.empty((n, groups, 2), device=x.device, dtype=torch.float32)
         ws = _workspace(lib.b2_groupnorm_workspace_bytes(n, c), x.device)
         gamma, beta = gamma.detach().contiguous(), beta.detach().contiguous()
@@ -487,11 +495,11 @@ class GroupNormActFn(Function):
         lib = _lib.load()
         x, y, gamma, stats = ctx.saved_tensors
         groups, relu, has_res = ctx.cfg
-        gy = cl3(gy)
+        gy = _cl(gy)
         n, c = x.shape[:2]
         s = x[0, 0].numel()
-        gx = empty_cl3(*x.shape, x.device)
-        gres = empty_cl3(*x.shape, x.device) if (has_res and relu) else None
+        gx = _empty_cl_like(x)
+        gres = _empty_cl_like(x) if (has_res and relu) else None
         ws = _workspace(lib.b2_groupnorm_workspace_bytes(n, c), x.device)
         with _op("groupnorm_bwd", 3, 4 * x.numel() * (5 + 2 * int(relu) + (gres is not None))):
             check(lib.b2_groupnorm_bwd(_p(gy), _p(x), _p(y), _p(gamma), _p(stats), _p(gx), _p(gres), n, c, s, groups,

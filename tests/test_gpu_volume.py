@@ -207,7 +207,7 @@ def test_pyramid_roi_dispatch_matches_oracle(ops):
     rois = torch.stack([torch.zeros(40), x1, y1, x1 + w, y1 + h], 1)
     ref = A.pyramid_roi_feat(feats, rois, 600.0, 7)
     out = stereo_rcnn.pyramid_roi_feat([f.cuda() for f in feats], rois.cuda(), 600.0, 7)
-    assert max_err(out.cpu(), ref) < 1e-5
+    assert max_err(out.cpu(), ref) < 1e-4
 
 
 # ---------------------------------------------------------------- conv3d, tensor-core path
