@@ -20,6 +20,7 @@
 //               mbarriers; two TMEM accumulators so the epilogue of tile i overlaps
 //               the MMAs of tile i+1.  Persistent: one CTA per SM, static tile striding.
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b2 {
@@ -289,6 +290,226 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
 }
 
+
+// =============================================================================================
+// Stride-1 fast path ("super tile").  The generic kernel above reloads the A box and the weight
+// tile for every tap: 1.33 MB of L2->SM traffic per 128-voxel tile, measured L2-bound at
+// 290 TFLOP/s (profiles/r1_conv3d_tcgen05_ncu.txt).  Here one CTA owns kS1Planes = 4 consecutive
+// depth planes of a 16h x 8w box (4 accumulators of Nt columns, double buffered = all of TMEM
+// for Nt = 64) and walks (kw, K-chunk) "generations":
+//   * A: per generation the 6 input planes d0-1 .. d0+4 are loaded ONCE each as an
+//     {32 ch, 8 w, 18 h} halo box (18 KB).  The three kh taps read the same smem tile at row
+//     offsets 0 / 8 / 16 (= +0 / +1024 / +2048 B, whole 128B-swizzle atoms), the three kd taps
+//     feed three different accumulators -> each A byte is used by up to 9 MMA groups.
+//   * B: the 9 (kd, kh) weight tiles of the generation are loaded once (ring of slots with their
+//     own full/empty barriers) and reused by all 4 planes.
+//   L2->SM traffic: 1080 KB per 512 voxels (4.9x less).  Cout > 64 is split in two N tiles.
+// =============================================================================================
+constexpr int kS1Planes = 4;
+constexpr int kS1ARows = (kTileH + 2) * kTileW;        // 144 rows
+constexpr int kS1ABytes = kS1ARows * 128;              // 18432 B = 18 swizzle atoms
+constexpr int kS1NA = 4;                               // A ring slots
+constexpr int kS1MaxNB = 18;                           // B ring slots (>= 9)
+
+struct S1Params {
+    int N, Cin, Cout, D, H, W;
+    int nt, n_tiles;           // N tile width, number of N tiles
+    int tiles_w, tiles_h, dblocks;
+    int kchunks;
+    int nb;                    // B ring slots
+    int b_bytes;               // nt * 128
+    int tmem_cols;
+    long long total_tiles;
+};
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
+
+struct S1Tile { int nti, n, d0, h0, w0; };
+
+__device__ __forceinline__ S1Tile s1_decode(const S1Params& p, long long t) {
+    S1Tile c;
+    c.w0 = (int)(t % p.tiles_w) * kTileW; t /= p.tiles_w;
+    c.h0 = (int)(t % p.tiles_h) * kTileH; t /= p.tiles_h;
+    c.d0 = (int)(t % p.dblocks) * kS1Planes; t /= p.dblocks;
+    c.n = (int)(t % p.N); t /= p.N;
+    c.nti = (int)t;
+    return c;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3d_s1_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         float* __restrict__ out, const S1Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kS1NA + 2 * kS1MaxNB + 4];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_base = smem_base, b_base = smem_base + kS1NA * kS1ABytes;
+    const uint32_t bar0 = smem_u32(bars);
+    auto fullA = [&](int s) { return bar0 + 8u * s; };
+    auto emptyA = [&](int s) { return bar0 + 8u * (kS1NA + s); };
+    auto fullB = [&](int s) { return bar0 + 8u * (2 * kS1NA + s); };
+    auto emptyB = [&](int s) { return bar0 + 8u * (2 * kS1NA + kS1MaxNB + s); };
+    auto tfull = [&](int a) { return bar0 + 8u * (2 * kS1NA + 2 * kS1MaxNB + a); };
+    auto tempty = [&](int a) { return bar0 + 8u * (2 * kS1NA + 2 * kS1MaxNB + 2 + a); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kS1NA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+        for (int s = 0; s < p.nb; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const int ngen = 3 * p.kchunks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t a_ord = 0, b_ord = 0;
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                S1Tile tc = s1_decode(p, t);
+                for (int g = 0; g < ngen; ++g) {
+                    const int kw = g / p.kchunks, kc = g % p.kchunks;
+                    for (int pr = 0; pr < kS1Planes + 2; ++pr) {
+                        if (pr < 3) {
+                            for (int kh = 0; kh < 3; ++kh, ++b_ord) {
+                                const int slot = b_ord % p.nb;
+                                mbar_wait(emptyB(slot), ((b_ord / p.nb) & 1) ^ 1);
+                                mbar_expect_tx(fullB(slot), (uint32_t)p.b_bytes);
+                                const int tap = (pr * 3 + kh) * 3 + kw;
+                                tma_load_2d(b_base + (uint32_t)slot * p.b_bytes, &map_b, fullB(slot), kc * kKChunk,
+                                            tap * p.Cout + tc.nti * p.nt);
+                            }
+                        }
+                        const int slot = a_ord % kS1NA;
+                        mbar_wait(emptyA(slot), ((a_ord / kS1NA) & 1) ^ 1);
+                        mbar_expect_tx(fullA(slot), (uint32_t)kS1ABytes);
+                        tma_load_5d(a_base + (uint32_t)slot * kS1ABytes, &map_a, fullA(slot), kc * kKChunk,
+                                    tc.w0 + kw - 1, tc.h0 - 1, tc.d0 - 1 + pr, tc.n);
+                        ++a_ord;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(128, p.nt);
+            uint32_t a_ord = 0, b_gen = 0;     // b_gen = tap ordinal of the current generation's first tap
+            long long it = 0;
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+                const int accbuf = (int)(it & 1);
+                mbar_wait(tempty(accbuf), (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t tmem_acc0 = tmem_base + (uint32_t)(accbuf * kS1Planes * p.nt);
+                for (int g = 0; g < ngen; ++g, b_gen += 9) {
+                    for (int pr = 0; pr < kS1Planes + 2; ++pr, ++a_ord) {
+                        const int aslot = a_ord % kS1NA;
+                        mbar_wait(fullA(aslot), (a_ord / kS1NA) & 1);
+                        tc_fence_after();
+                        const uint32_t sa = a_base + (uint32_t)aslot * kS1ABytes;
+                        for (int kd = 0; kd < 3; ++kd) {
+                            const int j = pr - kd;                 // accumulator = output plane d0 + j
+                            if (j < 0 || j >= kS1Planes) continue;
+                            for (int kh = 0; kh < 3; ++kh) {
+                                const uint32_t b_ord = b_gen + kd * 3 + kh;
+                                const int bslot = b_ord % p.nb;
+                                if (j == 0) {                      // first use of this weight tile
+                                    mbar_wait(fullB(bslot), (b_ord / p.nb) & 1);
+                                    tc_fence_after();
+                                }
+                                const uint64_t adesc = umma_desc_sw128(sa + (uint32_t)kh * 1024u);
+                                const uint64_t bdesc = umma_desc_sw128(b_base + (uint32_t)bslot * p.b_bytes);
+                                const uint32_t tmem_d = tmem_acc0 + (uint32_t)(j * p.nt);
+                                const uint32_t first = (g | kd | kh);
+#pragma unroll
+                                for (int k = 0; k < kKChunk / 8; ++k)
+                                    umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (first | k) != 0);
+                                if (j == kS1Planes - 1) umma_commit(emptyB(bslot));   // last use of the tile
+                            }
+                        }
+                        umma_commit(emptyA(aslot));
+                    }
+                }
+                umma_commit(tfull(accbuf));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue =====================
+        const int lane_grp = warp & 3;
+        const int m = lane_grp * 32 + lane;
+        const int hl = m / kTileW, wl = m % kTileW;
+        long long it = 0;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const int accbuf = (int)(it & 1);
+            S1Tile tc = s1_decode(p, t);
+            const int h = tc.h0 + hl, w = tc.w0 + wl;
+            const bool ok_hw = h < p.H && w < p.W;
+            mbar_wait(tfull(accbuf), (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            for (int j = 0; j < kS1Planes; ++j) {
+                const int d = tc.d0 + j;
+                const bool ok = ok_hw && d < p.D;
+                float* orow = out + ((((long long)tc.n * p.D + d) * p.H + h) * p.W + w) * p.Cout + tc.nti * p.nt;
+                const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) +
+                                       (uint32_t)((accbuf * kS1Planes + j) * p.nt);
+                int c0 = 0;
+                for (; c0 + 32 <= p.nt; c0 += 32) {
+                    uint32_t r[32];
+                    tmem_ld32(taddr + c0, r);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4*>(orow + c0 + 4 * q) =
+                                make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                            __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                    }
+                }
+                if (c0 < p.nt) {                                   // 16-column remainder (Nt = 48)
+                    uint32_t r[16];
+                    tmem_ld16(taddr + c0, r);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<float4*>(orow + c0 + 4 * q) =
+                                make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                            __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty(accbuf));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
 // ---------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -306,6 +527,57 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* wp, float* out, int N, int Cin,
+                            int Cout, int D, int H, int W, cudaStream_t st) {
+    S1Params p{};
+    p.N = N; p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W;
+    p.nt = Cout <= 64 ? Cout : Cout / 2;
+    p.n_tiles = Cout / p.nt;
+    p.tiles_w = (W + kTileW - 1) / kTileW;
+    p.tiles_h = (H + kTileH - 1) / kTileH;
+    p.dblocks = (D + kS1Planes - 1) / kS1Planes;
+    p.kchunks = Cin / kKChunk;
+    p.b_bytes = p.nt * 128;
+    p.nb = (216 * 1024 - kS1NA * kS1ABytes) / p.b_bytes;
+    if (p.nb > kS1MaxNB) p.nb = kS1MaxNB;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 2 * kS1Planes * p.nt) p.tmem_cols *= 2;
+    p.total_tiles = (long long)p.n_tiles * N * p.dblocks * p.tiles_h * p.tiles_w;
+
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+        cuuint64_t gstr[4] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4,
+                              (cuuint64_t)D * H * W * Cin * 4};
+        cuuint32_t box[5] = {(cuuint32_t)kKChunk, (cuuint32_t)kTileW, (cuuint32_t)kTileH + 2, 1, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in, gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3d(tcgen05,s1): cuTensorMapEncodeTiled(A) failed: %d", (int)r); return B2_ERR_DRIVER; }
+    }
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * Cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)Cin * 4};
+        cuuint32_t box[2] = {(cuuint32_t)kKChunk, (cuuint32_t)p.nt};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wp, gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3d(tcgen05,s1): cuTensorMapEncodeTiled(B) failed: %d", (int)r); return B2_ERR_DRIVER; }
+    }
+    const int smem = kS1NA * kS1ABytes + p.nb * p.b_bytes + 1024;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(conv3d_s1_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_error("conv3d(tcgen05,s1): cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return (int)e; }
+        attr_smem = smem;
+    }
+    int grid = (int)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
+    conv3d_s1_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p);
+    return check_launch("conv3d(tcgen05,s1)");
+}
+
 int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
                           int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st) {
     if (Cin % 32 != 0 || Cout % 32 != 0 || Cout > 256 || Cout < 32) {
@@ -315,6 +587,15 @@ int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, i
     }
     EncodeTiledFn encode = get_encode();
     if (!encode) { set_error("conv3d(tcgen05): cuTensorMapEncodeTiled not available from the driver"); return B2_ERR_DRIVER; }
+    {
+        // stride-1 convs (74 % of the flops) take the halo-reuse super-tile kernel; B2_CONV_S1_SIMPLE=1
+        // forces the generic one-tap-per-stage kernel (A/B testing)
+        static int simple = -1;
+        if (simple < 0) { const char* e = getenv("B2_CONV_S1_SIMPLE"); simple = (e && e[0] == '1') ? 1 : 0; }
+        const int nt = Cout <= 64 ? Cout : Cout / 2;
+        if (mode == 0 && stride == 1 && !simple && nt % 16 == 0)
+            return conv3d_s1_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st);
+    }
 
     TcParams p{};
     p.N = N; p.Cin = Cin; p.Cout = Cout; p.Do = Do; p.Ho = Ho; p.Wo = Wo;

@@ -22,6 +22,14 @@ struct GnLayout {
     int threads;  // lpr * rpb
 };
 
+// partial blocks per sample: at least ~128 rows each, at most two per SM
+static int gn_nblocks(int64_t S) {
+    int64_t nb = (S + 127) / 128;
+    if (nb < 1) nb = 1;
+    if (nb > kGnBlocks) nb = kGnBlocks;
+    return (int)nb;
+}
+
 static GnLayout gn_layout(int C) {
     GnLayout l;
     l.lpr = C / 4;
@@ -81,26 +89,28 @@ __global__ void gn_partials_kernel(const float4* __restrict__ a, const float4* _
     }
 }
 
-// Sum the per-block partials of channel c: kGnLanes threads per channel each add every
-// kGnLanes-th partial in order, then the lanes are combined in lane order -> fixed order.
-constexpr int kGnLanes = 4;       // kGnMaxC * kGnLanes = 1024 threads
+// Sum the per-block partials of channel c: `lanes` = 1024 / C threads per channel each add every
+// lanes-th partial in order, then the lanes are combined in lane order -> fixed summation order.
+constexpr int kGnFinThreads = 1024;
+constexpr int kGnLanes = 4;       // minimum lanes per channel (C = 256)
 
 __device__ __forceinline__ void gn_sum_partials(const float* __restrict__ partial, int n, int nblocks, int C,
-                                                double* s1, double* s2, double (*sh)[2][kGnMaxC]) {
-    const int c = threadIdx.x % kGnMaxC, l = threadIdx.x / kGnMaxC;
+                                                double* s1, double* s2, double* sh /* [2][1024] */) {
+    const int lanes = kGnFinThreads / C;            // >= 4
+    const int c = threadIdx.x % C, l = threadIdx.x / C;
     double a = 0.0, b = 0.0;
-    if (c < C) {
-        for (int k = l; k < nblocks; k += kGnLanes) {
+    if (l < lanes) {
+        for (int k = l; k < nblocks; k += lanes) {
             const float* p = partial + (((int64_t)n * nblocks + k) * 2) * C;
             a += (double)__ldg(p + c);
             b += (double)__ldg(p + C + c);
         }
     }
-    sh[l][0][c] = a; sh[l][1][c] = b;
+    sh[threadIdx.x] = a; sh[kGnFinThreads + threadIdx.x] = b;
     __syncthreads();
-    if (l == 0 && c < C) {
+    if (threadIdx.x < C) {
         double ta = 0.0, tb = 0.0;
-        for (int j = 0; j < kGnLanes; ++j) { ta += sh[j][0][c]; tb += sh[j][1][c]; }
+        for (int j = 0; j < lanes; ++j) { ta += sh[j * C + c]; tb += sh[kGnFinThreads + j * C + c]; }
         s1[c] = ta; s2[c] = tb;
     }
     __syncthreads();
@@ -108,12 +118,12 @@ __device__ __forceinline__ void gn_sum_partials(const float* __restrict__ partia
 
 // One block per sample, kGnLanes threads per channel.
 // fwd: stats[n][g] = (mean, rstd); coef[n][0][c] = scale, coef[n][1][c] = shift.
-__global__ void __launch_bounds__(kGnMaxC * kGnLanes)
+__global__ void __launch_bounds__(kGnFinThreads)
 gn_finalize_fwd(const float* __restrict__ partial, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float* __restrict__ stats,
                 float* __restrict__ coef, int C, int64_t S, int G, float eps, int nblocks) {
     __shared__ double s1[kGnMaxC], s2[kGnMaxC];
-    __shared__ double sh[kGnLanes][2][kGnMaxC];
+    __shared__ double sh[2 * kGnFinThreads];
     const int n = blockIdx.x, c = threadIdx.x;
     gn_sum_partials(partial, n, nblocks, C, s1, s2, sh);
     if (c < C) {
@@ -138,12 +148,12 @@ gn_finalize_fwd(const float* __restrict__ partial, const float* __restrict__ gam
 // bwd: coef[n][0][c] = gamma_c*rstd_g, coef[n][1][c] = c2_g, coef[n][2][c] = c3_g with
 //   ds = sum_c gamma_c * sum(gz*x), db = sum_c gamma_c * sum(gz)
 //   c2 = (db*mean - ds) * rstd^3 / m ; c3 = -c2*mean - db*rstd/m ; gx = coef0*gz + c2*x + c3
-__global__ void __launch_bounds__(kGnMaxC * kGnLanes)
+__global__ void __launch_bounds__(kGnFinThreads)
 gn_finalize_bwd(const float* __restrict__ partial, const float* __restrict__ gamma,
                 const float* __restrict__ stats, float* __restrict__ coef, int C,
                 int64_t S, int G, int nblocks) {
     __shared__ double s1[kGnMaxC], s2[kGnMaxC];
-    __shared__ double sh[kGnLanes][2][kGnMaxC];
+    __shared__ double sh[2 * kGnFinThreads];
     const int n = blockIdx.x, c = threadIdx.x;
     gn_sum_partials(partial, n, nblocks, C, s1, s2, sh);
     if (c < C) { s1[c] *= (double)gamma[c]; s2[c] *= (double)gamma[c]; }
@@ -243,10 +253,10 @@ extern "C" int b2_groupnorm_fwd(const float* x, const float* res, const float* g
     GnLayout l = gn_layout(C);
     float* partial = (float*)workspace;
     float* coef = partial + gn_partial_floats(N, C);
-    int nblocks = (int)(S < kGnBlocks ? S : kGnBlocks);
+    int nblocks = gn_nblocks(S);
     gn_partials_kernel<0><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
         nullptr, (const float4*)x, nullptr, partial, C, S, l.lpr, l.rpb, 0);
-    gn_finalize_fwd<<<N, kGnMaxC * kGnLanes, 0, st>>>(partial, gamma, beta, stats, coef, C, S, G, eps, nblocks);
+    gn_finalize_fwd<<<N, kGnFinThreads, 0, st>>>(partial, gamma, beta, stats, coef, C, S, G, eps, nblocks);
     int gx = stream_grid(S * l.lpr, 256 * 4, kNumSMs * 8);
     gn_apply_fwd<<<dim3(gx, N), 256, 2 * C * sizeof(float), st>>>((const float4*)x, (const float4*)res, coef,
                                                                   (float4*)y, C, S, relu);
@@ -265,10 +275,10 @@ extern "C" int b2_groupnorm_bwd(const float* gy, const float* x, const float* y,
     GnLayout l = gn_layout(C);
     float* partial = (float*)workspace;
     float* coef = partial + gn_partial_floats(N, C);
-    int nblocks = (int)(S < kGnBlocks ? S : kGnBlocks);
+    int nblocks = gn_nblocks(S);
     gn_partials_kernel<1><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
         (const float4*)gy, (const float4*)x, (const float4*)y, partial, C, S, l.lpr, l.rpb, relu);
-    gn_finalize_bwd<<<N, kGnMaxC * kGnLanes, 0, st>>>(partial, gamma, stats, coef, C, S, G, nblocks);
+    gn_finalize_bwd<<<N, kGnFinThreads, 0, st>>>(partial, gamma, stats, coef, C, S, G, nblocks);
     int gxd = stream_grid(S * l.lpr, 256 * 4, kNumSMs * 8);
     gn_apply_bwd<<<dim3(gxd, N), 256, 3 * C * sizeof(float), st>>>((const float4*)gy, (const float4*)x,
                                                                    (const float4*)y, coef, (float4*)gx,

@@ -361,8 +361,11 @@ def attack_loss(cfg, outputs, disp_true, labels):
     loss = 0.
     if cfg.loss_disp:
         pred = outputs['depth_preds']
-        mask = (disp_true > cfg.min_depth) & (disp_true <= cfg.max_depth)
-        loss = loss + F.smooth_l1_loss(pred[mask], disp_true[mask], reduction='mean')
+        mask = ((disp_true > cfg.min_depth) & (disp_true <= cfg.max_depth)).to(pred.dtype)
+        # mean over the valid pixels, written without boolean indexing (no host sync -> the
+        # iteration stays CUDA-graph capturable); same value as smooth_l1(pred[mask], gt[mask]).mean()
+        per = F.smooth_l1_loss(pred, disp_true, reduction='none')
+        loss = loss + (per * mask).sum() / mask.sum().clamp_min(1.0)
     if cfg.RPN3D_ENABLE:
         cls, reg, ctr = outputs['bbox_cls'], outputs['bbox_reg'], outputs['bbox_centerness']
         tgt = labels['cls']

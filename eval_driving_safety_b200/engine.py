@@ -1,0 +1,71 @@
+"""CUDA-graph engine for the attack iteration.
+
+One PGD iteration of one stereo pair (forward, loss, backward to the pixels, fused pixel
+update) has static shapes, ~1,400 kernel launches and is host-launch-bound when issued from
+Python (measured: 55 ms eager vs the ~40 ms of kernel time).  The iteration is therefore captured
+ONCE into a CUDA graph over static buffers and replayed for every pair and every iteration
+(reference loop: attack/DSGN/pgd_attack.py:300-354).  All libb2attack kernels launch on the
+current torch stream and never synchronise, so they capture like any torch op; the TMA
+descriptors baked into the conv launches stay valid because graph-pool addresses are fixed.
+"""
+import torch
+
+from . import attack, dsgn, ops
+
+
+class PgdIterationGraph:
+    """step(xL, xR, cleanL, cleanR, disp) runs ONE PGD iteration in place on xL/xR ([1,3,H,W]
+    normalised images; clean* are the denormalised clean copies) and returns the loss (device
+    scalar, valid until the next step)."""
+
+    def __init__(self, model, cfg, labels, calib, alpha, eps, example, norm='linf', use_graph=True, warmup=2):
+        self.model, self.cfg, self.labels, self.calib = model, cfg, labels, calib
+        self.alpha, self.eps, self.norm = alpha, eps, norm
+        self.use_graph = use_graph
+        self.launches_per_step = None
+        xL, xR, cL, cR, disp = example
+        if not use_graph:
+            return
+        self.s = [t.clone() for t in (xL, xR, cL, cR, disp)]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):                      # cuDNN autotune, plan/pack caches, workspaces
+                self._iteration(*self.s)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        for dst, src in zip(self.s, (xL, xR, cL, cR, disp)):
+            dst.copy_(src)
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.LAUNCH_COUNT
+        with torch.cuda.graph(self.graph):
+            self.loss = self._iteration(*self.s)
+        self.launches_per_step = ops.LAUNCH_COUNT - n0
+        for dst, src in zip(self.s, (xL, xR, cL, cR, disp)):
+            dst.copy_(src)
+
+    def _iteration(self, xL, xR, cL, cR, disp):
+        a, b = xL.detach().requires_grad_(True), xR.detach().requires_grad_(True)
+        out = self.model(a, b, self.calib[0], self.calib[1], self.calib[2], calibs_Proj_R=self.calib[3])
+        loss = dsgn.attack_loss(self.cfg, out, disp, self.labels)
+        gL, gR = torch.autograd.grad(loss, [a, b])
+        if self.norm == 'linf':
+            attack.pgd_step_pair(xL, gL.contiguous(), cL, xR, gR.contiguous(), cR, self.alpha, self.eps, inplace=True)
+        else:
+            attack.pgd_step(xL, gL.contiguous(), cL, self.alpha, self.eps, norm=self.norm, out=xL)
+            attack.pgd_step(xR, gR.contiguous(), cR, self.alpha, self.eps, norm=self.norm, out=xR)
+        return loss.detach()
+
+    def step(self, xL, xR, cL, cR, disp):
+        if not self.use_graph:
+            n0 = ops.LAUNCH_COUNT
+            loss = self._iteration(xL, xR, cL, cR, disp)
+            self.launches_per_step = ops.LAUNCH_COUNT - n0
+            return loss
+        for dst, src in zip(self.s, (xL, xR, cL, cR, disp)):
+            dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        xL.copy_(self.s[0], non_blocking=True)
+        xR.copy_(self.s[1], non_blocking=True)
+        return self.loss
