@@ -24,6 +24,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION/INFO; stdout must stay one JSON line
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import torch
 
 EPS, ALPHA = 0.03, 0.03 / 4
@@ -104,10 +108,10 @@ def make_batch(cfg, pair_ids, pin=False):
 
 def run_b200(args):
     from eval_driving_safety_b200 import attack, dsgn, engine, ops, parallel, synthetic
-    rank, world = parallel.init()
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    rank, world = parallel.init(device=dev)
     torch.backends.cudnn.benchmark = True
     cfg = dsgn.default_cfg()
     model = dsgn.build_model(cfg, seed=1, device=dev)

@@ -12,12 +12,13 @@ import torch.distributed as dist
 STAT_FIELDS = ("pair", "loss_0", "loss_K", "linf", "l2", "frac_changed", "depth_err_clean", "depth_err_adv")
 
 
-def init(backend=None):
+def init(backend=None, device=None):
     """Initialise torch.distributed from the torchrun environment (no-op for 1 process)."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world > 1 and not dist.is_initialized():
         backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
-        dist.init_process_group(backend=backend)
+        kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
+        dist.init_process_group(backend=backend, **kw)
     return rank(), world_size()
 
 
