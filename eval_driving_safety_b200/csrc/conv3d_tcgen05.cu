@@ -410,42 +410,60 @@ conv3d_s1_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
+        // One thread issues 864 MMAs per super tile; each MMA occupies the tensor pipe for only
+        // 32 cycles, so the scalar code between MMAs must stay tiny: the plane / kd / kh loops are
+        // fully unrolled (accumulator index, first/last-use tests are compile-time) and the ring
+        // slots of the 9 weight tiles of a generation are resolved once per generation.
         if (lane == 0) {
             const uint32_t idesc = umma_idesc_tf32(128, p.nt);
-            uint32_t a_ord = 0, b_gen = 0;     // b_gen = tap ordinal of the current generation's first tap
+            uint32_t aslot = 0, aphase = 0;            // A ring position
+            uint32_t bslot0 = 0, bphase0 = 0;          // B ring position of the generation's first tap
             long long it = 0;
             for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
                 const int accbuf = (int)(it & 1);
                 mbar_wait(tempty(accbuf), (uint32_t)(((it >> 1) & 1) ^ 1));
                 tc_fence_after();
                 const uint32_t tmem_acc0 = tmem_base + (uint32_t)(accbuf * kS1Planes * p.nt);
-                for (int g = 0; g < ngen; ++g, b_gen += 9) {
-                    for (int pr = 0; pr < kS1Planes + 2; ++pr, ++a_ord) {
-                        const int aslot = a_ord % kS1NA;
-                        mbar_wait(fullA(aslot), (a_ord / kS1NA) & 1);
+                for (int g = 0; g < ngen; ++g) {
+                    uint64_t bdesc[9];
+                    uint32_t bfull[9], bempty[9], bpar[9];
+                    {
+                        uint32_t sl = bslot0, ph = bphase0;
+#pragma unroll
+                        for (int q = 0; q < 9; ++q) {
+                            bdesc[q] = umma_desc_sw128(b_base + sl * (uint32_t)p.b_bytes);
+                            bfull[q] = fullB(sl); bempty[q] = emptyB(sl); bpar[q] = ph;
+                            if (++sl == (uint32_t)p.nb) { sl = 0; ph ^= 1; }
+                        }
+                        bslot0 = sl; bphase0 = ph;
+                    }
+#pragma unroll
+                    for (int pr = 0; pr < kS1Planes + 2; ++pr) {
+                        mbar_wait(fullA(aslot), aphase);
                         tc_fence_after();
-                        const uint32_t sa = a_base + (uint32_t)aslot * kS1ABytes;
+                        const uint64_t adesc0 = umma_desc_sw128(a_base + aslot * (uint32_t)kS1ABytes);
+#pragma unroll
                         for (int kd = 0; kd < 3; ++kd) {
                             const int j = pr - kd;                 // accumulator = output plane d0 + j
                             if (j < 0 || j >= kS1Planes) continue;
+                            const uint32_t tmem_d = tmem_acc0 + (uint32_t)(j * p.nt);
+#pragma unroll
                             for (int kh = 0; kh < 3; ++kh) {
-                                const uint32_t b_ord = b_gen + kd * 3 + kh;
-                                const int bslot = b_ord % p.nb;
+                                const int q = kd * 3 + kh;
                                 if (j == 0) {                      // first use of this weight tile
-                                    mbar_wait(fullB(bslot), (b_ord / p.nb) & 1);
+                                    mbar_wait(bfull[q], bpar[q]);
                                     tc_fence_after();
                                 }
-                                const uint64_t adesc = umma_desc_sw128(sa + (uint32_t)kh * 1024u);
-                                const uint64_t bdesc = umma_desc_sw128(b_base + (uint32_t)bslot * p.b_bytes);
-                                const uint32_t tmem_d = tmem_acc0 + (uint32_t)(j * p.nt);
-                                const uint32_t first = (g | kd | kh);
+                                const uint64_t adesc = adesc0 + (uint64_t)(kh * (1024 >> 4));
+                                const uint32_t later = (uint32_t)g | (uint32_t)q;   // 0 only for the very first MMA group of acc j
 #pragma unroll
                                 for (int k = 0; k < kKChunk / 8; ++k)
-                                    umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (first | k) != 0);
-                                if (j == kS1Planes - 1) umma_commit(emptyB(bslot));   // last use of the tile
+                                    umma_tf32(tmem_d, adesc + 2 * k, bdesc[q] + 2 * k, idesc, (later | (uint32_t)k) != 0);
+                                if (j == kS1Planes - 1) umma_commit(bempty[q]);   // last use of the tile
                             }
                         }
                         umma_commit(emptyA(aslot));
+                        if (++aslot == kS1NA) { aslot = 0; aphase ^= 1; }
                     }
                 }
                 umma_commit(tfull(accbuf));

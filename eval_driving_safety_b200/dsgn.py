@@ -320,10 +320,7 @@ class StereoNet(nn.Module):
 
     def depth_head(self, cost1, img_hw):
         cfg = self.cfg
-        up = F.interpolate(cost1, [cfg.maxdisp, img_hw[0], img_hw[1]], mode='trilinear', align_corners=False)
-        prob = F.softmax(up.squeeze(1), 1)
-        z = full_depths(cfg, cost1.device).view(1, -1, 1, 1)
-        return (prob * z).sum(1)
+        return ops.depth_head(cost1, (cfg.maxdisp, img_hw[0], img_hw[1]), cfg.min_depth, cfg.depth_interval)
 
     def lift(self, out, rpn_feat, proj):
         grid3, plan3, plan2 = self._lift_plan(proj, out.shape[2:], rpn_feat.shape[2:], out.device)

@@ -513,6 +513,44 @@ def groupnorm_act(x, gamma, beta, groups, eps=1e-5, relu=False, res=None):
     return GroupNormActFn.apply(x, res, gamma, beta, groups, eps, relu)
 
 
+class DepthHeadFn(Function):
+    """cost1 [N,1,D,Hc,Wc] -> depth [N,H,W]: fused trilinear upsample + softmax + expectation."""
+
+    @staticmethod
+    def forward(ctx, cost1, size, z0, dz):
+        _need_cuda(cost1)
+        lib = _lib.load()
+        cost1 = cost1.contiguous()
+        n, _, d, hc, wc = cost1.shape
+        j, h, w = size
+        depth = torch.empty((n, h, w), device=cost1.device, dtype=torch.float32)
+        with _op("depth_head_fwd", 1, 4 * (cost1.numel() + depth.numel())):
+            check(lib.b2_depth_head_fwd(_p(cost1), _p(depth), n, d, hc, wc, h, w, j, float(z0), float(dz), _stream()),
+                  "depth_head_fwd")
+        ctx.save_for_backward(cost1)
+        ctx.cfg = (n, d, hc, wc, h, w, j, float(z0), float(dz))
+        return depth
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gdepth):
+        lib = _lib.load()
+        (cost1,) = ctx.saved_tensors
+        n, d, hc, wc, h, w, j, z0, dz = ctx.cfg
+        g = gdepth.contiguous()
+        gcost = torch.empty_like(cost1)
+        ws = torch.empty(lib.b2_depth_head_workspace_bytes(n, d, h, w), device=g.device, dtype=torch.uint8)
+        with _op("depth_head_bwd", 2, 4 * (cost1.numel() * 2 + g.numel()) + 2 * ws.numel()):
+            check(lib.b2_depth_head_bwd(_p(cost1), _p(g), _p(gcost), n, d, hc, wc, h, w, j, z0, dz, _p(ws), _stream()),
+                  "depth_head_bwd")
+        return gcost, None, None, None
+
+
+def depth_head(cost1, size, z0, dz):
+    """size = (maxdisp, H, W); plane depths z_j = z0 + (j + 0.5) * dz."""
+    return DepthHeadFn.apply(cost1, tuple(size), z0, dz)
+
+
 # ---------------------------------------------------------------------------
 # RoIAlign (Stereo R-CNN, config 5)
 # ---------------------------------------------------------------------------

@@ -179,6 +179,18 @@ int b2_groupnorm_bwd(const float* gy, const float* x, const float* y, const floa
                      const float* stats, float* gx, float* gres, int N, int C, int64_t S, int G,
                      int relu, void* workspace, void* stream);
 
+/* Depth head of the PSV branch (SURVEY 8f "next" row 1), fused and deterministic: trilinear
+ * upsample of the 1-channel cost volume cost [N,D,Hc,Wc] to (J,H,W) (align_corners=False),
+ * softmax over the J planes, expectation over z_j = z0 + (j+0.5)*dz  ->  depth [N,H,W].
+ * Replaces F.interpolate + F.softmax + (prob*z).sum of upstream StereoNet, whose output is read
+ * at attack/DSGN/pgd_attack.py:310-317.  bwd: gdepth [N,H,W] -> gcost [N,D,Hc,Wc];
+ * workspace b2_depth_head_workspace_bytes(N,D,H,W) bytes. */
+int b2_depth_head_fwd(const float* cost, float* depth, int N, int D, int Hc, int Wc, int H, int W,
+                      int J, float z0, float dz, void* stream);
+int64_t b2_depth_head_workspace_bytes(int N, int D, int H, int W);
+int b2_depth_head_bwd(const float* cost, const float* gdepth, float* gcost, int N, int D, int Hc, int Wc,
+                      int H, int W, int J, float z0, float dz, void* workspace, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * RoIAlign forward / deterministic backward (Stereo R-CNN, config 5) -- replaces
  * upstream model.roi_layers.ROIAlign constructed at

@@ -260,3 +260,27 @@ def test_conv3d_kitti_size_tcgen05_vs_fp32_kernel(ops):
     assert rel_err(ops.conv3d(xs, wt, 2, True, impl=0), ops.conv3d(xs, wt, 2, True, impl=1)) < 3e-3
     w2 = (torch.randn(128, 64, 3, 3, 3, generator=g) * 0.03).cuda()
     assert rel_err(ops.conv3d(x, w2, 2, False, impl=0), ops.conv3d(x, w2, 2, False, impl=1)) < 3e-3
+
+
+# ---------------------------------------------------------------- fused depth head
+@pytest.mark.parametrize("dims", [(1, 8, 8, 16, 4), (2, 12, 5, 7, 4), (1, 6, 9, 11, 2)])
+def test_depth_head_vs_torch(ops, dims):
+    """trilinear upsample (align_corners=False) + softmax + expectation, fwd and deterministic bwd."""
+    n, d, hc, wc, f = dims
+    g = torch.Generator().manual_seed(sum(dims))
+    cost = (torch.randn(n, 1, d, hc, wc, generator=g) * 3).requires_grad_(True)
+    J, H, W = d * f, hc * f, wc * f
+    z0, dz = 2.0, 0.2
+    up = F.interpolate(cost, [J, H, W], mode='trilinear', align_corners=False)
+    prob = F.softmax(up.squeeze(1), 1)
+    z = (z0 + (torch.arange(J, dtype=torch.float32) + 0.5) * dz).view(1, -1, 1, 1)
+    ref = (prob * z).sum(1)
+    gy = torch.randn(ref.shape, generator=g)
+    (gc_ref,) = torch.autograd.grad(ref, cost, gy)
+    cc = cost.detach().cuda().requires_grad_(True)
+    out = ops.depth_head(cc, (J, H, W), z0, dz)
+    assert out.shape == ref.shape and max_err(out.cpu(), ref) < 2e-5
+    (gc,) = torch.autograd.grad(out, cc, gy.cuda())
+    assert max_err(gc.cpu(), gc_ref) < 2e-5
+    (gc2,) = torch.autograd.grad(ops.depth_head(cc, (J, H, W), z0, dz), cc, gy.cuda())
+    assert torch.equal(gc, gc2)
