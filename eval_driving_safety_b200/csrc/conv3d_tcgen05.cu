@@ -33,9 +33,11 @@ constexpr int kMaxStages = 8;
 
 struct TcParams {
     int N, Cin, Cout;
-    int Dt, Ht, Wt;            // extents of the tile grid space (conv: output dims; deconv: input dims)
+    int Dt, Ht, Wt;            // extents of the tile grid space in ROLE order (planes, rows, w)
+                               // (conv: output dims; deconv: input dims)
     int Do, Ho, Wo;            // output dims
     int mode;                  // 0 conv s1, 1 conv s2, 2 deconv s2
+    int swap;                  // 0: tile rows run along H, planes along D; 1: rows along D, planes along H
     int tiles_w, tiles_h;
     int kchunks;               // Cin / 32
     int stages;
@@ -186,19 +188,22 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 const int pw = tc.cls & 1, ph = (tc.cls >> 1) & 1, pd = (tc.cls >> 2) & 1;
                 for (int tap_i = 0; tap_i < ntaps; ++tap_i) {
                     int aw, ah, ad, tap;
+                    // kd / kh below are the taps along the PLANE / ROW roles
+                    int kw, kh, kd;
                     if (p.mode == 0) {
-                        int kd = tap_i / 9, kh = (tap_i / 3) % 3, kw = tap_i % 3;
-                        aw = tc.w0 + kw - 1; ah = tc.h0 + kh - 1; ad = tc.d + kd - 1; tap = tap_i;
+                        kd = tap_i / 9; kh = (tap_i / 3) % 3; kw = tap_i % 3;
+                        aw = tc.w0 + kw - 1; ah = tc.h0 + kh - 1; ad = tc.d + kd - 1;
                     } else if (p.mode == 1) {
-                        int kd = tap_i / 9, kh = (tap_i / 3) % 3, kw = tap_i % 3;
-                        aw = 2 * tc.w0 + kw - 1; ah = 2 * tc.h0 + kh - 1; ad = 2 * tc.d + kd - 1; tap = tap_i;
+                        kd = tap_i / 9; kh = (tap_i / 3) % 3; kw = tap_i % 3;
+                        aw = 2 * tc.w0 + kw - 1; ah = 2 * tc.h0 + kh - 1; ad = 2 * tc.d + kd - 1;
                     } else {
                         int nw = 1 + pw, nh = 1 + ph;
                         int jw = tap_i % nw, jh = (tap_i / nw) % nh, jd = tap_i / (nw * nh);
-                        int kw, kh, kd, sw, sh, sd;
+                        int sw, sh, sd;
                         deconv_axis(pw, jw, kw, sw); deconv_axis(ph, jh, kh, sh); deconv_axis(pd, jd, kd, sd);
-                        aw = tc.w0 + sw; ah = tc.h0 + sh; ad = tc.d + sd; tap = (kd * 3 + kh) * 3 + kw;
+                        aw = tc.w0 + sw; ah = tc.h0 + sh; ad = tc.d + sd;
                     }
+                    tap = p.swap ? (kh * 3 + kd) * 3 + kw : (kd * 3 + kh) * 3 + kw;   // weights are [kD][kH][kW]
                     for (int kc = 0; kc < p.kchunks; ++kc) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
                         mbar_expect_tx(full_bar(stage), tx);
@@ -253,14 +258,13 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             TileCoord tc = decode_tile(p, t);
             const int h = tc.h0 + hl, w = tc.w0 + wl;
             const bool ok = h < p.Ht && w < p.Wt;
-            long long vox;
+            int op = tc.d, orow = h, ow = w;                       // plane / row / w coordinates of the output
             if (p.mode == 2) {
-                int od = 2 * tc.d + ((tc.cls >> 2) & 1), oh = 2 * h + ((tc.cls >> 1) & 1), ow = 2 * w + (tc.cls & 1);
-                vox = (((long long)tc.n * p.Do + od) * p.Ho + oh) * p.Wo + ow;
-            } else {
-                vox = (((long long)tc.n * p.Do + tc.d) * p.Ho + h) * p.Wo + w;
+                op = 2 * tc.d + ((tc.cls >> 2) & 1); orow = 2 * h + ((tc.cls >> 1) & 1); ow = 2 * w + (tc.cls & 1);
             }
-            float* orow = out + vox * p.Cout;
+            const int od = p.swap ? orow : op, oh = p.swap ? op : orow;
+            const long long vox = (((long long)tc.n * p.Do + od) * p.Ho + oh) * p.Wo + ow;
+            float* optr = out + vox * p.Cout;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.Cout);
@@ -273,7 +277,7 @@ conv3d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     for (int j = 0; j < 8; ++j) {
                         float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
                                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-                        *reinterpret_cast<float4*>(orow + c0 + 4 * j) = v;
+                        *reinterpret_cast<float4*>(optr + c0 + 4 * j) = v;
                     }
                 }
             }
@@ -313,6 +317,7 @@ constexpr int kS1MaxNB = 18;                           // B ring slots (>= 9)
 
 struct S1Params {
     int N, Cin, Cout, D, H, W;
+    int P, R, swap;            // planes / rows extents in role order; swap = rows along D, planes along H
     int nt, n_tiles;           // N tile width, number of N tiles
     int tiles_w, tiles_h, dblocks;
     int kchunks;
@@ -393,7 +398,7 @@ conv3d_s1_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                                 const int slot = b_ord % p.nb;
                                 mbar_wait(emptyB(slot), ((b_ord / p.nb) & 1) ^ 1);
                                 mbar_expect_tx(fullB(slot), (uint32_t)p.b_bytes);
-                                const int tap = (pr * 3 + kh) * 3 + kw;
+                                const int tap = p.swap ? (kh * 3 + pr) * 3 + kw : (pr * 3 + kh) * 3 + kw;
                                 tma_load_2d(b_base + (uint32_t)slot * p.b_bytes, &map_b, fullB(slot), kc * kKChunk,
                                             tap * p.Cout + tc.nti * p.nt);
                             }
@@ -479,13 +484,14 @@ conv3d_s1_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
             const int accbuf = (int)(it & 1);
             S1Tile tc = s1_decode(p, t);
-            const int h = tc.h0 + hl, w = tc.w0 + wl;
-            const bool ok_hw = h < p.H && w < p.W;
+            const int r = tc.h0 + hl, w = tc.w0 + wl;
+            const bool ok_hw = r < p.R && w < p.W;
             mbar_wait(tfull(accbuf), (uint32_t)((it >> 1) & 1));
             tc_fence_after();
             for (int j = 0; j < kS1Planes; ++j) {
-                const int d = tc.d0 + j;
-                const bool ok = ok_hw && d < p.D;
+                const int pl = tc.d0 + j;
+                const bool ok = ok_hw && pl < p.P;
+                const int d = p.swap ? r : pl, h = p.swap ? pl : r;
                 float* orow = out + ((((long long)tc.n * p.D + d) * p.H + h) * p.W + w) * p.Cout + tc.nti * p.nt;
                 const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) +
                                        (uint32_t)((accbuf * kS1Planes + j) * p.nt);
@@ -551,9 +557,17 @@ static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* 
     p.N = N; p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W;
     p.nt = Cout <= 64 ? Cout : Cout / 2;
     p.n_tiles = Cout / p.nt;
+    {
+        auto padded = [](int rows, int planes) {
+            return (long long)((rows + kTileH - 1) / kTileH) * kTileH * ((planes + kS1Planes - 1) / kS1Planes) * kS1Planes;
+        };
+        p.swap = padded(D, H) < padded(H, D) ? 1 : 0;
+        p.R = p.swap ? D : H;
+        p.P = p.swap ? H : D;
+    }
     p.tiles_w = (W + kTileW - 1) / kTileW;
-    p.tiles_h = (H + kTileH - 1) / kTileH;
-    p.dblocks = (D + kS1Planes - 1) / kS1Planes;
+    p.tiles_h = (p.R + kTileH - 1) / kTileH;
+    p.dblocks = (p.P + kS1Planes - 1) / kS1Planes;
     p.kchunks = Cin / kKChunk;
     p.b_bytes = p.nt * 128;
     p.nb = (216 * 1024 - kS1NA * kS1ABytes) / p.b_bytes;
@@ -567,6 +581,10 @@ static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* 
         cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
         cuuint64_t gstr[4] = {(cuuint64_t)Cin * 4, (cuuint64_t)W * Cin * 4, (cuuint64_t)H * W * Cin * 4,
                               (cuuint64_t)D * H * W * Cin * 4};
+        if (p.swap) {   // tensor-map dim 2 = rows = D, dim 3 = planes = H
+            gdim[2] = (cuuint64_t)D; gdim[3] = (cuuint64_t)H;
+            gstr[1] = (cuuint64_t)H * W * Cin * 4; gstr[2] = (cuuint64_t)W * Cin * 4;
+        }
         cuuint32_t box[5] = {(cuuint32_t)kKChunk, (cuuint32_t)kTileW, (cuuint32_t)kTileH + 2, 1, 1};
         cuuint32_t estr[5] = {1, 1, 1, 1, 1};
         CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in, gdim, gstr, box, estr,
@@ -618,7 +636,17 @@ int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, i
     TcParams p{};
     p.N = N; p.Cin = Cin; p.Cout = Cout; p.Do = Do; p.Ho = Ho; p.Wo = Wo;
     p.mode = (mode == 1) ? 2 : (stride == 2 ? 1 : 0);
-    if (p.mode == 2) { p.Dt = Di; p.Ht = Hi; p.Wt = Wi; } else { p.Dt = Do; p.Ht = Ho; p.Wt = Wo; }
+    {
+        // tile rows (16) run along H or D, whichever wastes fewer padded voxels (e.g. the 192x20x304
+        // voxel grid tiles perfectly with rows along Z=192 but wastes 37 % with rows along Y=20)
+        const int td = (p.mode == 2) ? Di : Do, th = (p.mode == 2) ? Hi : Ho;
+        const long long cost_h = (long long)((th + kTileH - 1) / kTileH) * kTileH * td;
+        const long long cost_d = (long long)((td + kTileH - 1) / kTileH) * kTileH * th;
+        p.swap = cost_d < cost_h ? 1 : 0;
+        p.Wt = (p.mode == 2) ? Wi : Wo;
+        p.Dt = p.swap ? th : td;
+        p.Ht = p.swap ? td : th;
+    }
     p.tiles_w = (p.Wt + kTileW - 1) / kTileW;
     p.tiles_h = (p.Ht + kTileH - 1) / kTileH;
     p.kchunks = Cin / kKChunk;
@@ -634,6 +662,10 @@ int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, i
         cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)N};
         cuuint64_t gstr[4] = {(cuuint64_t)Cin * 4, (cuuint64_t)Wi * Cin * 4, (cuuint64_t)Hi * Wi * Cin * 4,
                               (cuuint64_t)Di * Hi * Wi * Cin * 4};
+        if (p.swap) {   // tensor-map dim 2 = rows = D, dim 3 = planes = H
+            gdim[2] = (cuuint64_t)Di; gdim[3] = (cuuint64_t)Hi;
+            gstr[1] = (cuuint64_t)Hi * Wi * Cin * 4; gstr[2] = (cuuint64_t)Wi * Cin * 4;
+        }
         const cuuint32_t s = (p.mode == 1) ? 2 : 1;
         // traversal box; with element stride s the box lands ceil(box/s) elements per dim in smem
         cuuint32_t box[5] = {(cuuint32_t)kKChunk, (cuuint32_t)kTileW * s, (cuuint32_t)kTileH * s, s, 1};

@@ -22,9 +22,9 @@ struct GnLayout {
     int threads;  // lpr * rpb
 };
 
-// partial blocks per sample: at least ~128 rows each, at most two per SM
+// partial blocks per sample: at least ~512 rows each, at most two per SM
 static int gn_nblocks(int64_t S) {
-    int64_t nb = (S + 127) / 128;
+    int64_t nb = (S + 511) / 512;
     if (nb < 1) nb = 1;
     if (nb > kGnBlocks) nb = kGnBlocks;
     return (int)nb;
@@ -92,7 +92,6 @@ __global__ void gn_partials_kernel(const float4* __restrict__ a, const float4* _
 // Sum the per-block partials of channel c: `lanes` = 1024 / C threads per channel each add every
 // lanes-th partial in order, then the lanes are combined in lane order -> fixed summation order.
 constexpr int kGnFinThreads = 1024;
-constexpr int kGnLanes = 4;       // minimum lanes per channel (C = 256)
 
 __device__ __forceinline__ void gn_sum_partials(const float* __restrict__ partial, int n, int nblocks, int C,
                                                 double* s1, double* s2, double* sh /* [2][1024] */) {
@@ -100,10 +99,20 @@ __device__ __forceinline__ void gn_sum_partials(const float* __restrict__ partia
     const int c = threadIdx.x % C, l = threadIdx.x / C;
     double a = 0.0, b = 0.0;
     if (l < lanes) {
-        for (int k = l; k < nblocks; k += lanes) {
-            const float* p = partial + (((int64_t)n * nblocks + k) * 2) * C;
-            a += (double)__ldg(p + c);
-            b += (double)__ldg(p + C + c);
+        const float* base = partial + ((int64_t)n * nblocks * 2) * C + c;
+        const int64_t step = (int64_t)2 * C;
+        int k = l;
+        for (; k + 3 * lanes < nblocks; k += 4 * lanes) {         // 8 independent loads in flight
+            float a0 = __ldg(base + (k) * step), b0 = __ldg(base + (k) * step + C);
+            float a1 = __ldg(base + (k + lanes) * step), b1 = __ldg(base + (k + lanes) * step + C);
+            float a2 = __ldg(base + (k + 2 * lanes) * step), b2 = __ldg(base + (k + 2 * lanes) * step + C);
+            float a3 = __ldg(base + (k + 3 * lanes) * step), b3 = __ldg(base + (k + 3 * lanes) * step + C);
+            a += (double)a0; a += (double)a1; a += (double)a2; a += (double)a3;
+            b += (double)b0; b += (double)b1; b += (double)b2; b += (double)b3;
+        }
+        for (; k < nblocks; k += lanes) {
+            a += (double)__ldg(base + k * step);
+            b += (double)__ldg(base + k * step + C);
         }
     }
     sh[threadIdx.x] = a; sh[kGnFinThreads + threadIdx.x] = b;

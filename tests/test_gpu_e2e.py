@@ -162,3 +162,40 @@ def test_pgd_attack_final_perturbation(setup):
     same = ((dL - dL_ref).abs() < 1e-6).float().mean().item()
     assert same > 0.98, same
     assert losses.shape == (K,)
+
+
+def test_patch_attack_loop_matches_oracle(setup):
+    """Universal-patch inner loop (attack/DSGN/patch_attack.py:367-430) on the tiny model: blend,
+    forward/backward, crop, clipped descent -- product kernels vs the oracle's restatement; and the
+    multi-GPU form (delta hook, world = 1) reproduces the sequential update exactly."""
+    from eval_driving_safety_b200 import attack, dsgn, ops, parallel
+    s = setup
+    ops.set_conv_impl(1)
+    radius = 3
+    dim = 2 * radius + 1
+    g = torch.Generator().manual_seed(9)
+    patch0 = torch.randn(1, 3, dim, dim, generator=g) * 0.5
+    cl, cr = [16, 40], [16, 30]
+    alpha, eps, iters = 1e3, 8 / 255, 2
+    # oracle loop
+    patch_r = patch0.clone()
+    imgL, imgR = s["pair"]["imgL"].clone(), s["pair"]["imgR"].clone()
+    for _ in range(iters):
+        imgL = A.patch_apply(imgL, patch_r, cl, radius)
+        imgR = A.patch_apply(imgR, patch_r, cr, radius)
+        _, _, gL, gR = _ref_grads(s, imgL, imgR)
+        patch_r = A.patch_update(patch_r, gL, gR, cl, cr, radius, alpha, eps)
+    # product loop
+    labels = {k: v.cuda() for k, v in s["labels"].items()}
+    disp = s["pair"]["disp_L"].cuda()
+    loss_fn = lambda out: dsgn.attack_loss(s["cfg_p"], out, disp, labels)
+    for hook in (None, parallel.allreduce_patch_delta):
+        patch_g = patch0.clone().cuda()
+        xl, xr = s["pair"]["imgL"].cuda().clone(), s["pair"]["imgR"].cuda().clone()
+        patch_g, losses = attack.patch_attack_step(s["model"], loss_fn, xl, xr, s["calib"], patch_g, cl, cr, radius,
+                                                   iters=iters, alpha=alpha, eps=eps, delta_hook=hook)
+        # the step is clipped to +-eps: entries agree wherever the (tiny) gradient difference does not
+        # move a value across the clip boundary; everything else is within fp32 noise of alpha*grad
+        assert (patch_g.cpu() - patch_r).abs().max() < 2e-3
+        assert ((patch_g.cpu() - patch_r).abs() < 1e-5).float().mean() > 0.9
+        assert losses.shape == (iters,)

@@ -213,7 +213,10 @@ def test_pyramid_roi_dispatch_matches_oracle(ops):
 # ---------------------------------------------------------------- conv3d, tensor-core path
 TC_CASES = [c for c in CONV_CASES if c[0] % 32 == 0 and c[1] % 32 == 0] + [
     (64, 64, 1, False, (3, 20, 19)), (64, 96, 1, False, (2, 5, 9)), (64, 128, 2, False, (6, 36, 20)),
-    (128, 64, 2, True, (3, 18, 10))]
+    (128, 64, 2, True, (3, 18, 10)),
+    # D >> H: the kernels put the 16-row tile dimension along D instead of H ("role swap")
+    (64, 64, 1, False, (20, 5, 9)), (96, 64, 1, False, (33, 3, 8)), (64, 128, 2, False, (32, 6, 8)),
+    (128, 64, 2, True, (16, 3, 5))]
 
 
 @pytest.mark.parametrize("case", TC_CASES)
