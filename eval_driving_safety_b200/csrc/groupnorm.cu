@@ -22,9 +22,9 @@ struct GnLayout {
     int threads;  // lpr * rpb
 };
 
-// partial blocks per sample: at least ~512 rows each, at most two per SM
+// partial blocks per sample: at least ~256 rows each, at most two (512-thread blocks) per SM
 static int gn_nblocks(int64_t S) {
-    int64_t nb = (S + 511) / 512;
+    int64_t nb = (S + 255) / 256;
     if (nb < 1) nb = 1;
     if (nb > kGnBlocks) nb = kGnBlocks;
     return (int)nb;
@@ -33,7 +33,7 @@ static int gn_nblocks(int64_t S) {
 static GnLayout gn_layout(int C) {
     GnLayout l;
     l.lpr = C / 4;
-    l.rpb = 256 / l.lpr;
+    l.rpb = 512 / l.lpr;
     if (l.rpb < 1) l.rpb = 1;
     l.threads = l.lpr * l.rpb;
     return l;
@@ -56,22 +56,40 @@ __global__ void gn_partials_kernel(const float4* __restrict__ a, const float4* _
     const int64_t s_end = min(S, s_begin + rows_per_block);
     const int64_t base = (int64_t)n * S * lpr;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f), q = p;
-    for (int64_t s = s_begin + r; s < s_end; s += rpb) {
-        int64_t i = base + s * lpr + lane;
+    auto accum = [&](float4 g, float4 v, float4 o) {
         if (MODE == 0) {
-            float4 v = ldg_stream(x + i);
             p.x += v.x; p.y += v.y; p.z += v.z; p.w += v.w;
             q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
         } else {
-            float4 g = __ldg(a + i), v = __ldg(x + i);
             if (relu) {
-                float4 o = __ldg(y + i);
                 g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
                 g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
             }
             p.x += g.x * v.x; p.y += g.y * v.y; p.z += g.z * v.z; p.w += g.w * v.w;
             q.x += g.x; q.y += g.y; q.z += g.z; q.w += g.w;
         }
+    };
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int64_t s = s_begin + r;
+    // 4 rows per trip: all loads are issued before the first use (memory-level parallelism)
+    for (; s + 3 * (int64_t)rpb < s_end; s += 4 * (int64_t)rpb) {
+        float4 vv[4], gg[4], oo[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int64_t i = base + (s + (int64_t)u * rpb) * lpr + lane;
+            vv[u] = ldg_stream(x + i);
+            gg[u] = MODE == 1 ? ldg_stream(a + i) : zero4;
+            oo[u] = (MODE == 1 && relu) ? ldg_stream(y + i) : zero4;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) accum(gg[u], vv[u], oo[u]);
+    }
+    for (; s < s_end; s += rpb) {
+        int64_t i = base + s * lpr + lane;
+        float4 v = ldg_stream(x + i);
+        float4 g = MODE == 1 ? ldg_stream(a + i) : zero4;
+        float4 o = (MODE == 1 && relu) ? ldg_stream(y + i) : zero4;
+        accum(g, v, o);
     }
     sh[r * lpr + lane] = p;
     sh[(rpb + r) * lpr + lane] = q;

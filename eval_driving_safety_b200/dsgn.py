@@ -330,9 +330,7 @@ class StereoNet(nn.Module):
         cfg = self.cfg
         v = run_convbn_3d(self.rpn3d_conv[0], vox, relu=True)
         v = self.rpn3d_hg(v, res=v)
-        v = F.avg_pool3d(v, (1, cfg.y_pool, 1))
-        n, c, zz, yy, xx = v.shape
-        bev = v.permute(0, 1, 3, 2, 4).reshape(n, c * yy, zz, xx).contiguous(memory_format=torch.channels_last)
+        bev = ops.bev_pool(v, cfg.y_pool)          # AvgPool3d over Y + (C, Y/p) -> channels, one pass
         bev = run_convbn_2d(self.bev_conv[0], bev, relu=True)
         bev = run_convbn_2d(self.bev_conv[2], bev, relu=True)
         return self.bbox_cls(bev), self.bbox_reg(bev), self.bbox_centerness(bev)

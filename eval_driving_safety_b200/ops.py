@@ -513,6 +513,38 @@ def groupnorm_act(x, gamma, beta, groups, eps=1e-5, relu=False, res=None):
     return GroupNormActFn.apply(x, res, gamma, beta, groups, eps, relu)
 
 
+class BevPoolFn(Function):
+    """[N,C,Z,Y,X] volume -> [N, C*(Y/p), Z, X] BEV map (channel = c*(Y/p)+yy), both channels-last:
+    F.avg_pool3d(v, (1,p,1)).permute(0,1,3,2,4).reshape(n, c*yy, z, x) in one pass."""
+
+    @staticmethod
+    def forward(ctx, v, p):
+        _need_cuda(v)
+        lib = _lib.load()
+        v = cl3(v)
+        n, c, z, y, x = v.shape
+        bev = empty_cl2(n, c * (y // p), z, x, v.device)
+        with _op("bev_pool_fwd", 1, 4 * (v.numel() + bev.numel())):
+            check(lib.b2_bev_pool_fwd(_p(v), _p(bev), n, c, z, y, x, p, _stream()), "bev_pool_fwd")
+        ctx.cfg = (n, c, z, y, x, p)
+        return bev
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        lib = _lib.load()
+        n, c, z, y, x, p = ctx.cfg
+        g = cl2(g)
+        gv = empty_cl3(n, c, z, y, x, g.device)
+        with _op("bev_pool_bwd", 1, 4 * (g.numel() + gv.numel())):
+            check(lib.b2_bev_pool_bwd(_p(g), _p(gv), n, c, z, y, x, p, _stream()), "bev_pool_bwd")
+        return gv, None
+
+
+def bev_pool(v, p):
+    return BevPoolFn.apply(v, p)
+
+
 class DepthHeadFn(Function):
     """cost1 [N,1,D,Hc,Wc] -> depth [N,H,W]: fused trilinear upsample + softmax + expectation."""
 

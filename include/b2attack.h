@@ -179,6 +179,12 @@ int b2_groupnorm_bwd(const float* gy, const float* x, const float* y, const floa
                      const float* stats, float* gx, float* gres, int N, int C, int64_t S, int G,
                      int relu, void* workspace, void* stream);
 
+/* Voxel -> BEV hand-off: AvgPool3d((1,p,1)) over the height axis + fold (C, Y/p) into channels
+ * (upstream StereoNet, behind attack/DSGN/pgd_attack.py:308/:336).  v [N,Z,Y,X,C] channels-last ->
+ * bev [N,Z,X,C*(Y/p)] channels-last with channel = c*(Y/p) + yy; bwd is the exact adjoint. */
+int b2_bev_pool_fwd(const float* v, float* bev, int N, int C, int Z, int Y, int X, int p, void* stream);
+int b2_bev_pool_bwd(const float* gbev, float* gv, int N, int C, int Z, int Y, int X, int p, void* stream);
+
 /* Depth head of the PSV branch (SURVEY 8f "next" row 1), fused and deterministic: trilinear
  * upsample of the 1-channel cost volume cost [N,D,Hc,Wc] to (J,H,W) (align_corners=False),
  * softmax over the J planes, expectation over z_j = z0 + (j+0.5)*dz  ->  depth [N,H,W].

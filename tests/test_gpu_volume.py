@@ -287,3 +287,19 @@ def test_depth_head_vs_torch(ops, dims):
     assert max_err(gc.cpu(), gc_ref) < 2e-5
     (gc2,) = torch.autograd.grad(ops.depth_head(cc, (J, H, W), z0, dz), cc, gy.cuda())
     assert torch.equal(gc, gc2)
+
+
+def test_bev_pool_vs_torch(ops):
+    g = torch.Generator().manual_seed(31)
+    v = torch.randn(2, 64, 6, 8, 5, generator=g, requires_grad=True)
+    for p in (2, 4):
+        t = F.avg_pool3d(v, (1, p, 1))
+        n, c, zz, yy, xx = t.shape
+        ref = t.permute(0, 1, 3, 2, 4).reshape(n, c * yy, zz, xx)
+        gy = torch.randn(ref.shape, generator=g)
+        (gv_ref,) = torch.autograd.grad(ref, v, gy)
+        vc = v.detach().cuda().requires_grad_(True)
+        out = ops.bev_pool(vc, p)
+        assert out.shape == ref.shape and max_err(out.cpu(), ref) < 1e-6
+        (gv,) = torch.autograd.grad(out, vc, gy.cuda())
+        assert max_err(gv.cpu(), gv_ref) < 1e-6
