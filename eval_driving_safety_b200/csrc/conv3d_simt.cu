@@ -116,70 +116,106 @@ conv3d_simt_kernel(const float* __restrict__ in, const float* __restrict__ wp,
 }
 
 // ---------------------------------------------------------------------------
-// Cout == 1 head.  LPV = Cin/4 lanes per voxel.
+// Cout == 1 head (classif1's last layer) and its data gradient.  Bandwidth-bound by
+// construction (368 MB in / 5.75 MB out per KITTI pair); the work is arranged so that the
+// 64-channel volume is streamed exactly once, fully coalesced:
+//   fwd  pass A: one thread per voxel of a 128-voxel tile (32 KB contiguous, staged in smem)
+//                computes the 27 tap products P[t][v] = x[v] . w[t]   (tap-major scratch)
+//        pass B: out[o] = sum_t P[t][o + off_t]  (27 coalesced reads per output voxel)
+//   dgrad      : one thread per voxel gathers its 27 g values, forms the 64-channel row in
+//                registers/smem and the block stores the 32 KB tile coalesced.
+// Cin is a template parameter (C4 = Cin/4 float4 per voxel row).
 // ---------------------------------------------------------------------------
-template <int LPV>
-__global__ void __launch_bounds__(256)
-conv3d_c1_fwd_kernel(const float4* __restrict__ in, const float4* __restrict__ w1,
-                     float* __restrict__ out, int N, int D, int H, int W) {
-    __shared__ float4 ws[27 * LPV];
-    for (int i = threadIdx.x; i < 27 * LPV; i += blockDim.x) ws[i] = w1[i];
+constexpr int kC1Tile = 128;
+
+template <int C4>
+__global__ void __launch_bounds__(kC1Tile)
+conv3d_c1_partial_kernel(const float4* __restrict__ in, const float4* __restrict__ w1, float* __restrict__ P,
+                         int64_t nvox) {
+    __shared__ float4 xs[kC1Tile][C4 + 1];
+    __shared__ float4 ws[27 * C4];
+    for (int i = threadIdx.x; i < 27 * C4; i += kC1Tile) ws[i] = w1[i];
+    const int64_t v0 = (int64_t)blockIdx.x * kC1Tile;
+    for (int i = threadIdx.x; i < kC1Tile * C4; i += kC1Tile) {
+        int64_t gi = v0 * C4 + i;
+        xs[i / C4][i % C4] = gi < nvox * C4 ? ldg_stream(in + gi) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __syncthreads();
-    const int lane = threadIdx.x % LPV;
-    const int64_t nvox = (int64_t)N * D * H * W;
-    const int64_t vstride = (int64_t)gridDim.x * (blockDim.x / LPV);
-    // all lanes of a warp iterate the same number of times (shuffles below)
-    const int64_t vbase0 = (int64_t)blockIdx.x * (blockDim.x / LPV);
-    for (int64_t vb = vbase0; vb < nvox; vb += vstride) {
-        int64_t v = vb + threadIdx.x / LPV;
-        bool ok = v < nvox;
-        float acc = 0.f;
-        if (ok) {
-            int w = (int)(v % W), h = (int)((v / W) % H), d = (int)((v / ((int64_t)W * H)) % D);
-            int n = (int)(v / ((int64_t)W * H * D));
-            const float4* base = in + (int64_t)n * D * H * W * LPV + lane;
+    float acc[27];
 #pragma unroll
-            for (int tap = 0; tap < 27; ++tap) {
-                int id = d + tap / 9 - 1, ih = h + (tap / 3) % 3 - 1, iw = w + tap % 3 - 1;
-                if (id >= 0 && id < D && ih >= 0 && ih < H && iw >= 0 && iw < W) {
-                    float4 x = __ldg(base + (((int64_t)id * H + ih) * W + iw) * LPV);
-                    float4 k = ws[tap * LPV + lane];
-                    acc += x.x * k.x + x.y * k.y + x.z * k.z + x.w * k.w;
-                }
-            }
+    for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+#pragma unroll 2
+    for (int c = 0; c < C4; ++c) {
+        const float4 x = xs[threadIdx.x][c];
+#pragma unroll
+        for (int t = 0; t < 27; ++t) {
+            const float4 k = ws[t * C4 + c];
+            acc[t] = fmaf(x.x, k.x, fmaf(x.y, k.y, fmaf(x.z, k.z, fmaf(x.w, k.w, acc[t]))));
         }
+    }
+    const int64_t v = v0 + threadIdx.x;
+    if (v < nvox) {
 #pragma unroll
-        for (int o = LPV / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (ok && lane == 0) out[v] = acc;
+        for (int t = 0; t < 27; ++t) P[(int64_t)t * nvox + v] = acc[t];
     }
 }
 
-template <int LPV>
 __global__ void __launch_bounds__(256)
-conv3d_c1_dgrad_kernel(const float* __restrict__ gout, const float4* __restrict__ w1,
-                       float4* __restrict__ gin, int N, int D, int H, int W) {
-    __shared__ float4 ws[27 * LPV];
-    for (int i = threadIdx.x; i < 27 * LPV; i += blockDim.x) ws[i] = w1[i];
-    __syncthreads();
-    const int lane = threadIdx.x % LPV;
+conv3d_c1_gather_kernel(const float* __restrict__ P, float* __restrict__ out, int N, int D, int H, int W) {
     const int64_t nvox = (int64_t)N * D * H * W;
-    const int64_t vstride = (int64_t)gridDim.x * (blockDim.x / LPV);
-    for (int64_t v = (int64_t)blockIdx.x * (blockDim.x / LPV) + threadIdx.x / LPV; v < nvox; v += vstride) {
-        int w = (int)(v % W), h = (int)((v / W) % H), d = (int)((v / ((int64_t)W * H)) % D);
-        int n = (int)(v / ((int64_t)W * H * D));
-        const float* gb = gout + (int64_t)n * D * H * W;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(v % W), h = (int)((v / W) % H), d = (int)((v / ((int64_t)W * H)) % D);
+        float acc = 0.f;
 #pragma unroll
-        for (int tap = 0; tap < 27; ++tap) {
-            // gin[i] = sum_k gout[i - k + 1] * w[k]
-            int od = d - (tap / 9) + 1, oh = h - ((tap / 3) % 3) + 1, ow = w - (tap % 3) + 1;
-            if (od >= 0 && od < D && oh >= 0 && oh < H && ow >= 0 && ow < W) {
-                float g = __ldg(gb + ((int64_t)od * H + oh) * W + ow);
-                float4 k = ws[tap * LPV + lane];
-                acc.x += g * k.x; acc.y += g * k.y; acc.z += g * k.z; acc.w += g * k.w;
-            }
+        for (int t = 0; t < 27; ++t) {
+            const int dd = t / 9 - 1, dh = (t / 3) % 3 - 1, dw = t % 3 - 1;
+            const int id = d + dd, ih = h + dh, iw = w + dw;
+            if (id >= 0 && id < D && ih >= 0 && ih < H && iw >= 0 && iw < W)
+                acc += __ldg(P + (int64_t)t * nvox + v + ((int64_t)dd * H + dh) * W + dw);
         }
-        stg_stream(gin + v * LPV + lane, acc);
+        out[v] = acc;
+    }
+}
+
+template <int C4>
+__global__ void __launch_bounds__(kC1Tile)
+conv3d_c1_dgrad_kernel(const float* __restrict__ gout, const float4* __restrict__ w1, float4* __restrict__ gin,
+                       int N, int D, int H, int W) {
+    __shared__ float4 os[kC1Tile][C4 + 1];
+    __shared__ float4 ws[27 * C4];
+    for (int i = threadIdx.x; i < 27 * C4; i += kC1Tile) ws[i] = w1[i];
+    const int64_t nvox = (int64_t)N * D * H * W;
+    const int64_t v0 = (int64_t)blockIdx.x * kC1Tile;
+    const int64_t v = v0 + threadIdx.x;
+    float g[27];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) g[t] = 0.f;
+    if (v < nvox) {
+        const int w = (int)(v % W), h = (int)((v / W) % H), d = (int)((v / ((int64_t)W * H)) % D);
+#pragma unroll
+        for (int t = 0; t < 27; ++t) {
+            // gin[i] = sum_k gout[i - k + 1] * w[k]
+            const int dd = 1 - t / 9, dh = 1 - (t / 3) % 3, dw = 1 - t % 3;
+            const int od = d + dd, oh = h + dh, ow = w + dw;
+            if (od >= 0 && od < D && oh >= 0 && oh < H && ow >= 0 && ow < W)
+                g[t] = __ldg(gout + v + ((int64_t)dd * H + dh) * W + dw);
+        }
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int c = 0; c < C4; ++c) {
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int t = 0; t < 27; ++t) {
+            const float4 k = ws[t * C4 + c];
+            a.x = fmaf(g[t], k.x, a.x); a.y = fmaf(g[t], k.y, a.y); a.z = fmaf(g[t], k.z, a.z); a.w = fmaf(g[t], k.w, a.w);
+        }
+        os[threadIdx.x][c] = a;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kC1Tile * C4; i += kC1Tile) {
+        int64_t gi = v0 * C4 + i;
+        if (gi < nvox * C4) stg_stream(gin + gi, os[i / C4][i % C4]);
     }
 }
 
@@ -202,25 +238,30 @@ using namespace b2;
 
 #define B2_C1_SWITCH(Cin, ...)                                                     \
     switch ((Cin) / 4) {                                                           \
-        case 4: { constexpr int LPV = 4; __VA_ARGS__; } break;                            \
-        case 8: { constexpr int LPV = 8; __VA_ARGS__; } break;                            \
-        case 16: { constexpr int LPV = 16; __VA_ARGS__; } break;                          \
-        case 32: { constexpr int LPV = 32; __VA_ARGS__; } break;                          \
+        case 4: { constexpr int C4 = 4; __VA_ARGS__; } break;                      \
+        case 8: { constexpr int C4 = 8; __VA_ARGS__; } break;                      \
+        case 16: { constexpr int C4 = 16; __VA_ARGS__; } break;                    \
         default:                                                                   \
-            b2::set_error("conv3d_c1: Cin must be 16, 32, 64 or 128 (got %d)", (Cin)); \
+            b2::set_error("conv3d_c1: Cin must be 16, 32 or 64 (got %d)", (Cin)); \
             return B2_ERR_UNSUPPORTED;                                             \
     }
 
+extern "C" int64_t b2_conv3d_c1_workspace_bytes(int N, int D, int H, int W) {
+    return (int64_t)27 * N * D * H * W * (int64_t)sizeof(float);
+}
+
 extern "C" int b2_conv3d_c1_fwd(const float* in, const float* w1, float* out, int N, int Cin, int D,
-                                int H, int W, void* stream) {
-    B2_REQUIRE(in && w1 && out, "conv3d_c1_fwd: null pointer");
+                                int H, int W, void* workspace, void* stream) {
+    B2_REQUIRE(in && w1 && out && workspace, "conv3d_c1_fwd: null pointer");
     int64_t nvox = (int64_t)N * D * H * W;
     if (nvox == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    unsigned tiles = (unsigned)((nvox + kC1Tile - 1) / kC1Tile);
     B2_C1_SWITCH(Cin, {
-        int grid = stream_grid(nvox, 256 / LPV, kNumSMs * 16);
-        conv3d_c1_fwd_kernel<LPV><<<grid, 256, 0, st>>>((const float4*)in, (const float4*)w1, out, N, D, H, W);
+        conv3d_c1_partial_kernel<C4><<<tiles, kC1Tile, 0, st>>>((const float4*)in, (const float4*)w1,
+                                                               (float*)workspace, nvox);
     });
+    conv3d_c1_gather_kernel<<<stream_grid(nvox, 256, kNumSMs * 16), 256, 0, st>>>((const float*)workspace, out, N, D, H, W);
     return check_launch("conv3d_c1_fwd");
 }
 
@@ -230,9 +271,9 @@ extern "C" int b2_conv3d_c1_dgrad(const float* gout, const float* w1, float* gin
     int64_t nvox = (int64_t)N * D * H * W;
     if (nvox == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
+    unsigned tiles = (unsigned)((nvox + kC1Tile - 1) / kC1Tile);
     B2_C1_SWITCH(Cin, {
-        int grid = stream_grid(nvox, 256 / LPV, kNumSMs * 16);
-        conv3d_c1_dgrad_kernel<LPV><<<grid, 256, 0, st>>>(gout, (const float4*)w1, (float4*)gin, N, D, H, W);
+        conv3d_c1_dgrad_kernel<C4><<<tiles, kC1Tile, 0, st>>>(gout, (const float4*)w1, (float4*)gin, N, D, H, W);
     });
     return check_launch("conv3d_c1_dgrad");
 }

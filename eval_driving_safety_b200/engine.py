@@ -18,32 +18,52 @@ class PgdIterationGraph:
     normalised images; clean* are the denormalised clean copies) and returns the loss (device
     scalar, valid until the next step)."""
 
-    def __init__(self, model, cfg, labels, calib, alpha, eps, example, norm='linf', use_graph=True, warmup=2):
+    def __init__(self, model, cfg, labels, calib, alpha, eps, example, norm='linf', use_graph=True, warmup=2,
+                 lanes=1):
+        """``lanes`` > 1 captures that many independent pair-iterations on parallel streams inside
+        ONE graph: the launch/latency-bound 2-D sections of one pair overlap the tensor-core
+        sections of the other (``step_multi``)."""
         self.model, self.cfg, self.labels, self.calib = model, cfg, labels, calib
         self.alpha, self.eps, self.norm = alpha, eps, norm
         self.use_graph = use_graph
+        self.lanes = lanes if use_graph else 1
         self.launches_per_step = None
         xL, xR, cL, cR, disp = example
         if not use_graph:
             return
-        self.s = [t.clone() for t in (xL, xR, cL, cR, disp)]
+        self.sl = [[t.clone() for t in (xL, xR, cL, cR, disp)] for _ in range(self.lanes)]
+        self.s = self.sl[0]
         cur = torch.cuda.current_stream()
-        side = torch.cuda.Stream()
-        side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            for _ in range(warmup):                      # cuDNN autotune, plan/pack caches, workspaces
-                self._iteration(*self.s)
-        cur.wait_stream(side)
+        self.streams = [torch.cuda.Stream() for _ in range(self.lanes)]
+        for st, bufs in zip(self.streams, self.sl):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                for _ in range(warmup):                  # cuDNN autotune, plan/pack caches, workspaces
+                    self._iteration(*bufs)
+            cur.wait_stream(st)
         torch.cuda.synchronize()
-        for dst, src in zip(self.s, (xL, xR, cL, cR, disp)):
-            dst.copy_(src)
+        for bufs in self.sl:
+            for dst, src in zip(bufs, (xL, xR, cL, cR, disp)):
+                dst.copy_(src)
         self.graph = torch.cuda.CUDAGraph()
         n0 = ops.LAUNCH_COUNT
         with torch.cuda.graph(self.graph):
-            self.loss = self._iteration(*self.s)
-        self.launches_per_step = ops.LAUNCH_COUNT - n0
-        for dst, src in zip(self.s, (xL, xR, cL, cR, disp)):
-            dst.copy_(src)
+            if self.lanes == 1:
+                self.losses = [self._iteration(*self.s)]
+            else:
+                cap = torch.cuda.current_stream()
+                self.losses = []
+                for st, bufs in zip(self.streams, self.sl):
+                    st.wait_stream(cap)
+                    with torch.cuda.stream(st):
+                        self.losses.append(self._iteration(*bufs))
+                for st in self.streams:
+                    cap.wait_stream(st)
+        self.loss = self.losses[0]
+        self.launches_per_step = (ops.LAUNCH_COUNT - n0) // self.lanes
+        for bufs in self.sl:
+            for dst, src in zip(bufs, (xL, xR, cL, cR, disp)):
+                dst.copy_(src)
 
     def _iteration(self, xL, xR, cL, cR, disp):
         a, b = xL.detach().requires_grad_(True), xR.detach().requires_grad_(True)
@@ -56,6 +76,18 @@ class PgdIterationGraph:
             attack.pgd_step(xL, gL.contiguous(), cL, self.alpha, self.eps, norm=self.norm, out=xL)
             attack.pgd_step(xR, gR.contiguous(), cR, self.alpha, self.eps, norm=self.norm, out=xR)
         return loss.detach()
+
+    def step_multi(self, pairs):
+        """``pairs`` = list of ``lanes`` tuples (xL, xR, cL, cR, disp): one iteration of each, concurrently."""
+        assert self.use_graph and len(pairs) == self.lanes
+        for bufs, pr in zip(self.sl, pairs):
+            for dst, src in zip(bufs, pr):
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        for bufs, pr in zip(self.sl, pairs):
+            pr[0].copy_(bufs[0], non_blocking=True)
+            pr[1].copy_(bufs[1], non_blocking=True)
+        return self.losses
 
     def step(self, xL, xR, cL, cR, disp):
         if not self.use_graph:

@@ -426,8 +426,9 @@ class Conv3dC1Fn(Function):
             w1 = weight.detach()[0].permute(1, 2, 3, 0).reshape(27, cin).contiguous()
             _cache_put(key, weight, w1)
         out = torch.empty((n, 1, d, h, w), device=x.device, dtype=torch.float32)
-        with _op("conv3d_c1_fwd", 1, 4 * (x.numel() + out.numel())):
-            check(lib.b2_conv3d_c1_fwd(_p(x), _p(w1), _p(out), n, cin, d, h, w, _stream()), "conv3d_c1_fwd")
+        ws = torch.empty(lib.b2_conv3d_c1_workspace_bytes(n, d, h, w), device=x.device, dtype=torch.uint8)
+        with _op("conv3d_c1_fwd", 2, 4 * (x.numel() + out.numel())):
+            check(lib.b2_conv3d_c1_fwd(_p(x), _p(w1), _p(out), n, cin, d, h, w, _p(ws), _stream()), "conv3d_c1_fwd")
         ctx.w1, ctx.dims = w1, (n, cin, d, h, w)
         return out
 

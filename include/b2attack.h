@@ -159,8 +159,9 @@ int b2_conv3d(const float* in, const float* wp, float* out, int N, int Cin, int 
 /* Cout == 1 head (classif1's last layer) and its data gradient: bandwidth-bound,
  * SIMT.  w1 [27][Cin].  fwd: in [N,D,H,W,Cin] -> out [N,D,H,W];
  * dgrad: gout [N,D,H,W] -> gin [N,D,H,W,Cin]. */
+int64_t b2_conv3d_c1_workspace_bytes(int N, int D, int H, int W);   /* 27 tap planes, fwd only */
 int b2_conv3d_c1_fwd(const float* in, const float* w1, float* out, int N, int Cin,
-                     int D, int H, int W, void* stream);
+                     int D, int H, int W, void* workspace, void* stream);
 int b2_conv3d_c1_dgrad(const float* gout, const float* w1, float* gin, int N, int Cin,
                        int D, int H, int W, void* stream);
 
