@@ -43,14 +43,21 @@ static GnLayout gn_layout(int C) {
 __host__ __device__ inline int64_t gn_partial_floats(int N, int C) { return (int64_t)N * kGnBlocks * 2 * C; }
 
 // MODE 0: sums of (x, x^2) per channel.  MODE 1: sums of (gz*x, gz) per channel,
-// gz = gy * (relu ? y > 0 : 1).
+// gz = gy * mask; relu == 1: mask = saved output y > 0; relu == 2: mask recomputed from x with the
+// forward's own scale/shift (fcoef = stats tail, identical fmaf) so y need not be read (or kept).
 template <int MODE>
 __global__ void gn_partials_kernel(const float4* __restrict__ a, const float4* __restrict__ x,
                                    const float4* __restrict__ y, float* __restrict__ partial,
-                                   int C, int64_t S, int lpr, int rpb, int relu) {
-    extern __shared__ float4 sh[];  // [2][rpb][lpr]
+                                   int C, int64_t S, int lpr, int rpb, int relu, const float* __restrict__ fstats, int G) {
+    extern __shared__ float4 sh[];  // [2][rpb][lpr] (+ [2][C] floats of forward coefficients)
     const int n = blockIdx.y;
     const int lane = threadIdx.x % lpr, r = threadIdx.x / lpr;
+    float4 fs = make_float4(0.f, 0.f, 0.f, 0.f), fb = fs;     // this lane's 4 channels: scale, shift
+    if (MODE == 1 && relu == 2) {
+        const float* fc = fstats + (int64_t)n * (2 * G + 2 * C) + 2 * G;      // forward scale / shift of sample n
+        fs = make_float4(fc[lane * 4], fc[lane * 4 + 1], fc[lane * 4 + 2], fc[lane * 4 + 3]);
+        fb = make_float4(fc[C + lane * 4], fc[C + lane * 4 + 1], fc[C + lane * 4 + 2], fc[C + lane * 4 + 3]);
+    }
     const int64_t rows_per_block = (S + gridDim.x - 1) / gridDim.x;
     const int64_t s_begin = (int64_t)blockIdx.x * rows_per_block;
     const int64_t s_end = min(S, s_begin + rows_per_block);
@@ -61,6 +68,7 @@ __global__ void gn_partials_kernel(const float4* __restrict__ a, const float4* _
             p.x += v.x; p.y += v.y; p.z += v.z; p.w += v.w;
             q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
         } else {
+            if (relu == 2) { o.x = fmaf(v.x, fs.x, fb.x); o.y = fmaf(v.y, fs.y, fb.y); o.z = fmaf(v.z, fs.z, fb.z); o.w = fmaf(v.w, fs.w, fb.w); }
             if (relu) {
                 g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
                 g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
@@ -79,7 +87,7 @@ __global__ void gn_partials_kernel(const float4* __restrict__ a, const float4* _
             int64_t i = base + (s + (int64_t)u * rpb) * lpr + lane;
             vv[u] = ldg_stream(x + i);
             gg[u] = MODE == 1 ? ldg_stream(a + i) : zero4;
-            oo[u] = (MODE == 1 && relu) ? ldg_stream(y + i) : zero4;
+            oo[u] = (MODE == 1 && relu == 1) ? ldg_stream(y + i) : zero4;
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) accum(gg[u], vv[u], oo[u]);
@@ -88,7 +96,7 @@ __global__ void gn_partials_kernel(const float4* __restrict__ a, const float4* _
         int64_t i = base + s * lpr + lane;
         float4 v = ldg_stream(x + i);
         float4 g = MODE == 1 ? ldg_stream(a + i) : zero4;
-        float4 o = (MODE == 1 && relu) ? ldg_stream(y + i) : zero4;
+        float4 o = (MODE == 1 && relu == 1) ? ldg_stream(y + i) : zero4;
         accum(g, v, o);
     }
     sh[r * lpr + lane] = p;
@@ -162,13 +170,17 @@ gn_finalize_fwd(const float* __restrict__ partial, const float* __restrict__ gam
         double var = sq / m - mean * mean;
         if (var < 0.0) var = 0.0;
         double rstd = 1.0 / sqrt(var + (double)eps);
+        float* st = stats + (int64_t)n * (2 * G + 2 * C);      // [2G] (mean, rstd) then [2][C] scale / shift
         if (c % cpg == 0) {
-            stats[((int64_t)n * G + g) * 2 + 0] = (float)mean;
-            stats[((int64_t)n * G + g) * 2 + 1] = (float)rstd;
+            st[g * 2 + 0] = (float)mean;
+            st[g * 2 + 1] = (float)rstd;
         }
         double scale = (double)gamma[c] * rstd;
-        coef[((int64_t)n * 3 + 0) * C + c] = (float)scale;
-        coef[((int64_t)n * 3 + 1) * C + c] = (float)((double)beta[c] - mean * scale);
+        const float fsc = (float)scale, fsh = (float)((double)beta[c] - mean * scale);
+        coef[((int64_t)n * 3 + 0) * C + c] = fsc;
+        coef[((int64_t)n * 3 + 1) * C + c] = fsh;
+        st[2 * G + c] = fsc;
+        st[2 * G + C + c] = fsh;
     }
 }
 
@@ -190,7 +202,8 @@ gn_finalize_bwd(const float* __restrict__ partial, const float* __restrict__ gam
         double ds = 0.0, db = 0.0;
         for (int j = 0; j < cpg; ++j) { ds += s1[g * cpg + j]; db += s2[g * cpg + j]; }
         double m = (double)cpg * (double)S;
-        double mean = stats[((int64_t)n * G + g) * 2 + 0], rstd = stats[((int64_t)n * G + g) * 2 + 1];
+        const float* st = stats + (int64_t)n * (2 * G + 2 * C);
+        double mean = st[g * 2 + 0], rstd = st[g * 2 + 1];
         double c2 = (db * mean - ds) * rstd * rstd * rstd / m;
         double c3 = -c2 * mean - db * rstd / m;
         coef[((int64_t)n * 3 + 0) * C + c] = (float)((double)gamma[c] * rstd);
@@ -212,10 +225,10 @@ gn_apply_fwd(const float4* __restrict__ x, const float4* __restrict__ res, const
         int q = (int)(i % lpr) * 4;
         float4 v = ldg_stream(x + base + i);
         float4 o;
-        o.x = v.x * shc[q] + shc[C + q];
-        o.y = v.y * shc[q + 1] + shc[C + q + 1];
-        o.z = v.z * shc[q + 2] + shc[C + q + 2];
-        o.w = v.w * shc[q + 3] + shc[C + q + 3];
+        o.x = fmaf(v.x, shc[q], shc[C + q]);
+        o.y = fmaf(v.y, shc[q + 1], shc[C + q + 1]);
+        o.z = fmaf(v.z, shc[q + 2], shc[C + q + 2]);
+        o.w = fmaf(v.w, shc[q + 3], shc[C + q + 3]);
         if (res) {
             float4 r = ldg_stream(res + base + i);
             o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
@@ -228,10 +241,13 @@ gn_apply_fwd(const float4* __restrict__ x, const float4* __restrict__ res, const
 __global__ void __launch_bounds__(256)
 gn_apply_bwd(const float4* gy, const float4* __restrict__ x, const float4* __restrict__ y,
              const float* __restrict__ coef, float4* __restrict__ gx, float4* gres, int C,
-             int64_t S, int relu) {
-    extern __shared__ float shc[];  // [3][C]
+             int64_t S, int relu, const float* __restrict__ fstats, int G) {
+    extern __shared__ float shc[];  // [3][C] backward coefficients (+ [2][C] forward scale / shift)
     const int n = blockIdx.y, lpr = C / 4;
     for (int i = threadIdx.x; i < 3 * C; i += blockDim.x) shc[i] = coef[(int64_t)n * 3 * C + i];
+    if (relu == 2)
+        for (int i = threadIdx.x; i < 2 * C; i += blockDim.x)
+            shc[3 * C + i] = fstats[(int64_t)n * (2 * G + 2 * C) + 2 * G + i];
     __syncthreads();
     const int64_t total = S * lpr, base = (int64_t)n * total;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -240,7 +256,14 @@ gn_apply_bwd(const float4* gy, const float4* __restrict__ x, const float4* __res
         float4 g = ldg_stream(gy + base + i);
         float4 v = ldg_stream(x + base + i);
         if (relu) {
-            float4 o = ldg_stream(y + base + i);
+            float4 o;
+            if (relu == 2) {
+                const float* fs = shc + 3 * C;
+                o.x = fmaf(v.x, fs[q], fs[C + q]); o.y = fmaf(v.y, fs[q + 1], fs[C + q + 1]);
+                o.z = fmaf(v.z, fs[q + 2], fs[C + q + 2]); o.w = fmaf(v.w, fs[q + 3], fs[C + q + 3]);
+            } else {
+                o = ldg_stream(y + base + i);
+            }
             g.x = o.x > 0.f ? g.x : 0.f; g.y = o.y > 0.f ? g.y : 0.f;
             g.z = o.z > 0.f ? g.z : 0.f; g.w = o.w > 0.f ? g.w : 0.f;
         }
@@ -282,7 +305,7 @@ extern "C" int b2_groupnorm_fwd(const float* x, const float* res, const float* g
     float* coef = partial + gn_partial_floats(N, C);
     int nblocks = gn_nblocks(S);
     gn_partials_kernel<0><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
-        nullptr, (const float4*)x, nullptr, partial, C, S, l.lpr, l.rpb, 0);
+        nullptr, (const float4*)x, nullptr, partial, C, S, l.lpr, l.rpb, 0, nullptr, G);
     gn_finalize_fwd<<<N, kGnFinThreads, 0, st>>>(partial, gamma, beta, stats, coef, C, S, G, eps, nblocks);
     int gx = stream_grid(S * l.lpr, 256 * 4, kNumSMs * 8);
     gn_apply_fwd<<<dim3(gx, N), 256, 2 * C * sizeof(float), st>>>((const float4*)x, (const float4*)res, coef,
@@ -294,7 +317,8 @@ extern "C" int b2_groupnorm_bwd(const float* gy, const float* x, const float* y,
                                 const float* stats, float* gx, float* gres, int N, int C, int64_t S,
                                 int G, int relu, void* workspace, void* stream) {
     B2_REQUIRE(gy && x && gamma && stats && gx && workspace, "groupnorm_bwd: null pointer");
-    B2_REQUIRE(!relu || y, "groupnorm_bwd: relu needs the saved output y");
+    B2_REQUIRE(relu != 1 || y, "groupnorm_bwd: relu == 1 needs the saved output y (relu == 2 recomputes the mask)");
+    B2_REQUIRE(relu >= 0 && relu <= 2, "groupnorm_bwd: relu must be 0, 1 or 2");
     if (int e = gn_check("groupnorm_bwd", N, C, S, G)) return e;
     B2_REQUIRE(aligned16(gy) && aligned16(x) && aligned16(gx), "groupnorm_bwd: pointers must be 16B aligned");
     if (N == 0 || S == 0) return 0;
@@ -304,11 +328,12 @@ extern "C" int b2_groupnorm_bwd(const float* gy, const float* x, const float* y,
     float* coef = partial + gn_partial_floats(N, C);
     int nblocks = gn_nblocks(S);
     gn_partials_kernel<1><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
-        (const float4*)gy, (const float4*)x, (const float4*)y, partial, C, S, l.lpr, l.rpb, relu);
+        (const float4*)gy, (const float4*)x, (const float4*)y, partial, C, S, l.lpr, l.rpb, relu,
+        stats, G);
     gn_finalize_bwd<<<N, kGnFinThreads, 0, st>>>(partial, gamma, stats, coef, C, S, G, nblocks);
     int gxd = stream_grid(S * l.lpr, 256 * 4, kNumSMs * 8);
-    gn_apply_bwd<<<dim3(gxd, N), 256, 3 * C * sizeof(float), st>>>((const float4*)gy, (const float4*)x,
+    gn_apply_bwd<<<dim3(gxd, N), 256, 5 * C * sizeof(float), st>>>((const float4*)gy, (const float4*)x,
                                                                    (const float4*)y, coef, (float4*)gx,
-                                                                   (float4*)gres, C, S, relu);
+                                                                   (float4*)gres, C, S, relu, stats, G);
     return check_launch("groupnorm_bwd");
 }

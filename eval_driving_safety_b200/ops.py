@@ -480,13 +480,16 @@ class GroupNormActFn(Function):
         n, c = x.shape[:2]
         s = x[0, 0].numel()
         y = _empty_cl_like(x)
-        stats = torch.empty((n, groups, 2), device=x.device, dtype=torch.float32)
+        stats = torch.empty((n, 2 * groups + 2 * c), device=x.device, dtype=torch.float32)
         ws = _workspace(lib.b2_groupnorm_workspace_bytes(n, c), x.device)
         gamma, beta = gamma.detach().contiguous(), beta.detach().contiguous()
         with _op("groupnorm_fwd", 3, 4 * x.numel() * (3 + (res is not None))):
             check(lib.b2_groupnorm_fwd(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(stats), n, c, s, groups,
                                        float(eps), int(relu), _p(ws), _stream()), "groupnorm_fwd")
-        ctx.save_for_backward(x, y, gamma, stats)
+        # ReLU without residual: the backward recomputes the mask from x (relu mode 2), so y is not
+        # kept alive by this node (and is never re-read)
+        keep_y = relu and res is not None
+        ctx.save_for_backward(x, y if keep_y else None, gamma, stats)
         ctx.cfg = (groups, relu, res is not None)
         return y
 
@@ -502,9 +505,10 @@ class GroupNormActFn(Function):
         gx = _empty_cl_like(x)
         gres = _empty_cl_like(x) if (has_res and relu) else None
         ws = _workspace(lib.b2_groupnorm_workspace_bytes(n, c), x.device)
-        with _op("groupnorm_bwd", 3, 4 * x.numel() * (5 + 2 * int(relu) + (gres is not None))):
+        mode = 0 if not relu else (1 if has_res else 2)
+        with _op("groupnorm_bwd", 3, 4 * x.numel() * (5 + 2 * int(mode == 1) + (gres is not None))):
             check(lib.b2_groupnorm_bwd(_p(gy), _p(x), _p(y), _p(gamma), _p(stats), _p(gx), _p(gres), n, c, s, groups,
-                                       int(relu), _p(ws), _stream()), "groupnorm_bwd")
+                                       mode, _p(ws), _stream()), "groupnorm_bwd")
         if has_res and not relu:
             gres = gy
         return gx, gres, None, None, None, None, None

@@ -168,10 +168,13 @@ int b2_conv3d_c1_dgrad(const float* gout, const float* w1, float* gin, int N, in
 /* GroupNorm (+ residual add) (+ ReLU) on channels-last 3-D volumes, forward and
  * data gradient -- the norm/activation that follows every conv3d (upstream
  * convbn_3d).  y = act(GN(x)*gamma + beta (+ res)).
- *   stats  [N,G,2] (mean, rstd) written by fwd, read by bwd
+ *   stats  [N, 2G + 2C]: per sample (mean, rstd) x G, then scale[C], shift[C]; written by fwd,
+ *          read by bwd
  *   workspace: b2_groupnorm_workspace_bytes(N, C) bytes
- * bwd: gx (and gres = masked gy when has_res; may alias gy).  y is the saved
- * forward output (the ReLU mask). */
+ * bwd: gx (and gres = masked gy when has_res; may alias gy).  relu = 0 none; 1 = mask from the
+ * saved forward output y; 2 = mask recomputed from x with the forward's own scale/shift (exactly
+ * the forward's fmaf, valid when the forward had no residual) -> y may be NULL and need not be
+ * kept alive. */
 int64_t b2_groupnorm_workspace_bytes(int N, int C);
 int b2_groupnorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,
                      float* y, float* stats, int N, int C, int64_t S, int G, float eps,
