@@ -551,6 +551,212 @@ static EncodeTiledFn get_encode() {
     return fn;
 }
 
+
+// =============================================================================================
+// Stride-1 fast path, "N-stacked" variant (default).  For one input plane pr and one (kh, kw, chunk),
+// the taps kd = 2,1,0 feed the accumulators of output planes pr-2, pr-1, pr -- which sit in
+// ADJACENT TMEM column ranges.  With the three weight tiles [W(kd=2); W(kd=1); W(kd=0)] stored
+// contiguously in smem, ONE tcgen05.mma with N = 3*Nt (192 for Nt = 64) covers all three planes:
+// the A tile is read from smem once instead of three times.  Operand smem traffic per generation
+// drops from 864 KB to 583 KB (the super-tile kernel above is smem-read bound: ~192 B/clk needed at
+// N = 64 vs 128 B/clk available), tensor-pipe bound goes from ~56 % to ~77 %.
+// Every MMA accumulates (the epilogue zeroes an accumulator with tcgen05.st after draining it),
+// because one MMA may touch a fresh and a partially summed plane at the same time.
+// =============================================================================================
+__device__ __forceinline__ void tmem_st32_zero(uint32_t taddr) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+        "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+        ::"r"(taddr), "r"(0u) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          float* __restrict__ out, const S1Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kS1NA + 2 * kS1MaxNB + 4];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t a_base = smem_base, b_base = smem_base + kS1NA * kS1ABytes;
+    const uint32_t bar0 = smem_u32(bars);
+    auto fullA = [&](int s) { return bar0 + 8u * s; };
+    auto emptyA = [&](int s) { return bar0 + 8u * (kS1NA + s); };
+    auto fullB = [&](int s) { return bar0 + 8u * (2 * kS1NA + s); };
+    auto emptyB = [&](int s) { return bar0 + 8u * (2 * kS1NA + kS1MaxNB + s); };
+    auto tfull = [&](int a) { return bar0 + 8u * (2 * kS1NA + 2 * kS1MaxNB + a); };
+    auto tempty = [&](int a) { return bar0 + 8u * (2 * kS1NA + 2 * kS1MaxNB + 2 + a); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kS1NA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); }
+        for (int s = 0; s < p.nb; ++s) { mbar_init(fullB(s), 1); mbar_init(emptyB(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull(a), 1); mbar_init(tempty(a), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const int ngen = 3 * p.kchunks;
+    const int gper = p.nb / 9;                  // generations resident in the B ring (1 or 2)
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t aslot = 0, aphase = 0, gord = 0;
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                S1Tile tc = s1_decode(p, t);
+                for (int g = 0; g < ngen; ++g, ++gord) {
+                    const int kw = g / p.kchunks, kc = g % p.kchunks;
+                    const uint32_t bbase = (gord % gper) * 9, bphase = (gord / gper) & 1;
+                    for (int pr = 0; pr < kS1Planes + 2; ++pr) {
+                        if (pr < 3) {                       // weight tiles of tap kd = pr, stored at position 2-kd
+                            for (int kh = 0; kh < 3; ++kh) {
+                                const uint32_t slot = bbase + kh * 3 + (2 - pr);
+                                mbar_wait(emptyB(slot), bphase ^ 1);
+                                mbar_expect_tx(fullB(slot), (uint32_t)p.b_bytes);
+                                const int tap = p.swap ? (kh * 3 + pr) * 3 + kw : (pr * 3 + kh) * 3 + kw;
+                                tma_load_2d(b_base + slot * (uint32_t)p.b_bytes, &map_b, fullB(slot), kc * kKChunk,
+                                            tap * p.Cout + tc.nti * p.nt);
+                            }
+                        }
+                        mbar_wait(emptyA(aslot), aphase ^ 1);
+                        mbar_expect_tx(fullA(aslot), (uint32_t)kS1ABytes);
+                        tma_load_5d(a_base + aslot * (uint32_t)kS1ABytes, &map_a, fullA(aslot), kc * kKChunk,
+                                    tc.w0 + kw - 1, tc.h0 - 1, tc.d0 - 1 + pr, tc.n);
+                        if (++aslot == kS1NA) { aslot = 0; aphase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc1 = umma_idesc_tf32(128, p.nt), idesc2 = umma_idesc_tf32(128, 2 * p.nt),
+                           idesc3 = umma_idesc_tf32(128, 3 * p.nt);
+            uint32_t aslot = 0, aphase = 0, gord = 0;
+            long long it = 0;
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+                const int accbuf = (int)(it & 1);
+                mbar_wait(tempty(accbuf), (uint32_t)((it >> 1) & 1));     // drained AND zeroed by the epilogue
+                tc_fence_after();
+                const uint32_t tmem_acc0 = tmem_base + (uint32_t)(accbuf * kS1Planes * p.nt);
+                for (int g = 0; g < ngen; ++g, ++gord) {
+                    const uint32_t bbase = (gord % gper) * 9, bphase = (gord / gper) & 1;
+#pragma unroll
+                    for (int pr = 0; pr < kS1Planes + 2; ++pr) {
+                        mbar_wait(fullA(aslot), aphase);
+                        tc_fence_after();
+                        const uint64_t adesc0 = umma_desc_sw128(a_base + aslot * (uint32_t)kS1ABytes);
+                        const int kd_hi = pr < 2 ? pr : 2, kd_lo = pr > 3 ? pr - 3 : 0;
+                        const int nplanes = kd_hi - kd_lo + 1;
+                        const uint32_t idesc = nplanes == 1 ? idesc1 : (nplanes == 2 ? idesc2 : idesc3);
+                        const uint32_t tmem_d = tmem_acc0 + (uint32_t)((pr - kd_hi) * p.nt);
+#pragma unroll
+                        for (int kh = 0; kh < 3; ++kh) {
+                            const uint32_t slot_hi = bbase + kh * 3 + (2 - kd_hi);
+                            if (pr <= 2) {                      // first use of the tile kd = pr (= kd_hi)
+                                mbar_wait(fullB(slot_hi), bphase);
+                                tc_fence_after();
+                            }
+                            const uint64_t adesc = adesc0 + (uint64_t)(kh * (1024 >> 4));
+                            const uint64_t bdesc = umma_desc_sw128(b_base + slot_hi * (uint32_t)p.b_bytes);
+#pragma unroll
+                            for (int k = 0; k < kKChunk / 8; ++k)
+                                umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, 1u);
+                            if (pr >= 3) umma_commit(emptyB(bbase + kh * 3 + (2 - (pr - 3))));   // last use of kd = pr-3
+                        }
+                        umma_commit(emptyA(aslot));
+                        if (++aslot == kS1NA) { aslot = 0; aphase ^= 1; }
+                    }
+                }
+                umma_commit(tfull(accbuf));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue =====================
+        const int lane_grp = warp & 3;
+        const int m = lane_grp * 32 + lane;
+        const int hl = m / kTileW, wl = m % kTileW;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        // zero both accumulator buffers, then hand them to the MMA warp
+        for (int c0 = 0; c0 < 2 * kS1Planes * p.nt; c0 += 16) tmem_st16_zero(lane_addr + c0);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(tempty(0));
+        mbar_arrive(tempty(1));
+        long long it = 0;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const int accbuf = (int)(it & 1);
+            S1Tile tc = s1_decode(p, t);
+            const int r = tc.h0 + hl, w = tc.w0 + wl;
+            const bool ok_hw = r < p.R && w < p.W;
+            mbar_wait(tfull(accbuf), (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            for (int j = 0; j < kS1Planes; ++j) {
+                const int pl = tc.d0 + j;
+                const bool ok = ok_hw && pl < p.P;
+                const int d = p.swap ? r : pl, h = p.swap ? pl : r;
+                float* orow = out + ((((long long)tc.n * p.D + d) * p.H + h) * p.W + w) * p.Cout + tc.nti * p.nt;
+                const uint32_t taddr = lane_addr + (uint32_t)((accbuf * kS1Planes + j) * p.nt);
+                int c0 = 0;
+                for (; c0 + 32 <= p.nt; c0 += 32) {
+                    uint32_t rr[32];
+                    tmem_ld32(taddr + c0, rr);
+                    tmem_ld_wait();
+                    tmem_st32_zero(taddr + c0);
+                    if (ok) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4*>(orow + c0 + 4 * q) =
+                                make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
+                                            __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
+                    }
+                }
+                if (c0 < p.nt) {
+                    uint32_t rr[16];
+                    tmem_ld16(taddr + c0, rr);
+                    tmem_ld_wait();
+                    tmem_st16_zero(taddr + c0);
+                    if (ok) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<float4*>(orow + c0 + 4 * q) =
+                                make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
+                                            __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
+                    }
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(tempty(accbuf));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
 static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* wp, float* out, int N, int Cin,
                             int Cout, int D, int H, int W, cudaStream_t st) {
     S1Params p{};
@@ -572,6 +778,10 @@ static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* 
     p.b_bytes = p.nt * 128;
     p.nb = (216 * 1024 - kS1NA * kS1ABytes) / p.b_bytes;
     if (p.nb > kS1MaxNB) p.nb = kS1MaxNB;
+    static int nstack = -1;
+    if (nstack < 0) { const char* e = getenv("B2_CONV_S1_NSTACK"); nstack = (e && e[0] == '0') ? 0 : 1; }
+    const bool use_nstack = nstack && p.nb >= 9 && (3 * p.nt) % 16 == 0 && 3 * p.nt <= 256;
+    if (use_nstack) p.nb = p.nb >= 18 ? 18 : 9;     // whole generations (9 tiles) in the ring
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * kS1Planes * p.nt) p.tmem_cols *= 2;
     p.total_tiles = (long long)p.n_tiles * N * p.dblocks * p.tiles_h * p.tiles_w;
@@ -606,11 +816,16 @@ static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* 
     static int attr_smem = 0;
     if (smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(conv3d_s1_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(conv3d_s1n_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { set_error("conv3d(tcgen05,s1): cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return (int)e; }
         attr_smem = smem;
     }
     int grid = (int)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
-    conv3d_s1_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p);
+    if (use_nstack)
+        conv3d_s1n_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p);
+    else
+        conv3d_s1_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p);
     return check_launch("conv3d(tcgen05,s1)");
 }
 

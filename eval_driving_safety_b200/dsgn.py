@@ -147,7 +147,9 @@ class FeatureExtraction(nn.Module):
         layers += [BasicBlock(cfg, cout, cout, 1, dilation) for _ in range(n - 1)]
         return nn.Sequential(*layers)
 
-    def forward(self, x):
+    def forward(self, x, rpn_samples=None):
+        """``rpn_samples``: compute the image-feature head only for the first that many samples
+        (the model runs left and right images as one batch; only the left needs that head)."""
         x = x.contiguous(memory_format=torch.channels_last)
         out = x
         for i in (0, 2, 4):
@@ -174,7 +176,8 @@ class FeatureExtraction(nn.Module):
                 cat.append(upsample_bilinear_matmul(y, size))
         cat = torch.cat(cat, 1).contiguous(memory_format=torch.channels_last)
         f = self.lastconv[2](run_convbn_2d(self.lastconv[0], cat, relu=True))
-        r = self.rpnconv[2](run_convbn_2d(self.rpnconv[0], cat, relu=True))
+        n_rpn = cat.shape[0] if rpn_samples is None else rpn_samples
+        r = self.rpnconv[2](run_convbn_2d(self.rpnconv[0], cat[:n_rpn], relu=True))
         return f, r
 
 
@@ -338,8 +341,12 @@ class StereoNet(nn.Module):
     def forward(self, imgL, imgR, calibs_fu, calibs_baseline, calibs_Proj, calibs_Proj_R=None):
         if not imgL.is_cuda:
             raise RuntimeError("StereoNet (B200 path) needs CUDA inputs; there is no CPU fallback")
-        featL, rpnL = self.feature_extraction(imgL)
-        featR, _ = self.feature_extraction(imgR)
+        # left and right images share the extractor weights: one batched pass (every kernel of the
+        # launch-bound 2-D section does twice the work; GroupNorm statistics are per sample, so the
+        # result equals two separate passes)
+        n = imgL.shape[0]
+        feat, rpnL = self.feature_extraction(torch.cat([imgL, imgR], 0), rpn_samples=n)
+        featL, featR = feat[:n], feat[n:]
         cost, out, cost1 = self.psv_stage(featL, featR, calibs_fu, calibs_baseline)
         outputs = {'depth_preds': self.depth_head(cost1, imgL.shape[-2:])}
         if self.cfg.RPN3D_ENABLE:
