@@ -115,67 +115,56 @@ __global__ void gn_partials_kernel(const float4* __restrict__ a, const float4* _
     }
 }
 
-// Sum the per-block partials of channel c: `lanes` = 1024 / C threads per channel each add every
-// lanes-th partial in order, then the lanes are combined in lane order -> fixed summation order.
-constexpr int kGnFinThreads = 1024;
+// Finalize: one block per (group, sample).  Thread t adds the partials k = t, t+128, ... of the
+// group's channels (fp64), then a fixed-shape tree over the 128 threads combines them -> the
+// summation order is a function of (nblocks, C, G) only, i.e. bitwise reproducible, and the
+// serial tail of a single-block finalize (11 us measured) is gone.
+constexpr int kGnFinThreads = 128;
+constexpr int kGnMaxCpg = 8;
 
-__device__ __forceinline__ void gn_sum_partials(const float* __restrict__ partial, int n, int nblocks, int C,
-                                                double* s1, double* s2, double* sh /* [2][1024] */) {
-    const int lanes = kGnFinThreads / C;            // >= 4
-    const int c = threadIdx.x % C, l = threadIdx.x / C;
+__device__ __forceinline__ void gn_group_sums(const float* __restrict__ partial, int n, int nblocks, int C, int c0,
+                                              int cpg, const float* __restrict__ wgt /* per-channel weight or null */,
+                                              double& S1, double& S2) {
+    __shared__ double sh[2][kGnFinThreads];
     double a = 0.0, b = 0.0;
-    if (l < lanes) {
-        const float* base = partial + ((int64_t)n * nblocks * 2) * C + c;
-        const int64_t step = (int64_t)2 * C;
-        int k = l;
-        for (; k + 3 * lanes < nblocks; k += 4 * lanes) {         // 8 independent loads in flight
-            float a0 = __ldg(base + (k) * step), b0 = __ldg(base + (k) * step + C);
-            float a1 = __ldg(base + (k + lanes) * step), b1 = __ldg(base + (k + lanes) * step + C);
-            float a2 = __ldg(base + (k + 2 * lanes) * step), b2 = __ldg(base + (k + 2 * lanes) * step + C);
-            float a3 = __ldg(base + (k + 3 * lanes) * step), b3 = __ldg(base + (k + 3 * lanes) * step + C);
-            a += (double)a0; a += (double)a1; a += (double)a2; a += (double)a3;
-            b += (double)b0; b += (double)b1; b += (double)b2; b += (double)b3;
-        }
-        for (; k < nblocks; k += lanes) {
-            a += (double)__ldg(base + k * step);
-            b += (double)__ldg(base + k * step + C);
+    for (int k = threadIdx.x; k < nblocks; k += kGnFinThreads) {
+        const float* p = partial + (((int64_t)n * nblocks + k) * 2) * C + c0;
+        for (int j = 0; j < cpg; ++j) {
+            const double w = wgt ? (double)__ldg(wgt + c0 + j) : 1.0;
+            a += w * (double)__ldg(p + j);
+            b += w * (double)__ldg(p + C + j);
         }
     }
-    sh[threadIdx.x] = a; sh[kGnFinThreads + threadIdx.x] = b;
+    sh[0][threadIdx.x] = a; sh[1][threadIdx.x] = b;
     __syncthreads();
-    if (threadIdx.x < C) {
-        double ta = 0.0, tb = 0.0;
-        for (int j = 0; j < lanes; ++j) { ta += sh[j * C + c]; tb += sh[kGnFinThreads + j * C + c]; }
-        s1[c] = ta; s2[c] = tb;
+    for (int off = kGnFinThreads / 2; off > 0; off >>= 1) {
+        if (threadIdx.x < off) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + off];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + off];
+        }
+        __syncthreads();
     }
-    __syncthreads();
+    S1 = sh[0][0]; S2 = sh[1][0];
 }
 
-// One block per sample, kGnLanes threads per channel.
-// fwd: stats[n][g] = (mean, rstd); coef[n][0][c] = scale, coef[n][1][c] = shift.
+// fwd: stats[n] = [(mean, rstd) x G][scale[C]][shift[C]]; coef[n][0][c] = scale, coef[n][1][c] = shift.
 __global__ void __launch_bounds__(kGnFinThreads)
 gn_finalize_fwd(const float* __restrict__ partial, const float* __restrict__ gamma,
                 const float* __restrict__ beta, float* __restrict__ stats,
                 float* __restrict__ coef, int C, int64_t S, int G, float eps, int nblocks) {
-    __shared__ double s1[kGnMaxC], s2[kGnMaxC];
-    __shared__ double sh[2 * kGnFinThreads];
-    const int n = blockIdx.x, c = threadIdx.x;
-    gn_sum_partials(partial, n, nblocks, C, s1, s2, sh);
-    if (c < C) {
-        const int cpg = C / G, g = c / cpg;
-        double sum = 0.0, sq = 0.0;
-        for (int j = 0; j < cpg; ++j) { sum += s1[g * cpg + j]; sq += s2[g * cpg + j]; }
-        double m = (double)cpg * (double)S;
-        double mean = sum / m;
-        double var = sq / m - mean * mean;
-        if (var < 0.0) var = 0.0;
-        double rstd = 1.0 / sqrt(var + (double)eps);
-        float* st = stats + (int64_t)n * (2 * G + 2 * C);      // [2G] (mean, rstd) then [2][C] scale / shift
-        if (c % cpg == 0) {
-            st[g * 2 + 0] = (float)mean;
-            st[g * 2 + 1] = (float)rstd;
-        }
-        double scale = (double)gamma[c] * rstd;
+    const int g = blockIdx.x, n = blockIdx.y, cpg = C / G;
+    double sum, sq;
+    gn_group_sums(partial, n, nblocks, C, g * cpg, cpg, nullptr, sum, sq);
+    const double m = (double)cpg * (double)S;
+    const double mean = sum / m;
+    double var = sq / m - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double rstd = 1.0 / sqrt(var + (double)eps);
+    float* st = stats + (int64_t)n * (2 * G + 2 * C);
+    if (threadIdx.x == 0) { st[g * 2 + 0] = (float)mean; st[g * 2 + 1] = (float)rstd; }
+    if (threadIdx.x < cpg) {
+        const int c = g * cpg + threadIdx.x;
+        const double scale = (double)gamma[c] * rstd;
         const float fsc = (float)scale, fsh = (float)((double)beta[c] - mean * scale);
         coef[((int64_t)n * 3 + 0) * C + c] = fsc;
         coef[((int64_t)n * 3 + 1) * C + c] = fsh;
@@ -191,21 +180,16 @@ __global__ void __launch_bounds__(kGnFinThreads)
 gn_finalize_bwd(const float* __restrict__ partial, const float* __restrict__ gamma,
                 const float* __restrict__ stats, float* __restrict__ coef, int C,
                 int64_t S, int G, int nblocks) {
-    __shared__ double s1[kGnMaxC], s2[kGnMaxC];
-    __shared__ double sh[2 * kGnFinThreads];
-    const int n = blockIdx.x, c = threadIdx.x;
-    gn_sum_partials(partial, n, nblocks, C, s1, s2, sh);
-    if (c < C) { s1[c] *= (double)gamma[c]; s2[c] *= (double)gamma[c]; }
-    __syncthreads();
-    if (c < C) {
-        const int cpg = C / G, g = c / cpg;
-        double ds = 0.0, db = 0.0;
-        for (int j = 0; j < cpg; ++j) { ds += s1[g * cpg + j]; db += s2[g * cpg + j]; }
-        double m = (double)cpg * (double)S;
-        const float* st = stats + (int64_t)n * (2 * G + 2 * C);
-        double mean = st[g * 2 + 0], rstd = st[g * 2 + 1];
-        double c2 = (db * mean - ds) * rstd * rstd * rstd / m;
-        double c3 = -c2 * mean - db * rstd / m;
+    const int g = blockIdx.x, n = blockIdx.y, cpg = C / G;
+    double ds, db;
+    gn_group_sums(partial, n, nblocks, C, g * cpg, cpg, gamma, ds, db);
+    const float* st = stats + (int64_t)n * (2 * G + 2 * C);
+    const double mean = st[g * 2 + 0], rstd = st[g * 2 + 1];
+    const double m = (double)cpg * (double)S;
+    const double c2 = (db * mean - ds) * rstd * rstd * rstd / m;
+    const double c3 = -c2 * mean - db * rstd / m;
+    if (threadIdx.x < cpg) {
+        const int c = g * cpg + threadIdx.x;
         coef[((int64_t)n * 3 + 0) * C + c] = (float)((double)gamma[c] * rstd);
         coef[((int64_t)n * 3 + 1) * C + c] = (float)c2;
         coef[((int64_t)n * 3 + 2) * C + c] = (float)c3;
@@ -288,6 +272,7 @@ extern "C" int64_t b2_groupnorm_workspace_bytes(int N, int C) {
 static int gn_check(const char* who, int N, int C, int64_t S, int G) {
     if (C % 4 != 0 || C > kGnMaxC || C < 4) { set_error("%s: C must be a multiple of 4 in [4,%d] (got %d)", who, kGnMaxC, C); return B2_ERR_UNSUPPORTED; }
     if (G < 1 || C % G != 0) { set_error("%s: G must divide C (C=%d, G=%d)", who, C, G); return B2_ERR_BAD_ARG; }
+    if (C / G > kGnFinThreads) { set_error("%s: at most %d channels per group", who, kGnFinThreads); return B2_ERR_UNSUPPORTED; }
     if (N < 0 || S < 0) { set_error("%s: negative size", who); return B2_ERR_BAD_ARG; }
     return 0;
 }
@@ -306,7 +291,7 @@ extern "C" int b2_groupnorm_fwd(const float* x, const float* res, const float* g
     int nblocks = gn_nblocks(S);
     gn_partials_kernel<0><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
         nullptr, (const float4*)x, nullptr, partial, C, S, l.lpr, l.rpb, 0, nullptr, G);
-    gn_finalize_fwd<<<N, kGnFinThreads, 0, st>>>(partial, gamma, beta, stats, coef, C, S, G, eps, nblocks);
+    gn_finalize_fwd<<<dim3(G, N), kGnFinThreads, 0, st>>>(partial, gamma, beta, stats, coef, C, S, G, eps, nblocks);
     int gx = stream_grid(S * l.lpr, 256 * 4, kNumSMs * 8);
     gn_apply_fwd<<<dim3(gx, N), 256, 2 * C * sizeof(float), st>>>((const float4*)x, (const float4*)res, coef,
                                                                   (float4*)y, C, S, relu);
@@ -330,7 +315,7 @@ extern "C" int b2_groupnorm_bwd(const float* gy, const float* x, const float* y,
     gn_partials_kernel<1><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
         (const float4*)gy, (const float4*)x, (const float4*)y, partial, C, S, l.lpr, l.rpb, relu,
         stats, G);
-    gn_finalize_bwd<<<N, kGnFinThreads, 0, st>>>(partial, gamma, stats, coef, C, S, G, nblocks);
+    gn_finalize_bwd<<<dim3(G, N), kGnFinThreads, 0, st>>>(partial, gamma, stats, coef, C, S, G, nblocks);
     int gxd = stream_grid(S * l.lpr, 256 * 4, kNumSMs * 8);
     gn_apply_bwd<<<dim3(gxd, N), 256, 5 * C * sizeof(float), st>>>((const float4*)gy, (const float4*)x,
                                                                    (const float4*)y, coef, (float4*)gx,
