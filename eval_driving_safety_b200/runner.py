@@ -1,0 +1,145 @@
+"""Runnable mirrors of the reference's attack scripts on synthetic KITTI-shaped data.
+
+  python -m eval_driving_safety_b200.runner pgd   --iter 10 --alpha 0.0075 --eps 0.03 --pairs 8
+  python -m eval_driving_safety_b200.runner patch --ratio 0.2 --epochs 1 --iter 2 --pairs 8
+  torchrun --nproc-per-node 8 -m eval_driving_safety_b200.runner pgd --pairs 64 --iter 20
+
+Flags follow attack/DSGN/pgd_attack.py:53-55 (--iter/--alpha/--eps) and
+attack/DSGN/patch_attack.py:53-56 (--iter/--eps/--epochs/--ratio).  Pairs are sharded over the
+ranks (pair i -> rank i mod world); per-pair statistics are all-gathered at the end;
+the universal patch is kept identical on all ranks by all-reducing the clipped step.
+``--save-dir`` writes the per-iteration images in the reference's hand-off layout
+``<dir>/dsgn_pgd_iters_{k}/image_{2,3}/%06d.png`` (attack/DSGN/pgd_attack.py:357-374) with the
+reference's tensor2im convention (denormalise, *255, truncating uint8 cast, :157-178).
+"""
+import argparse
+import os
+import random
+
+import numpy as np
+import torch
+
+from . import attack, dsgn, engine, parallel, synthetic
+
+
+def tensor2im(img_norm):
+    """attack/DSGN/pgd_attack.py:157-178: [3,H,W] normalised tensor -> HxWx3 uint8 (truncation)."""
+    a = img_norm.detach().cpu().float().numpy().copy()
+    for i in range(3):
+        a[i] = a[i] * attack.IMAGENET_STD[i] + attack.IMAGENET_MEAN[i]
+    a = a * 255
+    return np.transpose(a, (1, 2, 0)).astype(np.uint8)
+
+
+def save_pair(save_dir, k, index, imgL, imgR, w, h):
+    from PIL import Image
+    for sub, img in (("image_2", imgL), ("image_3", imgR)):
+        d = os.path.join(save_dir, "dsgn_pgd_iters_%d" % k, sub)
+        os.makedirs(d, exist_ok=True)
+        Image.fromarray(tensor2im(img[0])).crop((0, 0, w, h)).save(os.path.join(d, "%06d.png" % index))
+
+
+def _setup(args):
+    rank, world = parallel.init()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cfg = dsgn.tiny_cfg() if args.tiny else dsgn.default_cfg()
+    h, w = (32, 64) if args.tiny else (384, 1248)
+    model = dsgn.build_model(cfg, seed=args.seed, device=dev)
+    calib = synthetic.make_calib(1, scale=h / 384, cu=w / 2, cv=h / 2) if args.tiny else synthetic.make_calib(1)
+    labels = {k: v.to(dev) for k, v in synthetic.make_labels(cfg, 1, 7).items()}
+    return rank, world, dev, cfg, (h, w), model, calib, labels
+
+
+def run_pgd(args):
+    rank, world, dev, cfg, (h, w), model, calib, labels = _setup(args)
+    mean = torch.tensor(attack.IMAGENET_MEAN, device=dev).view(1, 3, 1, 1)
+    std = torch.tensor(attack.IMAGENET_STD, device=dev).view(1, 3, 1, 1)
+    rows, eng = [], None
+    for i in parallel.shard_pairs(args.pairs, rank, world):
+        p = synthetic.make_pair(i, h, w, max_depth=cfg.max_depth)
+        xL, xR, disp = p["imgL"].to(dev), p["imgR"].to(dev), p["disp_L"].to(dev)
+        cL, cR = xL * std + mean, xR * std + mean
+        if eng is None:
+            eng = engine.PgdIterationGraph(model, cfg, labels, calib, args.alpha, args.eps, (xL, xR, cL, cR, disp),
+                                           norm=args.norm, use_graph=not args.eager)
+        if args.save_dir:
+            save_pair(args.save_dir, 0, i, xL, xR, w, h)
+        losses = []
+        for k in range(args.iter):
+            losses.append(eng.step(xL, xR, cL, cR, disp).clone())
+            if args.save_dir:
+                save_pair(args.save_dir, k + 1, i, xL, xR, w, h)
+        rows.append(parallel.pair_stats(i, losses, xL * std + mean, cL))
+    stats = parallel.gather_stats(rows, args.pairs)
+    if rank == 0:
+        print("pair  loss_0  loss_K  linf  l2  frac_changed")
+        for r in stats.tolist():
+            print("%4d  %.4f  %.4f  %.4f  %.3f  %.3f" % (int(r[0]), r[1], r[2], r[3], r[4], r[5]))
+    return stats
+
+
+def run_patch(args):
+    """attack/DSGN/patch_attack.py:278-443 with seeded centres; ranks process different images of
+    the same step and all-reduce the clipped patch step (world = 1 == the reference's sequence)."""
+    rank, world, dev, cfg, (h, w), model, calib, labels = _setup(args)
+    dim, radius = attack.patch_dim_radius(h, args.ratio)
+    patch = torch.zeros(1, 3, dim, dim, device=dev)                     # init_patch: zeros (:229)
+    rng = random.Random(args.seed)
+    alpha, losses_all = 1e3, []                                          # :279
+    steps = (args.pairs + world - 1) // world
+    for epoch in range(args.epochs):
+        for s in range(steps):
+            centres = [attack.generate_round_mask(radius, rng, h, w) for _ in range(world)]
+            i = s * world + rank
+            if i >= args.pairs:
+                i = i % args.pairs
+            cl, cr = centres[rank]
+            if cr[1] - radius < 0:                                       # tiny frames: keep the right box inside
+                cr = [cr[0], radius]
+            p = synthetic.make_pair(i, h, w, max_depth=cfg.max_depth)
+            xL, xR, disp = p["imgL"].to(dev), p["imgR"].to(dev), p["disp_L"].to(dev)
+            loss_fn = lambda out: dsgn.attack_loss(cfg, out, disp, labels)
+            hook = parallel.allreduce_patch_delta if world > 1 else None
+            patch, losses = attack.patch_attack_step(model, loss_fn, xL, xR, calib, patch, cl, cr, radius,
+                                                     iters=args.iter, alpha=alpha, eps=args.eps, delta_hook=hook)
+            losses_all.append(losses[-1])
+    if args.save_dir and rank == 0:
+        d = os.path.join(args.save_dir, "epoch%d" % args.epochs)
+        os.makedirs(d, exist_ok=True)
+        np.save(os.path.join(d, "patch.npy"), patch.cpu().numpy())       # :438-443
+    if rank == 0:
+        print("patch %dx%d  mean loss %.4f  |patch|max %.4f" % (dim, dim, torch.stack(losses_all).mean().item(),
+                                                               patch.abs().max().item()))
+    return patch
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
+    sub = ap.add_subparsers(dest="cmd", required=True)
+    a = sub.add_parser("pgd")
+    a.add_argument("--iter", type=int, default=4)                        # pgd_attack.py:53
+    a.add_argument("--alpha", type=float, default=1 / 255)               # :54
+    a.add_argument("--eps", type=float, default=0.3)                     # :55
+    a.add_argument("--norm", default="linf", choices=["linf", "l2"])
+    b = sub.add_parser("patch")
+    b.add_argument("--iter", type=int, default=2)                        # patch_attack.py:53
+    b.add_argument("--eps", type=float, default=8 / 255)                 # :54
+    b.add_argument("--epochs", type=int, default=80)                     # :55
+    b.add_argument("--ratio", type=float, default=0.2)                   # :56
+    for q in (a, b):
+        q.add_argument("--pairs", type=int, default=8)
+        q.add_argument("--seed", type=int, default=1)                    # :41
+        q.add_argument("--save-dir", default=None)
+        q.add_argument("--tiny", action="store_true", help="32x64 frames, shrunk volumes (tests)")
+        q.add_argument("--eager", action="store_true")
+    args = ap.parse_args(argv)
+    out = run_pgd(args) if args.cmd == "pgd" else run_patch(args)
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        torch.distributed.destroy_process_group()
+    return out
+
+
+if __name__ == "__main__":
+    main()

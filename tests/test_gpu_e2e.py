@@ -200,3 +200,29 @@ def test_patch_attack_loop_matches_oracle(setup):
         assert (patch_g.cpu() - patch_r).abs().max() <= 2 * eps * iters + 1e-6
         assert ((patch_g.cpu() - patch_r).abs() < 1e-5).float().mean() > 0.9
         assert losses.shape == (iters,)
+
+
+def test_runner_pgd_is_sharding_invariant_and_exports(built_lib, tmp_path):
+    """The reference-style PGD driver on 3 tiny pairs: per-pair results do not depend on how pairs are
+    sharded over ranks (independent units), statistics are consistent, PNG hand-off files appear."""
+    from eval_driving_safety_b200 import parallel, runner
+    from eval_driving_safety_b200 import ops
+    ops.set_conv_impl(1)
+    stats = runner.main(["pgd", "--tiny", "--pairs", "3", "--iter", "2", "--alpha", "0.0075", "--eps", "0.03",
+                         "--eager", "--save-dir", str(tmp_path)])
+    assert stats.shape == (3, len(parallel.STAT_FIELDS)) and stats[:, 0].tolist() == [0.0, 1.0, 2.0]
+    assert (stats[:, 3] <= 0.03 + 1e-6).all() and (stats[:, 3] > 0).all()        # linf of the perturbation
+    assert (tmp_path / "dsgn_pgd_iters_2" / "image_2" / "000002.png").exists()
+    assert (tmp_path / "dsgn_pgd_iters_0" / "image_3" / "000000.png").exists()
+    # graph-replayed path == eager path, bit for bit (same kernels, same order)
+    stats_g = runner.main(["pgd", "--tiny", "--pairs", "3", "--iter", "2", "--alpha", "0.0075", "--eps", "0.03"])
+    assert torch.equal(stats_g[:, 1:6], stats[:, 1:6])
+    ops.set_conv_impl(0)
+
+
+def test_runner_patch(built_lib, tmp_path):
+    from eval_driving_safety_b200 import runner
+    patch = runner.main(["patch", "--tiny", "--pairs", "2", "--epochs", "1", "--iter", "2", "--ratio", "0.2",
+                         "--save-dir", str(tmp_path)])
+    assert patch.shape == (1, 3, 7, 7) and 0 < patch.abs().max() <= 2 * 2 * (8 / 255) + 1e-6   # pairs*iters clipped steps
+    assert (tmp_path / "epoch1" / "patch.npy").exists()
