@@ -24,9 +24,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION/INFO; stdout must stay one JSON line
-if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout must carry exactly ONE JSON line, but NCCL / torch print a version banner to the C-level
+# stdout during init: park fd 1 on stderr for the whole run and emit the line on the saved fd.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
 
 import torch
 
@@ -254,7 +260,7 @@ def run_b200(args):
     }
     if not args.no_cpu_baseline and world == 1:
         line["cpu_baseline"] = cpu_baseline_sample()
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -328,7 +334,7 @@ def run_reference(args):
     sample = ("each step = 1 PGD iteration of the CPU oracle on a 384x%d W-crop of one pair (voxel grid cropped alike) "
               "= %.4f of a full pair's 3-D voxels; value scaled by that fraction to full-size pair-iterations/s"
               % (SAMPLE_W, frac))
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -336,7 +342,7 @@ def run_reference(args):
                                "un-vendored DSGN package and cannot run)", "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 def main():
