@@ -36,7 +36,7 @@ SIGNATURES = {
     "b2_grid_plan_fill": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_i64,
                                   c_int, c_vp]),
     "b2_grid_plan_sort": (c_int, [c_vp, c_vp, c_i64, c_vp]),
-    "b2_grid_sample_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_vp]),
+    "b2_grid_sample_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),
     "b2_conv3d": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_int, c_vp]),
     "b2_conv3d_c1_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),

@@ -25,42 +25,59 @@ __device__ __forceinline__ float4 lerp_valid(float4 r0, float4 r1, float f, floa
     return o;
 }
 
-// Channels-last forward.  One thread per float4 of the output row; consecutive
-// threads write consecutive 16 B -> fully coalesced 368 MB stream.
+// Channels-last forward.  One thread owns one float4 of one (n,h,w) feature row and walks the D
+// planes: the left value is loaded once and written D times, the right value is re-gathered per
+// plane from the L2-resident features; per-plane (integer shift, fraction) pairs sit in smem, so
+// the inner loop is address arithmetic-free.  For a fixed plane consecutive threads write
+// consecutive 16 B -> every store instruction is a fully coalesced 512 B per warp.
+constexpr int kCvMaxD = 256;
+
 __global__ void __launch_bounds__(kCvThreads)
 cost_volume_fwd_cl(const float4* __restrict__ left, const float4* __restrict__ right,
                    const float* __restrict__ shifts, float4* __restrict__ cost,
                    int N, int C4, int D, int H, int W) {
-    const int Q = 2 * C4;  // float4 per output voxel
-    const int64_t total = (int64_t)N * D * H * W * Q;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+    __shared__ int s_s0[kCvMaxD];
+    __shared__ float s_f[kCvMaxD];
+    const int n = blockIdx.y;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float s = __ldg(shifts + n * D + d), s0 = floorf(s);
+        s_s0[d] = (int)s0;
+        s_f[d] = __fsub_rn(s, s0);
+    }
+    __syncthreads();
+    const int Q = 2 * C4;
+    const int64_t per_n = (int64_t)H * W * Q;          // float4 per plane
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_n;
          i += (int64_t)gridDim.x * blockDim.x) {
-        int q = (int)(i % Q);
-        int64_t v = i / Q;
-        int w = (int)(v % W);
-        int h = (int)((v / W) % H);
-        int d = (int)((v / ((int64_t)W * H)) % D);
-        int n = (int)(v / ((int64_t)W * H * D));
-        float s = __ldg(shifts + n * D + d);
-        float s0 = floorf(s);
-        float f = __fsub_rn(s, s0);
-        int x0 = w - (int)s0;
-        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (x0 >= 0) {
-            int64_t row = ((int64_t)n * H + h) * W;
-            if (q < C4) {
-                o = __ldg(left + (row + w) * C4 + q);
-            } else {
-                int x0c = min(x0, W - 1);
-                float4 r0 = __ldg(right + (row + x0c) * C4 + (q - C4));
-                int x1 = x0 - 1;
-                float v1 = x1 >= 0 ? 1.f : 0.f;
-                int x1c = min(max(x1, 0), W - 1);
-                float4 r1 = __ldg(right + (row + x1c) * C4 + (q - C4));
-                o = lerp_valid(r0, r1, f, v1);
+        const int q = (int)(i % Q);
+        const int64_t p = i / Q;
+        const int w = (int)(p % W);
+        const int64_t row = (int64_t)n * H * W + (p - w);          // feature row index of (n,h,0)
+        float4* out = cost + (int64_t)n * D * per_n + i;
+        // blockIdx.z splits the planes into gridDim.z segments: more, shorter work items -> the
+        // last wave of blocks is a small fraction of the kernel (tail effect)
+        const int dseg = (D + gridDim.z - 1) / gridDim.z;
+        const int d_lo = blockIdx.z * dseg, d_hi = min(D, d_lo + dseg);
+        if (q < C4) {
+            const float4 l = __ldg(left + (row + w) * C4 + q);
+#pragma unroll 4
+            for (int d = d_lo; d < d_hi; ++d) out[(int64_t)d * per_n] = (w - s_s0[d] >= 0) ? l : zero;
+        } else {
+            const float4* rrow = right + row * C4 + (q - C4);
+#pragma unroll 4
+            for (int d = d_lo; d < d_hi; ++d) {
+                const int x0 = w - s_s0[d];
+                float4 o = zero;
+                if (x0 >= 0) {
+                    const float4 r0 = __ldg(rrow + (int64_t)min(x0, W - 1) * C4);
+                    const int x1 = x0 - 1;
+                    const float4 r1 = __ldg(rrow + (int64_t)min(max(x1, 0), W - 1) * C4);
+                    o = lerp_valid(r0, r1, s_f[d], x1 >= 0 ? 1.f : 0.f);
+                }
+                out[(int64_t)d * per_n] = o;
             }
         }
-        stg_stream(cost + i, o);
     }
 }
 
@@ -107,47 +124,48 @@ __global__ void __launch_bounds__(kCvThreads)
 cost_volume_bwd_cl(const float4* __restrict__ gcost, const float* __restrict__ shifts,
                    float4* __restrict__ gleft, float4* __restrict__ gright,
                    int N, int C4, int D, int H, int W) {
+    __shared__ int s_s0[kCvMaxD];
+    __shared__ float s_f[kCvMaxD];
+    const int n = blockIdx.y;
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        float s = __ldg(shifts + n * D + d), s0 = floorf(s);
+        s_s0[d] = (int)s0;
+        s_f[d] = s - s0;
+    }
+    __syncthreads();
     const int Q = 2 * C4;
-    const int64_t total = (int64_t)N * H * W * Q;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+    const int64_t per_n = (int64_t)H * W * Q;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < per_n;
          i += (int64_t)gridDim.x * blockDim.x) {
-        int q = (int)(i % Q);
-        int64_t p = i / Q;
-        int w = (int)(p % W);
-        int h = (int)((p / W) % H);
-        int n = (int)(p / ((int64_t)W * H));
+        const int q = (int)(i % Q);
+        const int64_t p = i / Q;
+        const int w = (int)(p % W);
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        const int64_t plane = (int64_t)H * W * Q;
-        const float4* gbase = gcost + (int64_t)n * D * plane + (int64_t)h * W * Q + q;
-        const float* sh = shifts + n * D;
+        const float4* gbase = gcost + (int64_t)n * D * per_n + i;     // (d = 0, h, w, q)
         if (q < C4) {
-#pragma unroll 4
+            // unconditional loads + select: the 8 loads of an unrolled trip are all in flight at once
+#pragma unroll 8
             for (int d = 0; d < D; ++d) {
-                int s0 = (int)floorf(__ldg(sh + d));
-                if (w - s0 >= 0) {
-                    float4 g = ldg_stream(gbase + d * plane + (int64_t)w * Q);
-                    acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
-                }
+                const float4 g = __ldg(gbase + (int64_t)d * per_n);
+                const float m = (w - s_s0[d] >= 0) ? 1.f : 0.f;
+                acc.x += m * g.x; acc.y += m * g.y; acc.z += m * g.z; acc.w += m * g.w;
             }
-            gleft[p * C4 + q] = acc;
+            gleft[((int64_t)n * H * W + p) * C4 + q] = acc;
         } else {
-#pragma unroll 4
+#pragma unroll 8
             for (int d = 0; d < D; ++d) {
-                float s = __ldg(sh + d);
-                float s0f = floorf(s);
-                float f = s - s0f;
-                int wa = w + (int)s0f;
-                if (wa < W) {
-                    float4 g = ldg_stream(gbase + d * plane + (int64_t)wa * Q);
-                    float a = 1.f - f;
-                    acc.x += a * g.x; acc.y += a * g.y; acc.z += a * g.z; acc.w += a * g.w;
-                }
-                if (wa + 1 < W) {
-                    float4 g = ldg_stream(gbase + d * plane + (int64_t)(wa + 1) * Q);
-                    acc.x += f * g.x; acc.y += f * g.y; acc.z += f * g.z; acc.w += f * g.w;
-                }
+                const int sa = s_s0[d];
+                const float f = s_f[d];
+                // columns w+s0 and w+s0+1, clamped into the row; out-of-row terms get weight 0
+                const int c0 = min(w + sa, W - 1) - w, c1 = min(w + sa + 1, W - 1) - w;
+                const float4* gp = gbase + (int64_t)d * per_n;
+                const float4 g0 = __ldg(gp + (int64_t)c0 * Q);
+                const float4 g1 = __ldg(gp + (int64_t)c1 * Q);
+                const float a = (w + sa < W) ? 1.f - f : 0.f, bb = (w + sa + 1 < W) ? f : 0.f;
+                acc.x += a * g0.x; acc.y += a * g0.y; acc.z += a * g0.z; acc.w += a * g0.w;
+                acc.x += bb * g1.x; acc.y += bb * g1.y; acc.z += bb * g1.z; acc.w += bb * g1.w;
             }
-            gright[p * C4 + (q - C4)] = acc;
+            gright[((int64_t)n * H * W + p) * C4 + (q - C4)] = acc;
         }
     }
 }
@@ -202,9 +220,10 @@ extern "C" int b2_cost_volume_fwd(const float* left, const float* right, const f
     if (layout == 1) {
         B2_REQUIRE(C % 4 == 0, "cost_volume_fwd: channels-last layout needs C %% 4 == 0 (C=%d)", C);
         B2_REQUIRE(aligned16(left) && aligned16(right) && aligned16(cost), "cost_volume_fwd: pointers must be 16B aligned");
-        int grid = stream_grid(total / 4, kCvThreads, kNumSMs * 32);
-        cost_volume_fwd_cl<<<grid, kCvThreads, 0, st>>>((const float4*)left, (const float4*)right, shifts,
-                                                       (float4*)cost, N, C / 4, D, H, W);
+        B2_REQUIRE(D <= kCvMaxD, "cost_volume_fwd: at most %d planes", kCvMaxD);
+        int grid = stream_grid((int64_t)H * W * (C / 2), kCvThreads, kNumSMs * 16);
+        cost_volume_fwd_cl<<<dim3(grid, N, D >= 16 ? 4 : 1), kCvThreads, 0, st>>>((const float4*)left, (const float4*)right, shifts,
+                                                                 (float4*)cost, N, C / 4, D, H, W);
     } else if (layout == 0) {
         int grid = stream_grid(total, kCvThreads, kNumSMs * 32);
         cost_volume_fwd_ncdhw<<<grid, kCvThreads, 0, st>>>(left, right, shifts, cost, N, C, D, H, W);
@@ -225,9 +244,10 @@ extern "C" int b2_cost_volume_bwd(const float* gcost, const float* shifts, float
     if (layout == 1) {
         B2_REQUIRE(C % 4 == 0, "cost_volume_bwd: channels-last layout needs C %% 4 == 0 (C=%d)", C);
         B2_REQUIRE(aligned16(gcost) && aligned16(gleft) && aligned16(gright), "cost_volume_bwd: pointers must be 16B aligned");
-        int grid = stream_grid(total / 4, kCvThreads, kNumSMs * 32);
-        cost_volume_bwd_cl<<<grid, kCvThreads, 0, st>>>((const float4*)gcost, shifts, (float4*)gleft,
-                                                       (float4*)gright, N, C / 4, D, H, W);
+        B2_REQUIRE(D <= kCvMaxD, "cost_volume_bwd: at most %d planes", kCvMaxD);
+        int grid = stream_grid((int64_t)H * W * (C / 2), kCvThreads, kNumSMs * 16);
+        cost_volume_bwd_cl<<<dim3(grid, N), kCvThreads, 0, st>>>((const float4*)gcost, shifts, (float4*)gleft,
+                                                                 (float4*)gright, N, C / 4, D, H, W);
     } else if (layout == 0) {
         int grid = stream_grid(total, kCvThreads, kNumSMs * 32);
         cost_volume_bwd_ncdhw<<<grid, kCvThreads, 0, st>>>(gcost, shifts, gleft, gright, N, C, D, H, W);

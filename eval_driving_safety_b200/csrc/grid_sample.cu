@@ -155,31 +155,46 @@ grid_plan_sort_kernel(const int32_t* __restrict__ row_ptr, int2* __restrict__ en
     }
 }
 
-// Gather backward: a sub-warp of LPV lanes owns one input cell.
-template <int LPV>
+// Gather backward: a group of LPV*SPLIT lanes owns one input cell (a lane = one float4 of
+// channels).  SPLIT = 1: sub-warp per cell (short rows, e.g. ~6 entries per PSV cell).
+// SPLIT = 32/LPV: a whole warp per cell whose sub-groups take every SPLIT-th CSR entry (an
+// image-feature pixel receives from ~150 voxels along its ray); the sub-group partial sums are
+// combined by a fixed shuffle tree.  Either way the summation order depends only on the plan.
+template <int LPV, int SPLIT>
 __global__ void __launch_bounds__(256)
 grid_sample_bwd_kernel(const float* __restrict__ gout, const int32_t* __restrict__ row_ptr,
                        const int2* __restrict__ entries, float4* __restrict__ gin, int64_t ncell,
                        int gout_cstride, int gout_coff) {
-    const int lane = threadIdx.x % LPV;
-    const int64_t cstride = (int64_t)gridDim.x * (blockDim.x / LPV);
-    for (int64_t c = (int64_t)blockIdx.x * (blockDim.x / LPV) + threadIdx.x / LPV; c < ncell; c += cstride) {
-        int b = __ldg(row_ptr + c), e = __ldg(row_ptr + c + 1);
+    constexpr int GS = LPV * SPLIT;                 // lanes per cell
+    const int cl = threadIdx.x % LPV, sub = (threadIdx.x / LPV) % SPLIT;
+    const int64_t cstride = (int64_t)gridDim.x * (blockDim.x / GS);
+    // the loop bound is warp-uniform (first cell of the warp) because of the shuffles below
+    for (int64_t c0 = (int64_t)blockIdx.x * (blockDim.x / GS) + (threadIdx.x / 32) * (32 / GS); c0 < ncell; c0 += cstride) {
+        const int64_t c = c0 + (threadIdx.x & 31) / GS;
+        const bool valid = c < ncell;
+        const int b = valid ? __ldg(row_ptr + c) : 0, e = valid ? __ldg(row_ptr + c + 1) : 0;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        int i = b;
-        for (; i + 1 < e; i += 2) {  // two independent loads in flight
-            int2 e0 = __ldg(entries + i), e1 = __ldg(entries + i + 1);
-            float4 g0 = __ldg(reinterpret_cast<const float4*>(gout + (int64_t)e0.x * gout_cstride + gout_coff) + lane);
-            float4 g1 = __ldg(reinterpret_cast<const float4*>(gout + (int64_t)e1.x * gout_cstride + gout_coff) + lane);
+        int i = b + sub;
+        for (; i + SPLIT < e; i += 2 * SPLIT) {  // two independent loads in flight
+            int2 e0 = __ldg(entries + i), e1 = __ldg(entries + i + SPLIT);
+            float4 g0 = __ldg(reinterpret_cast<const float4*>(gout + (int64_t)e0.x * gout_cstride + gout_coff) + cl);
+            float4 g1 = __ldg(reinterpret_cast<const float4*>(gout + (int64_t)e1.x * gout_cstride + gout_coff) + cl);
             fma4(acc, __int_as_float(e0.y), g0);
             fma4(acc, __int_as_float(e1.y), g1);
         }
         if (i < e) {
             int2 e0 = __ldg(entries + i);
-            float4 g0 = __ldg(reinterpret_cast<const float4*>(gout + (int64_t)e0.x * gout_cstride + gout_coff) + lane);
+            float4 g0 = __ldg(reinterpret_cast<const float4*>(gout + (int64_t)e0.x * gout_cstride + gout_coff) + cl);
             fma4(acc, __int_as_float(e0.y), g0);
         }
-        gin[c * LPV + lane] = acc;
+#pragma unroll
+        for (int off = GS / 2; off >= LPV; off >>= 1) {
+            acc.x += __shfl_down_sync(0xffffffffu, acc.x, off, GS);
+            acc.y += __shfl_down_sync(0xffffffffu, acc.y, off, GS);
+            acc.z += __shfl_down_sync(0xffffffffu, acc.z, off, GS);
+            acc.w += __shfl_down_sync(0xffffffffu, acc.w, off, GS);
+        }
+        if (valid && sub == 0) gin[c * LPV + cl] = acc;
     }
 }
 
@@ -275,16 +290,22 @@ extern "C" int b2_grid_plan_sort(const int32_t* row_ptr, void* entries, int64_t 
 
 extern "C" int b2_grid_sample_bwd(const float* gout, const int32_t* row_ptr, const void* entries,
                                   float* gin, int64_t ncell, int C, int gout_cstride, int gout_coff,
-                                  void* stream) {
+                                  int long_rows, void* stream) {
     B2_REQUIRE(gout && row_ptr && entries && gin, "grid_sample_bwd: null pointer");
     B2_REQUIRE(C % 4 == 0 && gout_cstride % 4 == 0 && gout_coff % 4 == 0 && aligned16(gout) && aligned16(gin),
                "grid_sample_bwd: channel counts/offsets must be multiples of 4 and pointers 16B aligned");
     if (ncell == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     B2_LPV_SWITCH(C, {
-        int grid_x = stream_grid(ncell, 256 / LPV, kNumSMs * 16);
-        grid_sample_bwd_kernel<LPV><<<grid_x, 256, 0, st>>>(gout, row_ptr, (const int2*)entries, (float4*)gin,
-                                                           ncell, gout_cstride, gout_coff);
+        if (long_rows) {
+            int grid_x = stream_grid(ncell, 256 / 32, kNumSMs * 32);
+            grid_sample_bwd_kernel<LPV, 32 / LPV><<<grid_x, 256, 0, st>>>(gout, row_ptr, (const int2*)entries,
+                                                                         (float4*)gin, ncell, gout_cstride, gout_coff);
+        } else {
+            int grid_x = stream_grid(ncell, 256 / LPV, kNumSMs * 16);
+            grid_sample_bwd_kernel<LPV, 1><<<grid_x, 256, 0, st>>>(gout, row_ptr, (const int2*)entries, (float4*)gin,
+                                                                  ncell, gout_cstride, gout_coff);
+        }
     });
     return check_launch("grid_sample_bwd");
 }

@@ -35,41 +35,38 @@ __device__ __forceinline__ float pgd_elem(float x, float g, float c, float alpha
 constexpr int kPgdThreads = 256;
 constexpr int kPgdUnroll = 4;
 
-// One launch over every image of every set.  per_set4 = n_img*C*hw/4 float4s.
+// One launch over every image of every set.  blockIdx.y = (set, image, channel) plane, so the
+// channel constants are block-uniform and no thread ever divides; blockIdx.x tiles the plane in
+// chunks of kPgdThreads*kPgdUnroll float4 (loads of a chunk are all issued before the first use).
 __global__ void __launch_bounds__(kPgdThreads)
-pgd_update_vec4(PgdSets s, int n_sets, int64_t per_set4, int64_t hw4, int C, float alpha, float eps,
-                int denorm, ChanParams cp) {
-    const int64_t total = per_set4 * n_sets;
-    const int64_t tile = (int64_t)kPgdThreads * kPgdUnroll;
-    for (int64_t base = (int64_t)blockIdx.x * tile; base < total; base += (int64_t)gridDim.x * tile) {
+pgd_update_vec4(PgdSets s, int planes_per_set, int C, int hw4, float alpha, float eps, int denorm, ChanParams cp) {
+    const int plane = blockIdx.y;
+    const int si = plane / planes_per_set, pl = plane - si * planes_per_set;
+    const int ch = pl % C;
+    const float m = cp.mean[ch], sd = cp.std_[ch], lo = cp.lo[ch], hi = cp.hi[ch];
+    const int64_t off = (int64_t)pl * hw4;
+    const float4* x = reinterpret_cast<const float4*>(s.x[si]) + off;
+    const float4* g = reinterpret_cast<const float4*>(s.g[si]) + off;
+    const float4* c = reinterpret_cast<const float4*>(s.c[si]) + off;
+    float4* o = reinterpret_cast<float4*>(s.o[si]) + off;
+    const int tile = kPgdThreads * kPgdUnroll;
+    for (int base = blockIdx.x * tile; base < hw4; base += gridDim.x * tile) {
         float4 xv[kPgdUnroll], gv[kPgdUnroll], cv[kPgdUnroll];
-        int64_t idx[kPgdUnroll];
-        int set[kPgdUnroll];
 #pragma unroll
         for (int u = 0; u < kPgdUnroll; ++u) {
-            int64_t i = base + (int64_t)u * kPgdThreads + threadIdx.x;
-            bool ok = i < total;
-            int si = ok ? (int)(i / per_set4) : 0;
-            int64_t li = ok ? i - (int64_t)si * per_set4 : 0;
-            set[u] = ok ? si : -1;
-            idx[u] = li;
-            if (ok) {
-                xv[u] = ldg_stream(reinterpret_cast<const float4*>(s.x[si]) + li);
-                gv[u] = ldg_stream(reinterpret_cast<const float4*>(s.g[si]) + li);
-                cv[u] = ldg_stream(reinterpret_cast<const float4*>(s.c[si]) + li);
-            }
+            const int i = base + u * kPgdThreads + threadIdx.x;
+            if (i < hw4) { xv[u] = ldg_stream(x + i); gv[u] = ldg_stream(g + i); cv[u] = ldg_stream(c + i); }
         }
 #pragma unroll
         for (int u = 0; u < kPgdUnroll; ++u) {
-            if (set[u] < 0) continue;
-            int ch = (int)((idx[u] / hw4) % C);
-            float m = cp.mean[ch], sd = cp.std_[ch], lo = cp.lo[ch], hi = cp.hi[ch];
+            const int i = base + u * kPgdThreads + threadIdx.x;
+            if (i >= hw4) continue;
             float4 r;
             r.x = pgd_elem(xv[u].x, gv[u].x, cv[u].x, alpha, eps, denorm, m, sd, lo, hi);
             r.y = pgd_elem(xv[u].y, gv[u].y, cv[u].y, alpha, eps, denorm, m, sd, lo, hi);
             r.z = pgd_elem(xv[u].z, gv[u].z, cv[u].z, alpha, eps, denorm, m, sd, lo, hi);
             r.w = pgd_elem(xv[u].w, gv[u].w, cv[u].w, alpha, eps, denorm, m, sd, lo, hi);
-            stg_stream(reinterpret_cast<float4*>(s.o[set[u]]) + idx[u], r);
+            stg_stream(o + i, r);
         }
     }
 }
@@ -252,10 +249,13 @@ extern "C" int b2_pgd_update(const float* const* x, const float* const* g, const
     int64_t per_set = (int64_t)n_img * C * hw;
     if (per_set == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (vec) {
-        int64_t per4 = per_set / 4;
-        int grid = stream_grid(per4 * n_sets, kPgdThreads * kPgdUnroll);
-        pgd_update_vec4<<<grid, kPgdThreads, 0, st>>>(s, n_sets, per4, hw / 4, C, alpha, eps, denorm, cp);
+    if (vec && hw / 4 < (int64_t)1 << 30 && (int64_t)n_sets * n_img * C <= 65535) {
+        const int hw4 = (int)(hw / 4);
+        const int planes = n_img * C;
+        int gx = (hw4 + kPgdThreads * kPgdUnroll - 1) / (kPgdThreads * kPgdUnroll);
+        const int cap = (kNumSMs * 16 + planes * n_sets - 1) / (planes * n_sets);     // keep ~16 blocks per SM overall
+        if (gx > cap) gx = cap < 1 ? 1 : cap;
+        pgd_update_vec4<<<dim3(gx, planes * n_sets), kPgdThreads, 0, st>>>(s, planes, C, hw4, alpha, eps, denorm, cp);
     } else {
         int grid = stream_grid(per_set * n_sets, kPgdThreads);
         pgd_update_scalar<<<grid, kPgdThreads, 0, st>>>(s, n_sets, per_set, hw, C, alpha, eps, denorm, cp);

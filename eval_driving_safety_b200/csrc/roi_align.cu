@@ -66,67 +66,87 @@ roi_align_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ r
     }
 }
 
-// Gather backward.  One thread per feature element (c, y, x) of batch 0..B-1; RoIs
-// are visited in index order and samples in (iy, ix) order -> fixed summation order.
-// For a pixel y the contributing sample rows are those whose (clamped) position lies
-// in (y-1, y+1]; candidates are enumerated generously and filtered with the exact
-// forward arithmetic.
-constexpr int kRoiChunk = 128;
+// Gather backward.  One thread per feature element (c, y, x); a block covers 256 consecutive x of
+// one (c, y) row.  Phase 1: the block builds, in RoI order (ballot + prefix, deterministic), the
+// list of RoIs whose sample footprint touches its row segment -- typically a handful of the R
+// RoIs.  Phase 2: every thread visits only those RoIs, samples in (iy, ix) order -> fixed
+// summation order, no atomics on floats.
+constexpr int kRoiMaxList = 1024;
 
 __global__ void __launch_bounds__(256)
 roi_align_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ rois,
                      float* __restrict__ gfeat, int R, int B, int C, int H, int W, int P, float scale) {
-    __shared__ float s_roi[kRoiChunk][5];
-    const int64_t total = (int64_t)B * C * H * W;
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool live = i < total;
-    int x = 0, y = 0, c = 0, b = 0;
-    if (live) {
-        x = (int)(i % W); y = (int)((i / W) % H);
-        c = (int)((i / ((int64_t)W * H)) % C); b = (int)(i / ((int64_t)W * H * C));
+    __shared__ int s_list[kRoiMaxList];
+    __shared__ int s_wcount[8];
+    __shared__ int s_n;
+    const int xseg = blockIdx.x * 256, y = blockIdx.y % H, c = (blockIdx.y / H) % C, b = blockIdx.y / (H * C);
+    const int x = xseg + threadIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    for (int r0 = 0; r0 < R; r0 += 256) {
+        const int r = r0 + threadIdx.x;
+        bool hit = false;
+        if (r < R) {
+            const float* roi = rois + r * 5;
+            if ((int)roi[0] == b) {
+                const float sw = roi[1] * scale, sh = roi[2] * scale, ew = roi[3] * scale, eh = roi[4] * scale;
+                const float rw = fmaxf(ew - sw, 1.f), rh = fmaxf(eh - sh, 1.f);
+                // samples lie inside [start, start + size]; a sample at p touches pixels floor(p), floor(p)+1
+                hit = (float)y >= sh - 2.f && (float)y <= sh + rh + 1.f &&
+                      (float)(xseg + 255) >= sw - 2.f && (float)xseg <= sw + rw + 1.f;
+            }
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) s_wcount[warp] = __popc(m);
+        __syncthreads();
+        int base = s_n;
+        for (int k = 0; k < warp; ++k) base += s_wcount[k];
+        if (hit) {
+            const int pos = base + __popc(m & ((1u << lane) - 1));
+            if (pos < kRoiMaxList) s_list[pos] = r;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = s_n; for (int k = 0; k < 8; ++k) t += s_wcount[k]; s_n = t; }
+        __syncthreads();
     }
+    const int nlist = min(s_n, kRoiMaxList);
+    if (x >= W) return;
     float acc = 0.f;
-    for (int r0 = 0; r0 < R; r0 += kRoiChunk) {
-        int nr = min(kRoiChunk, R - r0);
-        __syncthreads();
-        for (int k = threadIdx.x; k < nr * 5; k += blockDim.x) s_roi[k / 5][k % 5] = rois[(r0 + k / 5) * 5 + k % 5];
-        __syncthreads();
-        if (!live) continue;
-        for (int rr = 0; rr < nr; ++rr) {
-            const float* roi = s_roi[rr];
-            if ((int)roi[0] != b) continue;
-            RoiGeom g = roi_geom(roi, scale, P);
-            float sy = g.bin_h / (float)g.grid_h, sx = g.bin_w / (float)g.grid_w;
-            int ny = P * g.grid_h, nx = P * g.grid_w;
-            // sample j sits at start + (j + .5) * s ; want positions in [y-1, y+1]
-            int jy0 = max(0, (int)floorf(((float)y - 1.f - g.start_h) / sy - 0.5f) - 1);
-            int jy1 = min(ny - 1, (int)ceilf(((float)y + 1.f - g.start_h) / sy - 0.5f) + 1);
-            if (jy0 > jy1) continue;
-            int jx0 = max(0, (int)floorf(((float)x - 1.f - g.start_w) / sx - 0.5f) - 1);
-            int jx1 = min(nx - 1, (int)ceilf(((float)x + 1.f - g.start_w) / sx - 0.5f) + 1);
-            if (jx0 > jx1) continue;
-            float inv = 1.f / (float)(g.grid_h * g.grid_w);
-            const float* go = gout + ((int64_t)(r0 + rr) * C + c) * P * P;
-            for (int jy = jy0; jy <= jy1; ++jy) {
-                int ph = jy / g.grid_h, iy = jy % g.grid_h;
-                float py = g.start_h + ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.grid_h;
-                int yl, yh; float wyl, wyh;
-                if (!axis_interp(py, H, yl, yh, wyl, wyh)) continue;
-                float wy = (yl == y ? wyl : 0.f) + (yh == y ? wyh : 0.f);
-                if (yl != y && yh != y) continue;
-                for (int jx = jx0; jx <= jx1; ++jx) {
-                    int pw = jx / g.grid_w, ix = jx % g.grid_w;
-                    float px = g.start_w + pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.grid_w;
-                    int xl, xh; float wxl, wxh;
-                    if (!axis_interp(px, W, xl, xh, wxl, wxh)) continue;
-                    if (xl != x && xh != x) continue;
-                    float wx = (xl == x ? wxl : 0.f) + (xh == x ? wxh : 0.f);
-                    acc += wy * wx * __ldg(go + ph * P + pw) * inv;
-                }
+    for (int li = 0; li < nlist; ++li) {
+        const int r = s_list[li];
+        const float* roi = rois + r * 5;
+        float rr[5] = {__ldg(roi), __ldg(roi + 1), __ldg(roi + 2), __ldg(roi + 3), __ldg(roi + 4)};
+        RoiGeom g = roi_geom(rr, scale, P);
+        const float sy = g.bin_h / (float)g.grid_h, sx = g.bin_w / (float)g.grid_w;
+        const int ny = P * g.grid_h, nx = P * g.grid_w;
+        const int jy0 = max(0, (int)floorf(((float)y - 1.f - g.start_h) / sy - 0.5f) - 1);
+        const int jy1 = min(ny - 1, (int)ceilf(((float)y + 1.f - g.start_h) / sy - 0.5f) + 1);
+        if (jy0 > jy1) continue;
+        const int jx0 = max(0, (int)floorf(((float)x - 1.f - g.start_w) / sx - 0.5f) - 1);
+        const int jx1 = min(nx - 1, (int)ceilf(((float)x + 1.f - g.start_w) / sx - 0.5f) + 1);
+        if (jx0 > jx1) continue;
+        const float inv = 1.f / (float)(g.grid_h * g.grid_w);
+        const float* go = gout + ((int64_t)r * C + c) * P * P;
+        for (int jy = jy0; jy <= jy1; ++jy) {
+            const int ph = jy / g.grid_h, iy = jy % g.grid_h;
+            const float py = g.start_h + ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.grid_h;
+            int yl, yh; float wyl, wyh;
+            if (!axis_interp(py, H, yl, yh, wyl, wyh)) continue;
+            if (yl != y && yh != y) continue;
+            const float wy = (yl == y ? wyl : 0.f) + (yh == y ? wyh : 0.f);
+            for (int jx = jx0; jx <= jx1; ++jx) {
+                const int pw = jx / g.grid_w, ix = jx % g.grid_w;
+                const float px = g.start_w + pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.grid_w;
+                int xl, xh; float wxl, wxh;
+                if (!axis_interp(px, W, xl, xh, wxl, wxh)) continue;
+                if (xl != x && xh != x) continue;
+                const float wx = (xl == x ? wxl : 0.f) + (xh == x ? wxh : 0.f);
+                acc += wy * wx * __ldg(go + ph * P + pw) * inv;
             }
         }
     }
-    if (live) gfeat[i] = acc;
+    gfeat[(((int64_t)b * C + c) * H + y) * W + x] = acc;
 }
 
 }  // namespace b2
@@ -148,8 +168,8 @@ extern "C" int b2_roi_align_bwd(const float* gout, const float* rois, float* gfe
                                 int W, int P, float scale, void* stream) {
     B2_REQUIRE(gfeat && (R == 0 || (gout && rois)), "roi_align_bwd: null pointer");
     B2_REQUIRE(P >= 1 && C >= 1 && H >= 1 && W >= 1, "roi_align_bwd: bad dims");
-    int64_t total = (int64_t)C * H * W;   // batch of 1 (the attack scripts run batch size 1)
-    roi_align_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        gout, rois, gfeat, R, 1, C, H, W, P, scale);
+    B2_REQUIRE((int64_t)C * H <= 65535, "roi_align_bwd: C*H = %lld exceeds the grid limit 65535", (long long)C * H);
+    dim3 grid((W + 255) / 256, C * H);     // batch of 1 (the attack scripts run batch size 1)
+    roi_align_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gout, rois, gfeat, R, 1, C, H, W, P, scale);
     return check_launch("roi_align_bwd");
 }

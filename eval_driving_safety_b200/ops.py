@@ -206,6 +206,7 @@ class GridPlan:
         check(lib.b2_grid_plan_sort(_p(row_ptr), _p(entries), ncell, st), "grid_plan_sort")
         self.row_ptr, self.entries, self.ncell, self.nnz = row_ptr, entries, ncell, nnz
         self.ndim, self.in_spatial, self.n = ndim, tuple(in_spatial), n
+        self.long_rows = int(nnz > 32 * ncell)       # mean CSR row length decides the backward's mapping
 
 
 def _gs_fwd(lib, inp, grid, out, out_c, coff, align):
@@ -256,7 +257,7 @@ class GridSampleFn(Function):
         gin = empty_cl3(*ctx.in_shape, g.device) if nd == 3 else empty_cl2(*ctx.in_shape, g.device)
         with _op("grid_sample%dd_bwd" % nd, 1, 4 * (g.numel() + gin.numel()) + 8 * plan.nnz + 4 * plan.ncell):
             check(lib.b2_grid_sample_bwd(_p(g), _p(plan.row_ptr), _p(plan.entries), _p(gin), plan.ncell, c, c, 0,
-                                         _stream()), "grid_sample_bwd")
+                                         plan.long_rows, _stream()), "grid_sample_bwd")
         return gin, None, None, None
 
 
@@ -297,10 +298,10 @@ class LiftFn(Function):
         nv = g.numel() // ctot
         with _op("grid_sample3d_bwd", 1, 4 * (nv * s3[1] + g3.numel()) + 8 * p3.nnz + 4 * p3.ncell):
             check(lib.b2_grid_sample_bwd(_p(g), _p(p3.row_ptr), _p(p3.entries), _p(g3), p3.ncell, s3[1], ctot, 0,
-                                         _stream()), "grid_sample_bwd(3d)")
+                                         p3.long_rows, _stream()), "grid_sample_bwd(3d)")
         with _op("grid_sample2d_bwd", 1, 4 * (nv * s2[1] + g2.numel()) + 8 * p2.nnz + 4 * p2.ncell):
             check(lib.b2_grid_sample_bwd(_p(g), _p(p2.row_ptr), _p(p2.entries), _p(g2), p2.ncell, s2[1], ctot, s3[1],
-                                         _stream()), "grid_sample_bwd(2d)")
+                                         p2.long_rows, _stream()), "grid_sample_bwd(2d)")
         return g3, g2, None, None, None, None
 
 

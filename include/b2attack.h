@@ -134,7 +134,8 @@ int b2_grid_plan_fill(const float* grid, const int32_t* row_ptr, int32_t* cursor
                       int align_corners, void* stream);
 int b2_grid_plan_sort(const int32_t* row_ptr, void* entries, int64_t ncell, void* stream);
 int b2_grid_sample_bwd(const float* gout, const int32_t* row_ptr, const void* entries, float* gin,
-                       int64_t ncell, int C, int gout_cstride, int gout_coff, void* stream);
+                       int64_t ncell, int C, int gout_cstride, int gout_coff, int long_rows, void* stream);
+/* long_rows != 0: a whole warp walks each CSR row (rows of >~ 32 entries, e.g. the 2-D lifting). */
 
 /* ------------------------------------------------------------------------- *
  * (3) 3-D convolutions of the hourglass stacks -- replaces cuDNN Conv3d /

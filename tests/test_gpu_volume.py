@@ -303,3 +303,24 @@ def test_bev_pool_vs_torch(ops):
         assert out.shape == ref.shape and max_err(out.cpu(), ref) < 1e-6
         (gv,) = torch.autograd.grad(out, vc, gy.cuda())
         assert max_err(gv.cpu(), gv_ref) < 1e-6
+
+
+@pytest.mark.parametrize("c", [32, 64])
+def test_grid_sample_bwd_both_row_mappings(ops, c):
+    """The CSR backward has two thread mappings (sub-warp per cell / whole warp per cell with split
+    rows); both must give the reference gradient and each must be bitwise reproducible."""
+    g = torch.Generator().manual_seed(40 + c)
+    x = torch.randn(1, c, 6, 7, generator=g, requires_grad=True)
+    grid = torch.rand(1, 40, 50, 2, generator=g) * 2.2 - 1.1          # ~48 samples per input pixel
+    ref = F.grid_sample(x, grid, mode='bilinear', padding_mode='zeros', align_corners=True)
+    gy = torch.randn(ref.shape, generator=g)
+    (gx_ref,) = torch.autograd.grad(ref, x, gy)
+    xc = x.detach().cuda().requires_grad_(True)
+    for long_rows in (0, 1):
+        plan = ops.GridPlan(grid.cuda(), (6, 7), True)
+        plan.long_rows = long_rows
+        res = []
+        for _ in range(2):
+            out = ops.grid_sample(xc, grid.cuda(), True, plan)
+            res.append(torch.autograd.grad(out, xc, gy.cuda())[0])
+        assert max_err(res[0].cpu(), gx_ref) < 2e-4 and torch.equal(res[0], res[1])
