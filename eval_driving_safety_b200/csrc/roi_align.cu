@@ -66,68 +66,54 @@ roi_align_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ r
     }
 }
 
-// Gather backward.  One thread per feature element (c, y, x); a block covers 256 consecutive x of
-// one (c, y) row.  Phase 1: the block builds, in RoI order (ballot + prefix, deterministic), the
-// list of RoIs whose sample footprint touches its row segment -- typically a handful of the R
-// RoIs.  Phase 2: every thread visits only those RoIs, samples in (iy, ix) order -> fixed
-// summation order, no atomics on floats.
-constexpr int kRoiMaxList = 1024;
+// Gather backward.  One thread per feature PIXEL (y, x): the (RoI, bin, weight) contributions that
+// reach the pixel do not depend on the channel, so they are enumerated once (RoIs in index order,
+// samples in (iy, ix) order) into a small per-thread list and then replayed for all C channels --
+// the enumeration cost is amortised 256x and the summation order is fixed (deterministic, no
+// float atomics).  A list that fills up is flushed (accumulating into gfeat) and refilled.
+constexpr int kRoiEntries = 96;
 
-__global__ void __launch_bounds__(256)
+struct RoiEntry { int off; float w; };   // off = r*C*P*P + ph*P + pw ; the channel adds c*P*P
+
+__device__ __forceinline__ void roi_flush(const RoiEntry* e, int n, const float* __restrict__ gout,
+                                          float* __restrict__ gp, int C, int PP, int64_t cstride, bool first) {
+    for (int c = 0; c < C; ++c) {
+        float acc = first ? 0.f : gp[(int64_t)c * cstride];
+        const float* gc = gout + (int64_t)c * PP;
+        for (int k = 0; k < n; ++k) acc += e[k].w * __ldg(gc + e[k].off);
+        gp[(int64_t)c * cstride] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(128)
 roi_align_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ rois,
                      float* __restrict__ gfeat, int R, int B, int C, int H, int W, int P, float scale) {
-    __shared__ int s_list[kRoiMaxList];
-    __shared__ int s_wcount[8];
-    __shared__ int s_n;
-    const int xseg = blockIdx.x * 256, y = blockIdx.y % H, c = (blockIdx.y / H) % C, b = blockIdx.y / (H * C);
-    const int x = xseg + threadIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-    for (int r0 = 0; r0 < R; r0 += 256) {
-        const int r = r0 + threadIdx.x;
-        bool hit = false;
-        if (r < R) {
-            const float* roi = rois + r * 5;
-            if ((int)roi[0] == b) {
-                const float sw = roi[1] * scale, sh = roi[2] * scale, ew = roi[3] * scale, eh = roi[4] * scale;
-                const float rw = fmaxf(ew - sw, 1.f), rh = fmaxf(eh - sh, 1.f);
-                // samples lie inside [start, start + size]; a sample at p touches pixels floor(p), floor(p)+1
-                hit = (float)y >= sh - 2.f && (float)y <= sh + rh + 1.f &&
-                      (float)(xseg + 255) >= sw - 2.f && (float)xseg <= sw + rw + 1.f;
-            }
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) s_wcount[warp] = __popc(m);
-        __syncthreads();
-        int base = s_n;
-        for (int k = 0; k < warp; ++k) base += s_wcount[k];
-        if (hit) {
-            const int pos = base + __popc(m & ((1u << lane) - 1));
-            if (pos < kRoiMaxList) s_list[pos] = r;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) { int t = s_n; for (int k = 0; k < 8; ++k) t += s_wcount[k]; s_n = t; }
-        __syncthreads();
-    }
-    const int nlist = min(s_n, kRoiMaxList);
-    if (x >= W) return;
-    float acc = 0.f;
-    for (int li = 0; li < nlist; ++li) {
-        const int r = s_list[li];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * H * W) return;
+    const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((int64_t)W * H));
+    float* gp = gfeat + (int64_t)b * C * H * W + (int64_t)y * W + x;
+    const int64_t cstride = (int64_t)H * W;
+    const int PP = P * P;
+    RoiEntry ent[kRoiEntries];
+    int n = 0;
+    bool first = true;
+    for (int r = 0; r < R; ++r) {
         const float* roi = rois + r * 5;
-        float rr[5] = {__ldg(roi), __ldg(roi + 1), __ldg(roi + 2), __ldg(roi + 3), __ldg(roi + 4)};
-        RoiGeom g = roi_geom(rr, scale, P);
+        if ((int)__ldg(roi) != b) continue;
+        const float sw = __ldg(roi + 1) * scale, sh = __ldg(roi + 2) * scale;
+        const float ew = __ldg(roi + 3) * scale, eh = __ldg(roi + 4) * scale;
+        const float rw = fmaxf(ew - sw, 1.f), rh = fmaxf(eh - sh, 1.f);
+        if ((float)y < sh - 2.f || (float)y > sh + rh + 1.f || (float)x < sw - 2.f || (float)x > sw + rw + 1.f) continue;
+        float rr[5] = {(float)b, __ldg(roi + 1), __ldg(roi + 2), __ldg(roi + 3), __ldg(roi + 4)};
+        const RoiGeom g = roi_geom(rr, scale, P);
         const float sy = g.bin_h / (float)g.grid_h, sx = g.bin_w / (float)g.grid_w;
         const int ny = P * g.grid_h, nx = P * g.grid_w;
         const int jy0 = max(0, (int)floorf(((float)y - 1.f - g.start_h) / sy - 0.5f) - 1);
         const int jy1 = min(ny - 1, (int)ceilf(((float)y + 1.f - g.start_h) / sy - 0.5f) + 1);
-        if (jy0 > jy1) continue;
         const int jx0 = max(0, (int)floorf(((float)x - 1.f - g.start_w) / sx - 0.5f) - 1);
         const int jx1 = min(nx - 1, (int)ceilf(((float)x + 1.f - g.start_w) / sx - 0.5f) + 1);
-        if (jx0 > jx1) continue;
+        if (jy0 > jy1 || jx0 > jx1) continue;
         const float inv = 1.f / (float)(g.grid_h * g.grid_w);
-        const float* go = gout + ((int64_t)r * C + c) * P * P;
         for (int jy = jy0; jy <= jy1; ++jy) {
             const int ph = jy / g.grid_h, iy = jy % g.grid_h;
             const float py = g.start_h + ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.grid_h;
@@ -142,11 +128,14 @@ roi_align_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ r
                 if (!axis_interp(px, W, xl, xh, wxl, wxh)) continue;
                 if (xl != x && xh != x) continue;
                 const float wx = (xl == x ? wxl : 0.f) + (xh == x ? wxh : 0.f);
-                acc += wy * wx * __ldg(go + ph * P + pw) * inv;
+                if (n == kRoiEntries) { roi_flush(ent, n, gout, gp, C, PP, cstride, first); first = false; n = 0; }
+                ent[n].off = r * C * PP + ph * P + pw;
+                ent[n].w = wy * wx * inv;
+                ++n;
             }
         }
     }
-    gfeat[(((int64_t)b * C + c) * H + y) * W + x] = acc;
+    if (n > 0 || first) roi_flush(ent, n, gout, gp, C, PP, cstride, first);
 }
 
 }  // namespace b2
@@ -168,8 +157,9 @@ extern "C" int b2_roi_align_bwd(const float* gout, const float* rois, float* gfe
                                 int W, int P, float scale, void* stream) {
     B2_REQUIRE(gfeat && (R == 0 || (gout && rois)), "roi_align_bwd: null pointer");
     B2_REQUIRE(P >= 1 && C >= 1 && H >= 1 && W >= 1, "roi_align_bwd: bad dims");
-    B2_REQUIRE((int64_t)C * H <= 65535, "roi_align_bwd: C*H = %lld exceeds the grid limit 65535", (long long)C * H);
-    dim3 grid((W + 255) / 256, C * H);     // batch of 1 (the attack scripts run batch size 1)
-    roi_align_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gout, rois, gfeat, R, 1, C, H, W, P, scale);
+    B2_REQUIRE((int64_t)R * C * P * P < ((int64_t)1 << 31), "roi_align_bwd: gout has more than 2^31 elements");
+    const int64_t npix = (int64_t)H * W;     // batch of 1 (the attack scripts run batch size 1)
+    roi_align_bwd_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, (cudaStream_t)stream>>>(gout, rois, gfeat, R, 1, C, H, W,
+                                                                                          P, scale);
     return check_launch("roi_align_bwd");
 }

@@ -115,6 +115,39 @@ def run_patch(args):
     return patch
 
 
+def run_srcnn(args):
+    """BASELINE config 5: PGD in 0-255 space against the Stereo-R-CNN-shaped stand-in (RoIAlign fwd/bwd
+    path), attack/Stereo-RCNN/pgd_attack.py:151-217; flags :42-48 (--iter, --alpha 1.0, --eps 0.3)."""
+    import time
+    from . import stereo_rcnn as S
+    rank, world = parallel.init()
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    h, w, nroi = (96, 320, 24) if args.tiny else (600, 1987, 256)
+    model = S.SyntheticStereoRCNN(width=64 if args.tiny else 256, seed=args.seed).to(dev)
+    eps255 = 255 * args.eps                                               # pgd_attack.py:57
+    done, t0 = 0, None
+    for i in parallel.shard_pairs(args.pairs, rank, world):
+        il, ir = S.synthetic_pair(i, h, w)
+        rl, rr = S.synthetic_rois(nroi, h, w, seed=i)
+        tg = {k: v.to(dev) for k, v in S.synthetic_targets(nroi, seed=i).items()}
+        if t0 is None:                                                    # first pair = warm-up
+            S.pgd_attack(model, il.to(dev), ir.to(dev), rl.to(dev), rr.to(dev), tg, 1, args.alpha, eps255)
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+        al, ar, losses = S.pgd_attack(model, il.to(dev), ir.to(dev), rl.to(dev), rr.to(dev), tg, args.iter,
+                                      args.alpha, eps255)
+        done += args.iter
+    torch.cuda.synchronize()
+    rate = torch.tensor([done / (time.perf_counter() - t0)], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(rate)
+    if rank == 0:
+        print("stereo-rcnn PGD: %.2f pair-iterations/s on %d GPU(s); last loss %.4f -> %.4f; |delta|max %.3f"
+              % (rate.item(), world, losses[0].item(), losses[-1].item(), (al - il.to(dev)).abs().max().item()))
+    return rate.item()
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     sub = ap.add_subparsers(dest="cmd", required=True)
@@ -128,14 +161,18 @@ def main(argv=None):
     b.add_argument("--eps", type=float, default=8 / 255)                 # :54
     b.add_argument("--epochs", type=int, default=80)                     # :55
     b.add_argument("--ratio", type=float, default=0.2)                   # :56
-    for q in (a, b):
+    c = sub.add_parser("srcnn")
+    c.add_argument("--iter", type=int, default=10)                       # Stereo-RCNN/pgd_attack.py:42-48
+    c.add_argument("--alpha", type=float, default=1.0)
+    c.add_argument("--eps", type=float, default=0.03)
+    for q in (a, b, c):
         q.add_argument("--pairs", type=int, default=8)
         q.add_argument("--seed", type=int, default=1)                    # :41
         q.add_argument("--save-dir", default=None)
         q.add_argument("--tiny", action="store_true", help="32x64 frames, shrunk volumes (tests)")
         q.add_argument("--eager", action="store_true")
     args = ap.parse_args(argv)
-    out = run_pgd(args) if args.cmd == "pgd" else run_patch(args)
+    out = {"pgd": run_pgd, "patch": run_patch, "srcnn": run_srcnn}[args.cmd](args)
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         torch.distributed.destroy_process_group()
     return out

@@ -226,3 +226,44 @@ def test_runner_patch(built_lib, tmp_path):
                          "--save-dir", str(tmp_path)])
     assert patch.shape == (1, 3, 7, 7) and 0 < patch.abs().max() <= 2 * 2 * (8 / 255) + 1e-6   # pairs*iters clipped steps
     assert (tmp_path / "epoch1" / "patch.npy").exists()
+
+
+def test_stereo_rcnn_pgd_loop_vs_oracle(built_lib):
+    """Config 5 data flow on a small frame: FPN -> PyramidRoI_Feat (our RoIAlign fwd+bwd, 7x7 L/R and
+    14x14 keypoint branch) -> uncertainty-weighted loss -> 0-255-space PGD step, against the same
+    stock-torch network with torchvision's RoIAlign and the oracle's step on the CPU."""
+    from eval_driving_safety_b200 import stereo_rcnn as S
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    h, w, R = 96, 320, 24
+    il, ir = S.synthetic_pair(0, h, w)
+    rl, rr = S.synthetic_rois(R, h, w, seed=3)
+    tg = S.synthetic_targets(R, seed=3)
+    ref = S.SyntheticStereoRCNN(roi_feat_fn=A.pyramid_roi_feat, width=64)
+    gpu = S.SyntheticStereoRCNN(width=64).cuda()
+    gpu.load_state_dict(ref.state_dict())
+    # one iteration: loss and input gradient
+    xl, xr = il.clone().requires_grad_(True), ir.clone().requires_grad_(True)
+    loss_r = ref(xl, xr, rl, rr, tg)
+    gl_r, gr_r = torch.autograd.grad(loss_r, [xl, xr])
+    xlc, xrc = il.cuda().requires_grad_(True), ir.cuda().requires_grad_(True)
+    tgc = {k: v.cuda() for k, v in tg.items()}
+    loss_g = gpu(xlc, xrc, rl.cuda(), rr.cuda(), tgc)
+    gl_g, gr_g = torch.autograd.grad(loss_g, [xlc, xrc])
+    assert abs(loss_g.item() - loss_r.item()) < 1e-4 * abs(loss_r.item())
+    assert rel_err(gl_g.cpu(), gl_r) < 1e-3 and rel_err(gr_g.cpu(), gr_r) < 1e-3
+    # (bitwise determinism of our RoIAlign backward itself is asserted in test_gpu_volume.py; the stock
+    # bilinear-upsample / max-pool backwards of this stand-in network use atomics)
+    # 3-iteration loop: perturbation bounded, inside the per-channel range, mostly identical to the oracle loop
+    eps255, alpha = 255 * 0.03, 1.0
+    al, ar, losses = S.pgd_attack(gpu, il.cuda(), ir.cuda(), rl.cuda(), rr.cuda(), tgc, 3, alpha, eps255)
+    x_ref, clean = il.clone(), il.clone()
+    xr_ref = ir.clone()
+    for _ in range(3):
+        a, b = x_ref.clone().requires_grad_(True), xr_ref.clone().requires_grad_(True)
+        g1, g2 = torch.autograd.grad(ref(a, b, rl, rr, tg), [a, b])
+        x_ref = A.stereo_rcnn_pgd_step(a.detach(), g1, clean, alpha, eps255)
+        xr_ref = A.stereo_rcnn_pgd_step(b.detach(), g2, ir, alpha, eps255)
+    assert (al.cpu() - il).abs().max() <= eps255 + 1e-4
+    same = ((al.cpu() - x_ref).abs() < 1e-4).float().mean().item()
+    assert same > 0.97, same
