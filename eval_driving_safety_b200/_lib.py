@@ -27,7 +27,8 @@ SIGNATURES = {
     "b2_patch_update": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_f32, c_f32, _FP, _FP, c_vp, c_vp]),
     "b2_cost_volume_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
-    "b2_cost_volume_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
+    "b2_cost_volume_bwd_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
+    "b2_cost_volume_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "b2_grid_sample3d_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_i64,
                                      c_int, c_int, c_int, c_vp]),
     "b2_grid_sample2d_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_i64,

@@ -165,9 +165,12 @@ class BuildCostVolumeFn(Function):
             g = gcost.contiguous()
             gl = torch.empty((n, c, h, w), device=g.device, dtype=torch.float32)
             gr = torch.empty_like(gl)
-        with _op("cost_volume_bwd", 1, 4 * (2 * n * c * h * w + g.numel())):
+        ws = None
+        if channels_last:
+            ws = torch.empty(lib.b2_cost_volume_bwd_workspace_bytes(n, c, h, w), device=g.device, dtype=torch.uint8)
+        with _op("cost_volume_bwd", 2 if channels_last else 1, 4 * (2 * n * c * h * w + g.numel())):
             check(lib.b2_cost_volume_bwd(_p(g), _p(shifts), _p(gl), _p(gr), n, c, d, h, w,
-                                         1 if channels_last else 0, _stream()), "cost_volume_bwd")
+                                         1 if channels_last else 0, _p(ws), _stream()), "cost_volume_bwd")
         return gl, gr, None, None
 
 

@@ -96,8 +96,11 @@ int b2_patch_update(float* patch, const float* gL, const float* gR, int C, int H
  * ------------------------------------------------------------------------- */
 int b2_cost_volume_fwd(const float* left, const float* right, const float* shifts, float* cost,
                        int N, int C, int D, int H, int W, int layout, void* stream);
+int64_t b2_cost_volume_bwd_workspace_bytes(int N, int C, int H, int W);
 int b2_cost_volume_bwd(const float* gcost, const float* shifts, float* gleft, float* gright,
-                       int N, int C, int D, int H, int W, int layout, void* stream);
+                       int N, int C, int D, int H, int W, int layout, void* workspace, void* stream);
+/* workspace (channels-last layout only; may be NULL = slower plane-strided kernel): per-segment partial
+ * sums of the row-staged backward, combined in a fixed order. */
 
 /* ------------------------------------------------------------------------- *
  * (2) grid_sample lifting (frustum -> voxel), bilinear/trilinear, zeros padding
