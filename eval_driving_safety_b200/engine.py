@@ -95,6 +95,13 @@ class PgdIterationGraph:
             loss = self._iteration(xL, xR, cL, cR, disp)
             self.launches_per_step = ops.LAUNCH_COUNT - n0
             return loss
+        if self.lanes > 1:
+            # a lone pair (odd remainder): replaying the multi-lane graph would recompute idle lanes,
+            # so a single-lane graph is captured on first use
+            if getattr(self, "_single", None) is None:
+                self._single = PgdIterationGraph(self.model, self.cfg, self.labels, self.calib, self.alpha,
+                                                 self.eps, (xL, xR, cL, cR, disp), norm=self.norm, lanes=1)
+            return self._single.step(xL, xR, cL, cR, disp)
         for dst, src in zip(self.s, (xL, xR, cL, cR, disp)):
             dst.copy_(src, non_blocking=True)
         self.graph.replay()
