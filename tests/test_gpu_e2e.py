@@ -267,3 +267,34 @@ def test_stereo_rcnn_pgd_loop_vs_oracle(built_lib):
     assert (al.cpu() - il).abs().max() <= eps255 + 1e-4
     same = ((al.cpu() - x_ref).abs() < 1e-4).float().mean().item()
     assert same > 0.97, same
+
+
+def test_engine_two_lanes_and_odd_remainder(setup):
+    """Two pair-iterations captured side by side in one CUDA graph give the same pixels as one at a
+    time (and a lone remaining pair goes through a lazily captured single-lane graph)."""
+    from eval_driving_safety_b200 import engine, ops
+    s = setup
+    ops.set_conv_impl(1)
+    dev = torch.device("cuda")
+    mean = torch.tensor(A.IMAGENET_MEAN, device=dev).view(1, 3, 1, 1)
+    std = torch.tensor(A.IMAGENET_STD, device=dev).view(1, 3, 1, 1)
+    labels = {k: v.cuda() for k, v in s["labels"].items()}
+    g = torch.Generator().manual_seed(77)
+    pairs = []
+    for _ in range(3):
+        xL = (s["pair"]["imgL"] + 0.05 * torch.randn(s["pair"]["imgL"].shape, generator=g)).cuda()
+        xR = (s["pair"]["imgR"] + 0.05 * torch.randn(s["pair"]["imgR"].shape, generator=g)).cuda()
+        pairs.append([xL, xR, xL * std + mean, xR * std + mean, s["pair"]["disp_L"].cuda()])
+    ex = tuple(pairs[0])
+    e1 = engine.PgdIterationGraph(s["model"], s["cfg_p"], labels, s["calib"], 0.0075, 0.03, ex, lanes=1)
+    e2 = engine.PgdIterationGraph(s["model"], s["cfg_p"], labels, s["calib"], 0.0075, 0.03, ex, lanes=2)
+    a = [[t.clone() for t in p] for p in pairs]
+    b = [[t.clone() for t in p] for p in pairs]
+    for p in a:
+        e1.step(*p)
+    e2.step_multi([tuple(b[0]), tuple(b[1])])
+    e2.step(*b[2])                                        # odd remainder
+    torch.cuda.synchronize()
+    for pa, pb in zip(a, b):
+        assert torch.equal(pa[0], pb[0]) and torch.equal(pa[1], pb[1])
+    ops.set_conv_impl(0)
