@@ -122,6 +122,10 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     rank, world = parallel.init(device=dev)
     torch.backends.cudnn.benchmark = True
+    # stock 2-D convolutions of the extractor / BEV head (cuDNN): TF32 like our 3-D tensor-core convs
+    # unless --backbone-fp32 (fp32 CUDA-core cuDNN kernels: tighter parity, slower)
+    torch.backends.cudnn.allow_tf32 = not args.backbone_fp32
+    torch.backends.cuda.matmul.allow_tf32 = not args.backbone_fp32
     cfg = dsgn.default_cfg()
     model = dsgn.build_model(cfg, seed=1, device=dev)
     calib = synthetic.make_calib(1)
@@ -241,6 +245,7 @@ def run_b200(args):
                                "8 synthetic 384x1248 stereo pairs per GPU, random-init weights (seed 1)",
                    "pairs_per_gpu": PAIRS_PER_GPU, "image": [H, W], "psv": [64, 48, 96, 312],
                    "voxels": [96, 192, 20, 304], "parallelism": "dp%d (pairs sharded, no data-path collective)" % world,
+                   "backbone_2d": "cuDNN fp32" if args.backbone_fp32 else "cuDNN TF32 (PyTorch default)",
                    "execution": "eager" if args.eager else
                    "CUDA graph of %d concurrent pair-iteration(s) on parallel streams, replayed" % lanes,
                    "l2_policy": "per-iteration working set (~10 GB of activations per pair) is far larger than the 126 MB L2"},
@@ -356,6 +361,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graph (debug)")
+    ap.add_argument("--backbone-fp32", action="store_true", help="cuDNN 2-D convs in fp32 instead of TF32")
     ap.add_argument("--lanes", type=int, default=2, help="pair-iterations captured side by side in one graph")
     args = ap.parse_args()
     if args.impl == "reference":
