@@ -245,7 +245,9 @@ def run_b200(args):
                                "8 synthetic 384x1248 stereo pairs per GPU, random-init weights (seed 1)",
                    "pairs_per_gpu": PAIRS_PER_GPU, "image": [H, W], "psv": [64, 48, 96, 312],
                    "voxels": [96, 192, 20, 304], "parallelism": "dp%d (pairs sharded, no data-path collective)" % world,
-                   "backbone_2d": "cuDNN fp32" if args.backbone_fp32 else "cuDNN TF32 (PyTorch default)",
+                   "backbone_2d": "cuDNN fp32" if args.backbone_fp32 else
+                   ("cuDNN TF32 x3 (error-compensated split)" if dsgn.BACKBONE_PRECISION == "tf32x3"
+                    else "cuDNN TF32 (PyTorch default)"),
                    "execution": "eager" if args.eager else
                    "CUDA graph of %d concurrent pair-iteration(s) on parallel streams, replayed" % lanes,
                    "l2_policy": "per-iteration working set (~10 GB of activations per pair) is far larger than the 126 MB L2"},

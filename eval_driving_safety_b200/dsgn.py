@@ -11,6 +11,7 @@ What runs where:
   * 2-D feature extractor, depth soft-argmin head and BEV 2-D head: stock torch
     CUDA ops (outside the four subsystems of the north star; 8f "next" rows).
 """
+import os
 from types import SimpleNamespace
 
 import torch
@@ -66,11 +67,75 @@ def run_convbn_3d(seq, x, relu=False, res=None):
     return ops.groupnorm_act(y, norm.weight, norm.bias, norm.num_groups, norm.eps, relu=relu, res=res)
 
 
+# Stock 2-D convolutions (cuDNN).  'tf32' = PyTorch's default on this hardware; 'tf32x3' = the same
+# TF32 tensor-core kernels run on an error-compensated split (x = x_hi + x_lo, w = w_hi + w_lo,
+# y ~ x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, every factor exactly representable in TF32) -> fp32-class
+# accuracy at 3x the (small) 2-D conv cost.  cuDNN's true-fp32 channels-last kernels are ~10x slower.
+BACKBONE_PRECISION = os.environ.get("B2_BACKBONE", "tf32")
+
+
+def set_backbone_precision(mode):
+    global BACKBONE_PRECISION
+    assert mode in ("tf32", "tf32x3")
+    BACKBONE_PRECISION = mode
+
+
+def _tf32_split(t):
+    hi = (t.view(torch.int32) & ~0x1FFF).view(torch.float32)      # exactly TF32-representable
+    return hi, t - hi                                              # lo has <= 13 significant bits
+
+
+_W3_CACHE = {}
+
+
+def _w3(w, dim):
+    """[w_hi, w_lo, w_hi] stacked along ``dim`` (1: input channels for the forward, 0: output channels
+    for the data gradient); cached per frozen weight."""
+    key = (id(w), dim)
+    hit = _W3_CACHE.get(key)
+    if hit is not None and hit[0] is w and hit[1] == w._version:
+        return hit[2]
+    wh, wl = _tf32_split(w.detach())
+    w3 = torch.cat([wh, wl, wh], dim).contiguous(memory_format=torch.channels_last)
+    _W3_CACHE[key] = (w, w._version, w3)
+    return w3
+
+
+class Conv2dTf32x3Fn(torch.autograd.Function):
+    """conv2d(x, w) with frozen w: three TF32 convolutions fused into one call by stacking the split
+    operands along the input channels; the data gradient is the same trick on the output gradient."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, stride, padding, dilation):
+        xh, xl = _tf32_split(x)
+        x3 = torch.cat([xh, xh, xl], 1).contiguous(memory_format=torch.channels_last)
+        y = F.conv2d(x3, _w3(w, 1), bias, stride, padding, dilation)
+        ctx.save_for_backward(w)
+        ctx.cfg = (tuple(x.shape), stride, padding, dilation)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, g):
+        (w,) = ctx.saved_tensors
+        shape, stride, padding, dilation = ctx.cfg
+        gh, gl = _tf32_split(g)
+        g3 = torch.cat([gh, gh, gl], 1).contiguous(memory_format=torch.channels_last)
+        gx = torch.nn.grad.conv2d_input(shape, _w3(w, 0), g3, stride, padding, dilation)   # stacked along Cout
+        return gx, None, None, None, None, None
+
+
+def conv2d_stock(conv, x):
+    if BACKBONE_PRECISION == "tf32x3" and x.is_cuda and conv.in_channels >= 16:
+        return Conv2dTf32x3Fn.apply(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation)
+    return conv(x)
+
+
 def run_convbn_2d(seq, x, relu=False, res=None):
     """cuDNN conv2d (channels-last) -> our GroupNorm (+res) (+ReLU) kernel.
     ``seq`` = Sequential(Conv2d, GroupNorm)."""
     conv, norm = seq[0], seq[1]
-    y = conv(x)
+    y = conv2d_stock(conv, x)
     return ops.groupnorm_act(y, norm.weight, norm.bias, norm.num_groups, norm.eps, relu=relu, res=res)
 
 
@@ -175,9 +240,9 @@ class FeatureExtraction(nn.Module):
                 y = run_convbn_2d(br[1], br[0](skip), relu=True)
                 cat.append(upsample_bilinear_matmul(y, size))
         cat = torch.cat(cat, 1).contiguous(memory_format=torch.channels_last)
-        f = self.lastconv[2](run_convbn_2d(self.lastconv[0], cat, relu=True))
+        f = conv2d_stock(self.lastconv[2], run_convbn_2d(self.lastconv[0], cat, relu=True))
         n_rpn = cat.shape[0] if rpn_samples is None else rpn_samples
-        r = self.rpnconv[2](run_convbn_2d(self.rpnconv[0], cat[:n_rpn], relu=True))
+        r = conv2d_stock(self.rpnconv[2], run_convbn_2d(self.rpnconv[0], cat[:n_rpn], relu=True))
         return f, r
 
 
@@ -336,7 +401,7 @@ class StereoNet(nn.Module):
         bev = ops.bev_pool(v, cfg.y_pool)          # AvgPool3d over Y + (C, Y/p) -> channels, one pass
         bev = run_convbn_2d(self.bev_conv[0], bev, relu=True)
         bev = run_convbn_2d(self.bev_conv[2], bev, relu=True)
-        return self.bbox_cls(bev), self.bbox_reg(bev), self.bbox_centerness(bev)
+        return conv2d_stock(self.bbox_cls, bev), conv2d_stock(self.bbox_reg, bev), conv2d_stock(self.bbox_centerness, bev)
 
     def forward(self, imgL, imgR, calibs_fu, calibs_baseline, calibs_Proj, calibs_Proj_R=None):
         if not imgL.is_cuda:
