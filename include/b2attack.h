@@ -17,7 +17,9 @@
  *     cudaStream_t passed as `void* stream` (graph-capturable).
  *   - return 0 on success, non-zero (cudaError_t or B2_ERR_*) otherwise; the text
  *     of the last error on the calling thread is b2_last_error().  Never throws.
- *   - re-entrant; no global state except cached TMA descriptors (conv3d).
+ *   - no global state except one-time per-process cudaFuncSetAttribute flags (dynamic smem
+ *     opt-in); one process drives one GPU (the torchrun model), calls on one stream are
+ *     ordered by that stream.
  */
 #ifndef B2ATTACK_H
 #define B2ATTACK_H
