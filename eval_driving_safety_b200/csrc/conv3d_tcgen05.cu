@@ -829,6 +829,303 @@ static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* 
     return check_launch("conv3d(tcgen05,s1)");
 }
 
+// =============================================================================================
+// Transposed-conv (DECONV gather) fast path: "class-stacked" kernel.
+// The generic kernel treats the 8 output-parity classes as 8 independent tiles and reloads the A
+// box and a weight tile per tap: 96 KB of L2->SM traffic per 2 MFLOP (21 FLOP/B) -> L2-bound at
+// ~230 TFLOP/s on the 128->64 layers that write the full-resolution volumes.  But all classes of
+// one input block read the SAME input neighbourhood: per axis, input offset 0 serves parity 0
+// (tap k=1) and parity 1 (k=2), offset +1 serves parity 1 (k=0).
+// Work unit = (input block 16 rows x 8 w, input plane d, output-plane parity pd): its 4
+// (row, w)-parity classes c = 2*ph + pw own 4 adjacent TMEM accumulators of Nt columns (double
+// buffered = all 512 columns for Nt = 64).  Per (K chunk, plane tap (kd, sd), w shift sw) ONE
+// {32 ch, 8 w, 17 rows} halo box is loaded; the row shift sh = 1 is the same smem tile at
+// +8 rows (+1024 B, a whole swizzle atom).  Weight tiles of classes that share an input shift
+// and sit in adjacent accumulators are stored back to back and fed by ONE MMA:
+//   sw = 0:  sh = 0 -> classes 0..3 (kh = ph?2:1, kw = pw?2:1)  N = 4 Nt at column 0
+//            sh = 1 -> classes 2,3  (kh = 0,      kw = pw?2:1)  N = 2 Nt at column 2 Nt
+//   sw = 1:  sh = 0 -> class 1 (kh = 1, kw = 0), class 3 (kh = 2, kw = 0)      2 x N = Nt
+//            sh = 1 -> class 3 (kh = 0, kw = 0)                                N = Nt
+// = the 9 (kh, kw) taps of one plane tap.  L2->SM: 2 (or 4) A boxes of 17 KB per K chunk instead
+// of 9 (or 18) of 16 KB; smem operand reads per K step drop from 54 KB to 38 KB.
+// =============================================================================================
+constexpr int kDcARows = (kTileH + 1) * kTileW;        // 136 rows
+constexpr int kDcABytes = kDcARows * 128;              // 17408 B = 17 swizzle atoms
+constexpr int kDcMaxStages = 6;
+
+struct DcParams {
+    int N, Cin, Cout;
+    int Pt, Rt, Wt;            // INPUT extents in role order (planes, rows, w)
+    int Do, Ho, Wo;            // output dims
+    int swap;                  // rows along D, planes along H
+    int nt, n_tiles;
+    int tiles_w, tiles_h;
+    int kchunks;
+    int stages, stage_bytes, b_bytes;
+    int tmem_cols;
+    long long total_units;
+};
+
+struct DcUnit { int nti, n, d, pd, h0, w0; };
+
+__device__ __forceinline__ DcUnit dc_decode(const DcParams& p, long long t) {
+    DcUnit u;
+    u.w0 = (int)(t % p.tiles_w) * kTileW; t /= p.tiles_w;
+    u.h0 = (int)(t % p.tiles_h) * kTileH; t /= p.tiles_h;
+    u.pd = (int)(t & 1); t >>= 1;
+    u.d = (int)(t % p.Pt); t /= p.Pt;
+    u.n = (int)(t % p.N); t /= p.N;
+    u.nti = (int)t;
+    return u;
+}
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         float* __restrict__ out, const DcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kDcMaxStages + 4];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kDcMaxStages + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kDcMaxStages + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kDcMaxStages + 2 + a); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long t = blockIdx.x; t < p.total_units; t += gridDim.x) {
+                const DcUnit u = dc_decode(p, t);
+                const int nptap = 1 + u.pd;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    for (int jt = 0; jt < nptap; ++jt) {
+                        int kd, sd;
+                        deconv_axis(u.pd, jt, kd, sd);
+                        for (int sw = 0; sw < 2; ++sw) {
+                            const int nb = sw == 0 ? 6 : 3;
+                            mbar_wait(empty_bar(stage), phase ^ 1);
+                            mbar_expect_tx(full_bar(stage), (uint32_t)(kDcABytes + nb * p.b_bytes));
+                            const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                            tma_load_5d(sa, &map_a, full_bar(stage), kc * kKChunk, u.w0 + sw, u.h0, u.d + sd, u.n);
+                            for (int b = 0; b < nb; ++b) {
+                                int kh, kw;
+                                if (sw == 0) {
+                                    if (b < 4) { kh = (b >> 1) ? 2 : 1; kw = (b & 1) ? 2 : 1; }
+                                    else       { kh = 0;                kw = (b & 1) ? 2 : 1; }   // b = 4, 5 -> classes 2, 3
+                                } else {
+                                    kw = 0; kh = b == 0 ? 1 : (b == 1 ? 2 : 0);
+                                }
+                                const int tap = p.swap ? (kh * 3 + kd) * 3 + kw : (kd * 3 + kh) * 3 + kw;
+                                tma_load_2d(sa + kDcABytes + (uint32_t)(b * p.b_bytes), &map_b, full_bar(stage),
+                                            kc * kKChunk, tap * p.Cout + u.nti * p.nt);
+                            }
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc1 = umma_idesc_tf32(128, p.nt), idesc2 = umma_idesc_tf32(128, 2 * p.nt),
+                           idesc4 = umma_idesc_tf32(128, 4 * p.nt);
+            int stage = 0; uint32_t phase = 0;
+            long long it = 0;
+            for (long long t = blockIdx.x; t < p.total_units; t += gridDim.x, ++it) {
+                const int acc = (int)(it & 1);
+                mbar_wait(tempty_bar(acc), (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 4 * p.nt);
+                const DcUnit u = dc_decode(p, t);
+                const int nst = p.kchunks * (1 + u.pd);
+                for (int s = 0; s < nst; ++s) {
+                    // ---- sw = 0 stage: classes 0..3 (sh = 0) and 2,3 (sh = 1)
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    {
+                        const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                        const uint64_t a0 = umma_desc_sw128(sa), a1 = umma_desc_sw128(sa + 1024);
+                        const uint64_t b0 = umma_desc_sw128(sa + kDcABytes),
+                                       b4 = umma_desc_sw128(sa + kDcABytes + 4u * p.b_bytes);
+#pragma unroll
+                        for (int k = 0; k < kKChunk / 8; ++k)
+                            umma_tf32(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc4, (s | k) != 0);
+#pragma unroll
+                        for (int k = 0; k < kKChunk / 8; ++k)
+                            umma_tf32(tmem_d + 2 * p.nt, a1 + 2 * k, b4 + 2 * k, idesc2, 1u);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    // ---- sw = 1 stage: class 1 and class 3 (sh = 0), class 3 (sh = 1)
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    {
+                        const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                        const uint64_t a0 = umma_desc_sw128(sa), a1 = umma_desc_sw128(sa + 1024);
+                        const uint64_t b0 = umma_desc_sw128(sa + kDcABytes),
+                                       b1 = umma_desc_sw128(sa + kDcABytes + (uint32_t)p.b_bytes),
+                                       b2 = umma_desc_sw128(sa + kDcABytes + 2u * p.b_bytes);
+#pragma unroll
+                        for (int k = 0; k < kKChunk / 8; ++k)
+                            umma_tf32(tmem_d + p.nt, a0 + 2 * k, b0 + 2 * k, idesc1, 1u);
+#pragma unroll
+                        for (int k = 0; k < kKChunk / 8; ++k)
+                            umma_tf32(tmem_d + 3 * p.nt, a0 + 2 * k, b1 + 2 * k, idesc1, 1u);
+#pragma unroll
+                        for (int k = 0; k < kKChunk / 8; ++k)
+                            umma_tf32(tmem_d + 3 * p.nt, a1 + 2 * k, b2 + 2 * k, idesc1, 1u);
+                    }
+                    umma_commit(empty_bar(stage));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue =====================
+        const int lane_grp = warp & 3;
+        const int m = lane_grp * 32 + lane;
+        const int hl = m / kTileW, wl = m % kTileW;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        long long it = 0;
+        for (long long t = blockIdx.x; t < p.total_units; t += gridDim.x, ++it) {
+            const int acc = (int)(it & 1);
+            const DcUnit u = dc_decode(p, t);
+            const int h = u.h0 + hl, w = u.w0 + wl;
+            const bool ok = h < p.Rt && w < p.Wt;
+            const int op = 2 * u.d + u.pd;
+            mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            for (int c = 0; c < 4; ++c) {
+                const int orow = 2 * h + (c >> 1), ow = 2 * w + (c & 1);
+                const int od = p.swap ? orow : op, oh = p.swap ? op : orow;
+                float* optr = out + ((((long long)u.n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.Cout + u.nti * p.nt;
+                const uint32_t taddr = lane_addr + (uint32_t)((acc * 4 + c) * p.nt);
+                int c0 = 0;
+                for (; c0 + 32 <= p.nt; c0 += 32) {
+                    uint32_t rr[32];
+                    tmem_ld32(taddr + c0, rr);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            *reinterpret_cast<float4*>(optr + c0 + 4 * q) =
+                                make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
+                                            __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
+                    }
+                }
+                if (c0 < p.nt) {
+                    uint32_t rr[16];
+                    tmem_ld16(taddr + c0, rr);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            *reinterpret_cast<float4*>(optr + c0 + 4 * q) =
+                                make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
+                                            __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
+static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* wp, float* out, int N, int Cin,
+                            int Cout, int Di, int Hi, int Wi, cudaStream_t st) {
+    DcParams p{};
+    p.N = N; p.Cin = Cin; p.Cout = Cout;
+    p.Do = 2 * Di; p.Ho = 2 * Hi; p.Wo = 2 * Wi;
+    p.nt = Cout <= 64 ? Cout : Cout / 2;
+    p.n_tiles = Cout / p.nt;
+    {
+        const long long cost_h = (long long)((Hi + kTileH - 1) / kTileH) * kTileH * Di;
+        const long long cost_d = (long long)((Di + kTileH - 1) / kTileH) * kTileH * Hi;
+        p.swap = cost_d < cost_h ? 1 : 0;
+        p.Rt = p.swap ? Di : Hi;
+        p.Pt = p.swap ? Hi : Di;
+        p.Wt = Wi;
+    }
+    p.tiles_w = (p.Wt + kTileW - 1) / kTileW;
+    p.tiles_h = (p.Rt + kTileH - 1) / kTileH;
+    p.kchunks = Cin / kKChunk;
+    p.b_bytes = p.nt * 128;
+    p.stage_bytes = kDcABytes + 6 * p.b_bytes;
+    p.stages = (212 * 1024) / p.stage_bytes;
+    if (p.stages > kDcMaxStages) p.stages = kDcMaxStages;
+    p.tmem_cols = 32;
+    while (p.tmem_cols < 8 * p.nt) p.tmem_cols *= 2;
+    p.total_units = (long long)p.n_tiles * N * p.Pt * 2 * p.tiles_h * p.tiles_w;
+
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t gdim[5] = {(cuuint64_t)Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)Di, (cuuint64_t)N};
+        cuuint64_t gstr[4] = {(cuuint64_t)Cin * 4, (cuuint64_t)Wi * Cin * 4, (cuuint64_t)Hi * Wi * Cin * 4,
+                              (cuuint64_t)Di * Hi * Wi * Cin * 4};
+        if (p.swap) {
+            gdim[2] = (cuuint64_t)Di; gdim[3] = (cuuint64_t)Hi;
+            gstr[1] = (cuuint64_t)Hi * Wi * Cin * 4; gstr[2] = (cuuint64_t)Wi * Cin * 4;
+        }
+        cuuint32_t box[5] = {(cuuint32_t)kKChunk, (cuuint32_t)kTileW, (cuuint32_t)kTileH + 1, 1, 1};
+        cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+        CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in, gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3d(tcgen05,deconv): cuTensorMapEncodeTiled(A) failed: %d", (int)r); return B2_ERR_DRIVER; }
+    }
+    {
+        cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * Cout};
+        cuuint64_t gstr[1] = {(cuuint64_t)Cin * 4};
+        cuuint32_t box[2] = {(cuuint32_t)kKChunk, (cuuint32_t)p.nt};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wp, gdim, gstr, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_error("conv3d(tcgen05,deconv): cuTensorMapEncodeTiled(B) failed: %d", (int)r); return B2_ERR_DRIVER; }
+    }
+    const int smem = p.stages * p.stage_bytes + 1024;
+    static int attr_smem = 0;
+    if (smem > attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(conv3d_dc_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) { set_error("conv3d(tcgen05,deconv): cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return (int)e; }
+        attr_smem = smem;
+    }
+    int grid = (int)(p.total_units < kNumSMs ? p.total_units : kNumSMs);
+    conv3d_dc_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p);
+    return check_launch("conv3d(tcgen05,deconv)");
+}
+
 int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
                           int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st) {
     if (Cin % 32 != 0 || Cout % 32 != 0 || Cout > 256 || Cout < 32) {
@@ -846,6 +1143,11 @@ int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, i
         const int nt = Cout <= 64 ? Cout : Cout / 2;
         if (mode == 0 && stride == 1 && !simple && nt % 16 == 0)
             return conv3d_s1_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st);
+        // transposed convs take the class-stacked kernel; B2_CONV_DC_SIMPLE=1 forces the generic one
+        static int dc_simple = -1;
+        if (dc_simple < 0) { const char* e = getenv("B2_CONV_DC_SIMPLE"); dc_simple = (e && e[0] == '1') ? 1 : 0; }
+        if (mode == 1 && !dc_simple && nt % 16 == 0 && 4 * nt <= 256)
+            return conv3d_dc_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st);
     }
 
     TcParams p{};
