@@ -40,12 +40,17 @@ SIGNATURES = {
     "b2_grid_sample_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),
     "b2_conv3d": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_int, c_vp]),
+    "b2_conv3d_stat_rows": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "b2_conv3d_stats": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_vp]),
     "b2_conv3d_c1_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
     "b2_conv3d_c1_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "b2_conv3d_c1_dgrad": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "b2_groupnorm_workspace_bytes": (c_i64, [c_int, c_int]),
     "b2_groupnorm_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int,
                                  c_f32, c_int, c_vp, c_vp]),
+    "b2_groupnorm_fwd_ext": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64, c_int,
+                                     c_f32, c_int, c_vp, c_int, c_vp, c_vp]),
     "b2_groupnorm_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64,
                                  c_int, c_int, c_vp, c_vp]),
     "b2_bev_pool_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),

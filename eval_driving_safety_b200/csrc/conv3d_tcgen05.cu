@@ -123,6 +123,52 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- GroupNorm statistics in the epilogue
+// v[i] (i = 0..31) holds this lane's value for channel i; on return v[0] of lane l is the sum over
+// the warp's 32 lanes of channel l (recursive halving: 16+8+4+2+1 = 31 shuffles, fixed order).
+__device__ __forceinline__ void warp_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
+// Per-lane running totals of one epilogue warp: slot = n_tile * 2 + (32-channel chunk), lane = channel
+// inside the chunk.  Static indexing only (stays in registers).
+struct StatTotals {
+    float s[4], q[4];
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { s[i] = 0.f; q[i] = 0.f; }
+    }
+    __device__ __forceinline__ void add(int slot, float ds, float dq) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i == slot) { s[i] += ds; q[i] += dq; }
+    }
+};
+
+// After the CTA-wide barrier: one warp adds the four epilogue warps' totals in a fixed order and writes
+// this CTA's row of the partial-sum table [gridDim.x][2][Cout] (sum, sum of squares per channel).
+__device__ __forceinline__ void stat_store_row(const float (*sh)[8][32], float* __restrict__ stat_partial, int Cout,
+                                               int nt, int n_tiles, int lane) {
+    float* row = stat_partial + (long long)blockIdx.x * 2 * Cout;
+    for (int nti = 0; nti < n_tiles; ++nti)
+        for (int ch = 0; ch < nt / 32; ++ch) {
+            const int slot = nti * 2 + ch;
+            const float ts = ((sh[0][slot][lane] + sh[1][slot][lane]) + sh[2][slot][lane]) + sh[3][slot][lane];
+            const float tq = ((sh[0][4 + slot][lane] + sh[1][4 + slot][lane]) + sh[2][4 + slot][lane]) + sh[3][4 + slot][lane];
+            row[nti * nt + ch * 32 + lane] = ts;
+            row[Cout + nti * nt + ch * 32 + lane] = tq;
+        }
+}
+
 // ---------------------------------------------------------------- tile / step decode
 struct TileCoord { int cls, n, d, h0, w0; };
 
@@ -580,10 +626,11 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                          float* __restrict__ out, const S1Params p) {
+                          float* __restrict__ out, const S1Params p, float* __restrict__ stat_partial) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kS1NA + 2 * kS1MaxNB + 4];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float stat_sh[4][8][32];          // [epilogue warp][sum slots 0..3, square slots 4..7][lane]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -701,6 +748,9 @@ conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         tc_fence_before();
         mbar_arrive(tempty(0));
         mbar_arrive(tempty(1));
+        const bool stats = stat_partial != nullptr;       // fused GroupNorm statistics of the output
+        StatTotals tot;
+        tot.clear();
         long long it = 0;
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
             const int accbuf = (int)(it & 1);
@@ -709,14 +759,21 @@ conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             const bool ok_hw = r < p.R && w < p.W;
             mbar_wait(tfull(accbuf), (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            for (int j = 0; j < kS1Planes; ++j) {
+            auto out_row = [&](int j) {
                 const int pl = tc.d0 + j;
-                const bool ok = ok_hw && pl < p.P;
                 const int d = p.swap ? r : pl, h = p.swap ? pl : r;
-                float* orow = out + ((((long long)tc.n * p.D + d) * p.H + h) * p.W + w) * p.Cout + tc.nti * p.nt;
-                const uint32_t taddr = lane_addr + (uint32_t)((accbuf * kS1Planes + j) * p.nt);
-                int c0 = 0;
-                for (; c0 + 32 <= p.nt; c0 += 32) {
+                return out + ((((long long)tc.n * p.D + d) * p.H + h) * p.W + w) * p.Cout + tc.nti * p.nt;
+            };
+            int c0 = 0;
+            for (; c0 + 32 <= p.nt; c0 += 32) {           // 32-channel chunk outer, the 4 planes inner
+                float ssum[32], ssq[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+#pragma unroll 1
+                for (int j = 0; j < kS1Planes; ++j) {
+                    const bool ok = ok_hw && tc.d0 + j < p.P;
+                    float* orow = out_row(j);
+                    const uint32_t taddr = lane_addr + (uint32_t)((accbuf * kS1Planes + j) * p.nt);
                     uint32_t rr[32];
                     tmem_ld32(taddr + c0, rr);
                     tmem_ld_wait();
@@ -727,9 +784,27 @@ conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                             *reinterpret_cast<float4*>(orow + c0 + 4 * q) =
                                 make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
                                             __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
+                        if (stats) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const float v = __uint_as_float(rr[i]);
+                                ssum[i] += v;
+                                ssq[i] = fmaf(v, v, ssq[i]);
+                            }
+                        }
                     }
                 }
-                if (c0 < p.nt) {
+                if (stats) {
+                    warp_transpose_sum32(ssum, lane);
+                    warp_transpose_sum32(ssq, lane);
+                    tot.add(tc.nti * 2 + (c0 >> 5), ssum[0], ssq[0]);
+                }
+            }
+            if (c0 < p.nt) {                               // 16-channel tail (Nt = 16 or 48; no statistics)
+                for (int j = 0; j < kS1Planes; ++j) {
+                    const bool ok = ok_hw && tc.d0 + j < p.P;
+                    float* orow = out_row(j);
+                    const uint32_t taddr = lane_addr + (uint32_t)((accbuf * kS1Planes + j) * p.nt);
                     uint32_t rr[16];
                     tmem_ld16(taddr + c0, rr);
                     tmem_ld_wait();
@@ -747,18 +822,27 @@ conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             tc_fence_before();
             mbar_arrive(tempty(accbuf));
         }
+        if (stats) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { stat_sh[lane_grp][i][lane] = tot.s[i]; stat_sh[lane_grp][4 + i][lane] = tot.q[i]; }
+        }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (stat_partial != nullptr && warp == 2) stat_store_row(stat_sh, stat_partial, p.Cout, p.nt, p.n_tiles, lane);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
     }
 }
 
+// stat_partial != null: also write the per-CTA GroupNorm partial sums of the output, table
+// [grid][2][Cout]; *stat_rows (if given) receives the number of rows (= grid), 0 when this launch
+// configuration cannot produce them.  query = only compute *stat_rows, launch nothing.
 static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* wp, float* out, int N, int Cin,
-                            int Cout, int D, int H, int W, cudaStream_t st) {
+                            int Cout, int D, int H, int W, cudaStream_t st, float* stat_partial, int* stat_rows,
+                            bool query) {
     S1Params p{};
     p.N = N; p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W;
     p.nt = Cout <= 64 ? Cout : Cout / 2;
@@ -785,6 +869,13 @@ static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* 
     p.tmem_cols = 32;
     while (p.tmem_cols < 2 * kS1Planes * p.nt) p.tmem_cols *= 2;
     p.total_tiles = (long long)p.n_tiles * N * p.dblocks * p.tiles_h * p.tiles_w;
+    const int grid = (int)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
+    // statistics need one sample per launch (a CTA's row mixes all its tiles), whole 32-channel chunks,
+    // at most 2 x 2 (n tile, chunk) slots and the N-stacked kernel
+    const bool stats_ok = use_nstack && N == 1 && p.nt % 32 == 0 && p.nt <= 64 && p.n_tiles <= 2;
+    if (stat_rows) *stat_rows = stats_ok ? grid : 0;
+    if (query) return 0;
+    if (stat_partial && !stats_ok) { set_error("conv3d(tcgen05,s1): statistics not available for this shape"); return B2_ERR_UNSUPPORTED; }
 
     CUtensorMap map_a, map_b;
     {
@@ -821,9 +912,8 @@ static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* 
         if (e != cudaSuccess) { set_error("conv3d(tcgen05,s1): cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return (int)e; }
         attr_smem = smem;
     }
-    int grid = (int)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
     if (use_nstack)
-        conv3d_s1n_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p);
+        conv3d_s1n_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p, stat_partial);
     else
         conv3d_s1_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p);
     return check_launch("conv3d(tcgen05,s1)");
@@ -881,10 +971,11 @@ __device__ __forceinline__ DcUnit dc_decode(const DcParams& p, long long t) {
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                         float* __restrict__ out, const DcParams p) {
+                         float* __restrict__ out, const DcParams p, float* __restrict__ stat_partial) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kDcMaxStages + 4];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float stat_sh[4][8][32];          // [epilogue warp][sum slots 0..3, square slots 4..7][lane]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -1009,6 +1100,9 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         const int m = lane_grp * 32 + lane;
         const int hl = m / kTileW, wl = m % kTileW;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        const bool stats = stat_partial != nullptr;       // fused GroupNorm statistics of the output
+        StatTotals tot;
+        tot.clear();
         long long it = 0;
         for (long long t = blockIdx.x; t < p.total_units; t += gridDim.x, ++it) {
             const int acc = (int)(it & 1);
@@ -1018,13 +1112,20 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             const int op = 2 * u.d + u.pd;
             mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            for (int c = 0; c < 4; ++c) {
+            auto out_row = [&](int c) {
                 const int orow = 2 * h + (c >> 1), ow = 2 * w + (c & 1);
                 const int od = p.swap ? orow : op, oh = p.swap ? op : orow;
-                float* optr = out + ((((long long)u.n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.Cout + u.nti * p.nt;
-                const uint32_t taddr = lane_addr + (uint32_t)((acc * 4 + c) * p.nt);
-                int c0 = 0;
-                for (; c0 + 32 <= p.nt; c0 += 32) {
+                return out + ((((long long)u.n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.Cout + u.nti * p.nt;
+            };
+            int c0 = 0;
+            for (; c0 + 32 <= p.nt; c0 += 32) {           // 32-channel chunk outer, the 4 parity classes inner
+                float ssum[32], ssq[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    float* optr = out_row(c);
+                    const uint32_t taddr = lane_addr + (uint32_t)((acc * 4 + c) * p.nt);
                     uint32_t rr[32];
                     tmem_ld32(taddr + c0, rr);
                     tmem_ld_wait();
@@ -1034,9 +1135,26 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                             *reinterpret_cast<float4*>(optr + c0 + 4 * q) =
                                 make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
                                             __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
+                        if (stats) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) {
+                                const float v = __uint_as_float(rr[i]);
+                                ssum[i] += v;
+                                ssq[i] = fmaf(v, v, ssq[i]);
+                            }
+                        }
                     }
                 }
-                if (c0 < p.nt) {
+                if (stats) {
+                    warp_transpose_sum32(ssum, lane);
+                    warp_transpose_sum32(ssq, lane);
+                    tot.add(u.nti * 2 + (c0 >> 5), ssum[0], ssq[0]);
+                }
+            }
+            if (c0 < p.nt) {                               // 16-channel tail (no statistics)
+                for (int c = 0; c < 4; ++c) {
+                    float* optr = out_row(c);
+                    const uint32_t taddr = lane_addr + (uint32_t)((acc * 4 + c) * p.nt);
                     uint32_t rr[16];
                     tmem_ld16(taddr + c0, rr);
                     tmem_ld_wait();
@@ -1052,10 +1170,15 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
         }
+        if (stats) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { stat_sh[lane_grp][i][lane] = tot.s[i]; stat_sh[lane_grp][4 + i][lane] = tot.q[i]; }
+        }
     }
 
     tc_fence_before();
     __syncthreads();
+    if (stat_partial != nullptr && warp == 2) stat_store_row(stat_sh, stat_partial, p.Cout, p.nt, p.n_tiles, lane);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -1063,7 +1186,8 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 }
 
 static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* wp, float* out, int N, int Cin,
-                            int Cout, int Di, int Hi, int Wi, cudaStream_t st) {
+                            int Cout, int Di, int Hi, int Wi, cudaStream_t st, float* stat_partial, int* stat_rows,
+                            bool query) {
     DcParams p{};
     p.N = N; p.Cin = Cin; p.Cout = Cout;
     p.Do = 2 * Di; p.Ho = 2 * Hi; p.Wo = 2 * Wi;
@@ -1087,6 +1211,11 @@ static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* 
     p.tmem_cols = 32;
     while (p.tmem_cols < 8 * p.nt) p.tmem_cols *= 2;
     p.total_units = (long long)p.n_tiles * N * p.Pt * 2 * p.tiles_h * p.tiles_w;
+    const int grid = (int)(p.total_units < kNumSMs ? p.total_units : kNumSMs);
+    const bool stats_ok = N == 1 && p.nt % 32 == 0 && p.nt <= 64 && p.n_tiles <= 2;
+    if (stat_rows) *stat_rows = stats_ok ? grid : 0;
+    if (query) return 0;
+    if (stat_partial && !stats_ok) { set_error("conv3d(tcgen05,deconv): statistics not available for this shape"); return B2_ERR_UNSUPPORTED; }
 
     CUtensorMap map_a, map_b;
     {
@@ -1121,20 +1250,22 @@ static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* 
         if (e != cudaSuccess) { set_error("conv3d(tcgen05,deconv): cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return (int)e; }
         attr_smem = smem;
     }
-    int grid = (int)(p.total_units < kNumSMs ? p.total_units : kNumSMs);
-    conv3d_dc_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p);
+    conv3d_dc_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p, stat_partial);
     return check_launch("conv3d(tcgen05,deconv)");
 }
 
 int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
-                          int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st) {
+                          int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st,
+                          float* stat_partial, int* stat_rows, bool query) {
+    if (stat_rows) *stat_rows = 0;
     if (Cin % 32 != 0 || Cout % 32 != 0 || Cout > 256 || Cout < 32) {
+        if (query) return 0;
         set_error("conv3d(tcgen05): needs Cin %% 32 == 0 and Cout in {32,64,...,256} (got %d -> %d); "
                   "use impl=1 for other widths", Cin, Cout);
         return B2_ERR_UNSUPPORTED;
     }
     EncodeTiledFn encode = get_encode();
-    if (!encode) { set_error("conv3d(tcgen05): cuTensorMapEncodeTiled not available from the driver"); return B2_ERR_DRIVER; }
+    if (!encode && !query) { set_error("conv3d(tcgen05): cuTensorMapEncodeTiled not available from the driver"); return B2_ERR_DRIVER; }
     {
         // stride-1 convs (74 % of the flops) take the halo-reuse super-tile kernel; B2_CONV_S1_SIMPLE=1
         // forces the generic one-tap-per-stage kernel (A/B testing)
@@ -1142,13 +1273,16 @@ int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, i
         if (simple < 0) { const char* e = getenv("B2_CONV_S1_SIMPLE"); simple = (e && e[0] == '1') ? 1 : 0; }
         const int nt = Cout <= 64 ? Cout : Cout / 2;
         if (mode == 0 && stride == 1 && !simple && nt % 16 == 0)
-            return conv3d_s1_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st);
+            return conv3d_s1_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st, stat_partial, stat_rows, query);
         // transposed convs take the class-stacked kernel; B2_CONV_DC_SIMPLE=1 forces the generic one
         static int dc_simple = -1;
         if (dc_simple < 0) { const char* e = getenv("B2_CONV_DC_SIMPLE"); dc_simple = (e && e[0] == '1') ? 1 : 0; }
         if (mode == 1 && !dc_simple && nt % 16 == 0 && 4 * nt <= 256)
-            return conv3d_dc_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st);
+            return conv3d_dc_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st, stat_partial, stat_rows, query);
     }
+
+    if (query) return 0;                                   // the generic kernel has no statistics epilogue
+    if (stat_partial) { set_error("conv3d(tcgen05): statistics not available for this shape"); return B2_ERR_UNSUPPORTED; }
 
     TcParams p{};
     p.N = N; p.Cin = Cin; p.Cout = Cout; p.Do = Do; p.Ho = Ho; p.Wo = Wo;

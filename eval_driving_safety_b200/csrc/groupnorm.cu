@@ -277,25 +277,45 @@ static int gn_check(const char* who, int N, int C, int64_t S, int G) {
     return 0;
 }
 
-extern "C" int b2_groupnorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,
-                                float* y, float* stats, int N, int C, int64_t S, int G, float eps,
-                                int relu, void* workspace, void* stream) {
+static int groupnorm_fwd_impl(const float* x, const float* res, const float* gamma, const float* beta,
+                              float* y, float* stats, int N, int C, int64_t S, int G, float eps,
+                              int relu, const float* ext_partial, int ext_rows, void* workspace, void* stream) {
     B2_REQUIRE(x && gamma && beta && y && stats && workspace, "groupnorm_fwd: null pointer");
     if (int e = gn_check("groupnorm_fwd", N, C, S, G)) return e;
     B2_REQUIRE(aligned16(x) && aligned16(y) && (!res || aligned16(res)), "groupnorm_fwd: pointers must be 16B aligned");
+    B2_REQUIRE(!ext_partial || (N == 1 && ext_rows >= 1), "groupnorm_fwd: external partial sums need N == 1 and >= 1 row");
     if (N == 0 || S == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     GnLayout l = gn_layout(C);
     float* partial = (float*)workspace;
     float* coef = partial + gn_partial_floats(N, C);
-    int nblocks = gn_nblocks(S);
-    gn_partials_kernel<0><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
-        nullptr, (const float4*)x, nullptr, partial, C, S, l.lpr, l.rpb, 0, nullptr, G);
-    gn_finalize_fwd<<<dim3(G, N), kGnFinThreads, 0, st>>>(partial, gamma, beta, stats, coef, C, S, G, eps, nblocks);
+    if (ext_partial) {
+        // statistics pass already done by the producer (conv epilogue): table [ext_rows][2][C]
+        gn_finalize_fwd<<<dim3(G, N), kGnFinThreads, 0, st>>>(ext_partial, gamma, beta, stats, coef, C, S, G, eps, ext_rows);
+    } else {
+        int nblocks = gn_nblocks(S);
+        gn_partials_kernel<0><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
+            nullptr, (const float4*)x, nullptr, partial, C, S, l.lpr, l.rpb, 0, nullptr, G);
+        gn_finalize_fwd<<<dim3(G, N), kGnFinThreads, 0, st>>>(partial, gamma, beta, stats, coef, C, S, G, eps, nblocks);
+    }
     int gx = stream_grid(S * l.lpr, 256 * 4, kNumSMs * 8);
     gn_apply_fwd<<<dim3(gx, N), 256, 2 * C * sizeof(float), st>>>((const float4*)x, (const float4*)res, coef,
                                                                   (float4*)y, C, S, relu);
     return check_launch("groupnorm_fwd");
+}
+
+extern "C" int b2_groupnorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,
+                                float* y, float* stats, int N, int C, int64_t S, int G, float eps,
+                                int relu, void* workspace, void* stream) {
+    return groupnorm_fwd_impl(x, res, gamma, beta, y, stats, N, C, S, G, eps, relu, nullptr, 0, workspace, stream);
+}
+
+extern "C" int b2_groupnorm_fwd_ext(const float* x, const float* res, const float* gamma, const float* beta,
+                                    float* y, float* stats, int N, int C, int64_t S, int G, float eps,
+                                    int relu, const float* ext_partial, int ext_rows, void* workspace,
+                                    void* stream) {
+    B2_REQUIRE(ext_partial, "groupnorm_fwd_ext: null partial-sum table");
+    return groupnorm_fwd_impl(x, res, gamma, beta, y, stats, N, C, S, G, eps, relu, ext_partial, ext_rows, workspace, stream);
 }
 
 extern "C" int b2_groupnorm_bwd(const float* gy, const float* x, const float* y, const float* gamma,

@@ -63,8 +63,9 @@ def run_convbn_3d(seq, x, relu=False, res=None):
     ``seq`` = Sequential(Conv3d | ConvTranspose3d, GroupNorm) used as parameter holder."""
     conv, norm = seq[0], seq[1]
     transposed = isinstance(conv, nn.ConvTranspose3d)
-    y = ops.conv3d(x, conv.weight, stride=conv.stride[0], transposed=transposed)
-    return ops.groupnorm_act(y, norm.weight, norm.bias, norm.num_groups, norm.eps, relu=relu, res=res)
+    # the conv epilogue adds up the GroupNorm statistics of its own output where the kernel supports it
+    y, part = ops.conv3d_with_stats(x, conv.weight, stride=conv.stride[0], transposed=transposed)
+    return ops.groupnorm_act(y, norm.weight, norm.bias, norm.num_groups, norm.eps, relu=relu, res=res, partial=part)
 
 
 # Stock 2-D convolutions (cuDNN).  'tf32' = PyTorch's default on this hardware; 'tf32x3' = the same

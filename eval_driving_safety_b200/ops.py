@@ -360,7 +360,12 @@ def _cache_put(key, weight, packed):
     _PACK_CACHE[key] = (weakref.ref(weight), (weight._version, weight.data_ptr()), packed)
 
 
-def _conv_call(x, wp, stride, mode, impl):
+FUSE_GN_STATS = os.environ.get("B2_FUSE_GN_STATS", "1") != "0"
+
+
+def _conv_call(x, wp, stride, mode, impl, stats=False):
+    """``stats``: also return the conv epilogue's GroupNorm partial sums of the output
+    ([rows, 2, Cout]) or None when this launch configuration cannot produce them."""
     lib = _lib.load()
     n, cin, di, hi, wi = x.shape
     cout = wp.shape[1]
@@ -373,10 +378,17 @@ def _conv_call(x, wp, stride, mode, impl):
     # algorithmic flops: 2*Cin*Cout*27 per output voxel for CONV; a transposed conv touches
     # 27/8 taps per output voxel on average (= 2*Cin*Cout*27 per INPUT voxel)
     vox = n * do * ho * wo if mode == 0 else n * di * hi * wi
+    rows = lib.b2_conv3d_stat_rows(n, cin, cout, di, hi, wi, stride, mode) if (stats and impl == 0 and FUSE_GN_STATS) else 0
+    part = None
     with _op("conv3d_tcgen05" if impl == 0 else "conv3d_simt", 1, 2 * cin * cout * 27 * vox):
-        check(lib.b2_conv3d(_p(x), _p(wp), _p(out), n, cin, cout, di, hi, wi, stride, mode, impl, _stream()),
-              "conv3d(mode=%d,stride=%d,impl=%d)" % (mode, stride, impl))
-    return out
+        if rows > 0:
+            part = torch.empty((rows, 2, cout), device=x.device, dtype=torch.float32)
+            check(lib.b2_conv3d_stats(_p(x), _p(wp), _p(out), _p(part), n, cin, cout, di, hi, wi, stride, mode,
+                                      _stream()), "conv3d_stats(mode=%d,stride=%d)" % (mode, stride))
+        else:
+            check(lib.b2_conv3d(_p(x), _p(wp), _p(out), n, cin, cout, di, hi, wi, stride, mode, impl, _stream()),
+                  "conv3d(mode=%d,stride=%d,impl=%d)" % (mode, stride, impl))
+    return (out, part) if stats else out
 
 
 class Conv3dFn(Function):
@@ -385,7 +397,7 @@ class Conv3dFn(Function):
     data gradient.  Weights are frozen in an attack: no weight gradient."""
 
     @staticmethod
-    def forward(ctx, x, weight, stride, transposed, impl):
+    def forward(ctx, x, weight, stride, transposed, impl, stats=False):
         _need_cuda(x, weight)
         if weight.requires_grad:
             raise RuntimeError("attack path: weights are frozen; call requires_grad_(False) on the model "
@@ -398,15 +410,21 @@ class Conv3dFn(Function):
         impl = CONV_IMPL if impl is None else impl
         if transposed:
             assert stride == 2
-            out = _conv_call(x, _packed(weight, "deconv_fwd"), 2, 1, impl)
+            out = _conv_call(x, _packed(weight, "deconv_fwd"), 2, 1, impl, stats)
         else:
-            out = _conv_call(x, _packed(weight, "conv_fwd"), stride, 0, impl)
+            out = _conv_call(x, _packed(weight, "conv_fwd"), stride, 0, impl, stats)
         ctx.weight, ctx.cfg = weight, (stride, transposed, impl)
+        if stats:
+            out, part = out
+            if part is None:
+                part = out.new_empty(0)               # "no statistics": autograd outputs must be tensors
+            ctx.mark_non_differentiable(part)
+            return out, part
         return out
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gout):
+    def backward(ctx, gout, *_unused):
         stride, transposed, impl = ctx.cfg
         g = cl3(gout)
         if transposed:
@@ -415,11 +433,20 @@ class Conv3dFn(Function):
             gin = _conv_call(g, _packed(ctx.weight, "conv_dgrad_s1"), 1, 0, impl)
         else:
             gin = _conv_call(g, _packed(ctx.weight, "conv_dgrad_s2"), 2, 1, impl)
-        return gin, None, None, None, None
+        return gin, None, None, None, None, None
 
 
 def conv3d(x, weight, stride=1, transposed=False, impl=None):
-    return Conv3dFn.apply(x, weight, stride, transposed, impl)
+    return Conv3dFn.apply(x, weight, stride, transposed, impl, False)
+
+
+def conv3d_with_stats(x, weight, stride=1, transposed=False, impl=None):
+    """conv3d whose epilogue also adds up the GroupNorm statistics of its output.  Returns
+    (y, partial): ``partial`` [rows, 2, Cout] goes to ``groupnorm_act(..., partial=)``; it is None
+    when the kernel that serves this shape has no statistics epilogue (GroupNorm then runs its own
+    statistics pass)."""
+    y, part = Conv3dFn.apply(x, weight, stride, transposed, impl, True)
+    return y, (part if part.numel() else None)
 
 
 class Conv3dC1Fn(Function):
@@ -485,7 +512,7 @@ class GroupNormActFn(Function):
     """y = act(GroupNorm(x) (+ res)) on channels-last 3-D volumes or 2-D maps; data gradient only."""
 
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, groups, eps, relu):
+    def forward(ctx, x, res, gamma, beta, groups, eps, relu, partial=None):
         _need_cuda(x, res, gamma, beta)
         lib = _lib.load()
         x = _cl(x)
@@ -496,9 +523,16 @@ class GroupNormActFn(Function):
         stats = torch.empty((n, 2 * groups + 2 * c), device=x.device, dtype=torch.float32)
         ws = _workspace(lib.b2_groupnorm_workspace_bytes(n, c), x.device)
         gamma, beta = gamma.detach().contiguous(), beta.detach().contiguous()
-        with _op("groupnorm_fwd", 3, 4 * x.numel() * (3 + (res is not None))):
-            check(lib.b2_groupnorm_fwd(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(stats), n, c, s, groups,
-                                       float(eps), int(relu), _p(ws), _stream()), "groupnorm_fwd")
+        if partial is not None:
+            assert n == 1 and partial.dim() == 3 and partial.shape[1:] == (2, c), (partial.shape, n, c)
+            with _op("groupnorm_fwd", 2, 4 * x.numel() * (2 + (res is not None))):
+                check(lib.b2_groupnorm_fwd_ext(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(stats), n, c, s, groups,
+                                               float(eps), int(relu), _p(partial), partial.shape[0], _p(ws),
+                                               _stream()), "groupnorm_fwd_ext")
+        else:
+            with _op("groupnorm_fwd", 3, 4 * x.numel() * (3 + (res is not None))):
+                check(lib.b2_groupnorm_fwd(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(stats), n, c, s, groups,
+                                           float(eps), int(relu), _p(ws), _stream()), "groupnorm_fwd")
         # ReLU without residual: the backward recomputes the mask from x (relu mode 2), so y is not
         # kept alive by this node (and is never re-read)
         keep_y = relu and res is not None
@@ -524,11 +558,13 @@ class GroupNormActFn(Function):
                                        mode, _p(ws), _stream()), "groupnorm_bwd")
         if has_res and not relu:
             gres = gy
-        return gx, gres, None, None, None, None, None
+        return gx, gres, None, None, None, None, None, None
 
 
-def groupnorm_act(x, gamma, beta, groups, eps=1e-5, relu=False, res=None):
-    return GroupNormActFn.apply(x, res, gamma, beta, groups, eps, relu)
+def groupnorm_act(x, gamma, beta, groups, eps=1e-5, relu=False, res=None, partial=None):
+    """``partial``: per-channel partial sums of x from the producing conv's epilogue
+    (``conv3d_with_stats``); the statistics pass over x is skipped."""
+    return GroupNormActFn.apply(x, res, gamma, beta, groups, eps, relu, partial)
 
 
 class BevPoolFn(Function):

@@ -57,6 +57,54 @@ def test_conv3d_adjoint_at_kitti_sizes(ops, cin, cout, stride, transposed, sp):
     assert torch.equal(ops.conv3d(2 * x.detach(), w, stride=stride, transposed=transposed), 2 * y.detach())
 
 
+STAT_CASES = [
+    # (N, Cin, Cout, stride, transposed, input spatial, statistics expected)
+    (1, 64, 64, 1, False, (48, 96, 312), True),       # N-stacked stride-1 kernel, KITTI PSV size
+    (1, 96, 64, 1, False, (192, 20, 304), True),      # role-swapped tiles
+    (1, 128, 128, 1, False, (12, 24, 78), True),      # two N tiles
+    (1, 32, 32, 1, False, (5, 7, 9), True),           # ragged: partial tiles / planes must not be counted
+    (1, 128, 64, 2, True, (24, 48, 156), True),       # class-stacked transposed kernel
+    (1, 128, 128, 2, True, (6, 5, 9), True),          # transposed, two N tiles, ragged
+    (1, 64, 128, 2, False, (12, 24, 40), False),      # stride-2 conv: generic kernel, GroupNorm's own pass
+    (2, 64, 64, 1, False, (6, 16, 16), False),        # N > 1: a CTA row would mix samples
+]
+
+
+@pytest.mark.parametrize("n,cin,cout,stride,transposed,sp,expect", STAT_CASES)
+def test_conv_epilogue_groupnorm_statistics(ops, n, cin, cout, stride, transposed, sp, expect):
+    """conv3d_with_stats: the epilogue's per-CTA partial sums reproduce the statistics of the written
+    output (fp64 reference), GroupNorm fed with them equals GroupNorm with its own pass, forward and
+    backward, and the whole thing is bitwise reproducible."""
+    g = torch.Generator().manual_seed(cin * 3 + cout + sp[0])
+    x = _cl3((n, cin) + sp, g).requires_grad_(True)
+    wshape = (cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3)
+    w = (torch.randn(wshape, generator=g) * (27 * cin) ** -0.5).cuda()
+    y, part = ops.conv3d_with_stats(x, w, stride=stride, transposed=transposed)
+    y0 = ops.conv3d(x, w, stride=stride, transposed=transposed)
+    assert torch.equal(y, y0)                                        # same kernel, same output
+    assert (part is not None) == expect
+    gamma = (torch.rand(cout, generator=g) + 0.5).cuda()
+    beta = torch.randn(cout, generator=g).cuda()
+    ref = ops.groupnorm_act(y0, gamma, beta, 32, 1e-5, relu=True)
+    if part is None:
+        return
+    assert part.shape[1:] == (2, cout)
+    yd = y.detach().double()
+    s_ref, q_ref = yd.sum((0, 2, 3, 4)), (yd * yd).sum((0, 2, 3, 4))
+    s_got, q_got = part[:, 0].double().sum(0), part[:, 1].double().sum(0)
+    scale = q_ref.sqrt() * yd[0, 0].numel() ** 0.5 + 1e-6
+    assert ((s_got - s_ref).abs() / scale).max().item() < 1e-5
+    assert ((q_got - q_ref).abs() / q_ref).max().item() < 1e-5
+    out = ops.groupnorm_act(y, gamma, beta, 32, 1e-5, relu=True, partial=part)
+    assert (out - ref).abs().max().item() < 2e-5
+    gy = _cl3(tuple(out.shape), g)
+    (gx,) = torch.autograd.grad(out, x, gy)
+    (gx_ref,) = torch.autograd.grad(ref, x, gy)
+    assert (gx - gx_ref).abs().max().item() < 1e-4 * gx_ref.abs().max().item() + 1e-6
+    y2, part2 = ops.conv3d_with_stats(x, w, stride=stride, transposed=transposed)
+    assert torch.equal(part, part2)                                  # fixed summation order
+
+
 def test_conv3d_c1_adjoint_at_kitti_size(ops):
     g = torch.Generator().manual_seed(5)
     x = _cl3((1, 64, 48, 96, 312), g).requires_grad_(True)
