@@ -139,6 +139,22 @@ __device__ __forceinline__ void warp_transpose_sum32(float (&v)[32], int lane) {
     }
 }
 
+// out = accumulator + addend (the other gradient that autograd would add in a separate pass):
+// NQ float4 of the addend row are loaded first, then added to the drained accumulator registers.
+template <int NQ>
+__device__ __forceinline__ void epilogue_add(uint32_t* rr, const float* __restrict__ arow) {
+    float4 a[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) a[q] = __ldg(reinterpret_cast<const float4*>(arow) + q);
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        rr[4 * q] = __float_as_uint(__uint_as_float(rr[4 * q]) + a[q].x);
+        rr[4 * q + 1] = __float_as_uint(__uint_as_float(rr[4 * q + 1]) + a[q].y);
+        rr[4 * q + 2] = __float_as_uint(__uint_as_float(rr[4 * q + 2]) + a[q].z);
+        rr[4 * q + 3] = __float_as_uint(__uint_as_float(rr[4 * q + 3]) + a[q].w);
+    }
+}
+
 // Per-lane running totals of one epilogue warp: slot = n_tile * 2 + (32-channel chunk), lane = channel
 // inside the chunk.  Static indexing only (stays in registers).
 struct StatTotals {
@@ -626,7 +642,8 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                          float* __restrict__ out, const S1Params p, float* __restrict__ stat_partial) {
+                          float* __restrict__ out, const S1Params p, float* __restrict__ stat_partial,
+                          const float* __restrict__ addend) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kS1NA + 2 * kS1MaxNB + 4];
     __shared__ uint32_t tmem_base_slot;
@@ -759,10 +776,10 @@ conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             const bool ok_hw = r < p.R && w < p.W;
             mbar_wait(tfull(accbuf), (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            auto out_row = [&](int j) {
+            auto row_off = [&](int j) {
                 const int pl = tc.d0 + j;
                 const int d = p.swap ? r : pl, h = p.swap ? pl : r;
-                return out + ((((long long)tc.n * p.D + d) * p.H + h) * p.W + w) * p.Cout + tc.nti * p.nt;
+                return ((((long long)tc.n * p.D + d) * p.H + h) * p.W + w) * p.Cout + tc.nti * p.nt;
             };
             int c0 = 0;
             for (; c0 + 32 <= p.nt; c0 += 32) {           // 32-channel chunk outer, the 4 planes inner
@@ -772,13 +789,15 @@ conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
 #pragma unroll 1
                 for (int j = 0; j < kS1Planes; ++j) {
                     const bool ok = ok_hw && tc.d0 + j < p.P;
-                    float* orow = out_row(j);
+                    const long long off = row_off(j);
+                    float* orow = out + off;
                     const uint32_t taddr = lane_addr + (uint32_t)((accbuf * kS1Planes + j) * p.nt);
                     uint32_t rr[32];
                     tmem_ld32(taddr + c0, rr);
                     tmem_ld_wait();
                     tmem_st32_zero(taddr + c0);
                     if (ok) {
+                        if (addend) epilogue_add<8>(rr, addend + off + c0);
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
                             *reinterpret_cast<float4*>(orow + c0 + 4 * q) =
@@ -803,13 +822,15 @@ conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             if (c0 < p.nt) {                               // 16-channel tail (Nt = 16 or 48; no statistics)
                 for (int j = 0; j < kS1Planes; ++j) {
                     const bool ok = ok_hw && tc.d0 + j < p.P;
-                    float* orow = out_row(j);
+                    const long long off = row_off(j);
+                    float* orow = out + off;
                     const uint32_t taddr = lane_addr + (uint32_t)((accbuf * kS1Planes + j) * p.nt);
                     uint32_t rr[16];
                     tmem_ld16(taddr + c0, rr);
                     tmem_ld_wait();
                     tmem_st16_zero(taddr + c0);
                     if (ok) {
+                        if (addend) epilogue_add<4>(rr, addend + off + c0);
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
                             *reinterpret_cast<float4*>(orow + c0 + 4 * q) =
@@ -842,7 +863,7 @@ conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
 // configuration cannot produce them.  query = only compute *stat_rows, launch nothing.
 static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* wp, float* out, int N, int Cin,
                             int Cout, int D, int H, int W, cudaStream_t st, float* stat_partial, int* stat_rows,
-                            bool query) {
+                            bool query, const float* addend, int* addend_ok) {
     S1Params p{};
     p.N = N; p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W;
     p.nt = Cout <= 64 ? Cout : Cout / 2;
@@ -874,8 +895,10 @@ static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* 
     // at most 2 x 2 (n tile, chunk) slots and the N-stacked kernel
     const bool stats_ok = use_nstack && N == 1 && p.nt % 32 == 0 && p.nt <= 64 && p.n_tiles <= 2;
     if (stat_rows) *stat_rows = stats_ok ? grid : 0;
+    if (addend_ok) *addend_ok = use_nstack ? 1 : 0;
     if (query) return 0;
     if (stat_partial && !stats_ok) { set_error("conv3d(tcgen05,s1): statistics not available for this shape"); return B2_ERR_UNSUPPORTED; }
+    if (addend && !use_nstack) { set_error("conv3d(tcgen05,s1): fused addend not available for this shape"); return B2_ERR_UNSUPPORTED; }
 
     CUtensorMap map_a, map_b;
     {
@@ -913,7 +936,7 @@ static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* 
         attr_smem = smem;
     }
     if (use_nstack)
-        conv3d_s1n_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p, stat_partial);
+        conv3d_s1n_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p, stat_partial, addend);
     else
         conv3d_s1_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p);
     return check_launch("conv3d(tcgen05,s1)");
@@ -971,7 +994,8 @@ __device__ __forceinline__ DcUnit dc_decode(const DcParams& p, long long t) {
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                         float* __restrict__ out, const DcParams p, float* __restrict__ stat_partial) {
+                         float* __restrict__ out, const DcParams p, float* __restrict__ stat_partial,
+                         const float* __restrict__ addend) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kDcMaxStages + 4];
     __shared__ uint32_t tmem_base_slot;
@@ -1112,10 +1136,10 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             const int op = 2 * u.d + u.pd;
             mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            auto out_row = [&](int c) {
+            auto row_off = [&](int c) {
                 const int orow = 2 * h + (c >> 1), ow = 2 * w + (c & 1);
                 const int od = p.swap ? orow : op, oh = p.swap ? op : orow;
-                return out + ((((long long)u.n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.Cout + u.nti * p.nt;
+                return ((((long long)u.n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.Cout + u.nti * p.nt;
             };
             int c0 = 0;
             for (; c0 + 32 <= p.nt; c0 += 32) {           // 32-channel chunk outer, the 4 parity classes inner
@@ -1124,12 +1148,14 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 for (int i = 0; i < 32; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
-                    float* optr = out_row(c);
+                    const long long off = row_off(c);
+                    float* optr = out + off;
                     const uint32_t taddr = lane_addr + (uint32_t)((acc * 4 + c) * p.nt);
                     uint32_t rr[32];
                     tmem_ld32(taddr + c0, rr);
                     tmem_ld_wait();
                     if (ok) {
+                        if (addend) epilogue_add<8>(rr, addend + off + c0);
 #pragma unroll
                         for (int q = 0; q < 8; ++q)
                             *reinterpret_cast<float4*>(optr + c0 + 4 * q) =
@@ -1153,12 +1179,14 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             }
             if (c0 < p.nt) {                               // 16-channel tail (no statistics)
                 for (int c = 0; c < 4; ++c) {
-                    float* optr = out_row(c);
+                    const long long off = row_off(c);
+                    float* optr = out + off;
                     const uint32_t taddr = lane_addr + (uint32_t)((acc * 4 + c) * p.nt);
                     uint32_t rr[16];
                     tmem_ld16(taddr + c0, rr);
                     tmem_ld_wait();
                     if (ok) {
+                        if (addend) epilogue_add<4>(rr, addend + off + c0);
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
                             *reinterpret_cast<float4*>(optr + c0 + 4 * q) =
@@ -1187,7 +1215,7 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 
 static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* wp, float* out, int N, int Cin,
                             int Cout, int Di, int Hi, int Wi, cudaStream_t st, float* stat_partial, int* stat_rows,
-                            bool query) {
+                            bool query, const float* addend, int* addend_ok) {
     DcParams p{};
     p.N = N; p.Cin = Cin; p.Cout = Cout;
     p.Do = 2 * Di; p.Ho = 2 * Hi; p.Wo = 2 * Wi;
@@ -1214,6 +1242,7 @@ static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* 
     const int grid = (int)(p.total_units < kNumSMs ? p.total_units : kNumSMs);
     const bool stats_ok = N == 1 && p.nt % 32 == 0 && p.nt <= 64 && p.n_tiles <= 2;
     if (stat_rows) *stat_rows = stats_ok ? grid : 0;
+    if (addend_ok) *addend_ok = 1;
     if (query) return 0;
     if (stat_partial && !stats_ok) { set_error("conv3d(tcgen05,deconv): statistics not available for this shape"); return B2_ERR_UNSUPPORTED; }
 
@@ -1250,14 +1279,15 @@ static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* 
         if (e != cudaSuccess) { set_error("conv3d(tcgen05,deconv): cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return (int)e; }
         attr_smem = smem;
     }
-    conv3d_dc_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p, stat_partial);
+    conv3d_dc_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p, stat_partial, addend);
     return check_launch("conv3d(tcgen05,deconv)");
 }
 
 int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
                           int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st,
-                          float* stat_partial, int* stat_rows, bool query) {
+                          float* stat_partial, int* stat_rows, bool query, const float* addend, int* addend_ok) {
     if (stat_rows) *stat_rows = 0;
+    if (addend_ok) *addend_ok = 0;
     if (Cin % 32 != 0 || Cout % 32 != 0 || Cout > 256 || Cout < 32) {
         if (query) return 0;
         set_error("conv3d(tcgen05): needs Cin %% 32 == 0 and Cout in {32,64,...,256} (got %d -> %d); "
@@ -1273,16 +1303,18 @@ int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, i
         if (simple < 0) { const char* e = getenv("B2_CONV_S1_SIMPLE"); simple = (e && e[0] == '1') ? 1 : 0; }
         const int nt = Cout <= 64 ? Cout : Cout / 2;
         if (mode == 0 && stride == 1 && !simple && nt % 16 == 0)
-            return conv3d_s1_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st, stat_partial, stat_rows, query);
+            return conv3d_s1_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st, stat_partial, stat_rows, query, addend,
+                                    addend_ok);
         // transposed convs take the class-stacked kernel; B2_CONV_DC_SIMPLE=1 forces the generic one
         static int dc_simple = -1;
         if (dc_simple < 0) { const char* e = getenv("B2_CONV_DC_SIMPLE"); dc_simple = (e && e[0] == '1') ? 1 : 0; }
         if (mode == 1 && !dc_simple && nt % 16 == 0 && 4 * nt <= 256)
-            return conv3d_dc_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st, stat_partial, stat_rows, query);
+            return conv3d_dc_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st, stat_partial, stat_rows, query, addend,
+                                    addend_ok);
     }
 
     if (query) return 0;                                   // the generic kernel has no statistics epilogue
-    if (stat_partial) { set_error("conv3d(tcgen05): statistics not available for this shape"); return B2_ERR_UNSUPPORTED; }
+    if (stat_partial || addend) { set_error("conv3d(tcgen05): fused statistics / addend not available for this shape"); return B2_ERR_UNSUPPORTED; }
 
     TcParams p{};
     p.N = N; p.Cin = Cin; p.Cout = Cout; p.Do = Do; p.Ho = Ho; p.Wo = Wo;

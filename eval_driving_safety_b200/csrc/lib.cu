@@ -18,7 +18,7 @@ int conv3d_simt_launch(const float* in, const float* wp, float* out, int N, int 
                        int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st);
 int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
                           int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st,
-                          float* stat_partial, int* stat_rows, bool query);
+                          float* stat_partial, int* stat_rows, bool query, const float* addend, int* addend_ok);
 
 }  // namespace b2
 
@@ -28,7 +28,7 @@ extern "C" const char* b2_last_error(void) { return b2::g_err; }
 
 static int conv3d_dispatch(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
                            int Hi, int Wi, int stride, int mode, int impl, void* stream, float* stat_partial,
-                           int* stat_rows, bool query) {
+                           int* stat_rows, bool query, const float* addend = nullptr, int* addend_ok = nullptr) {
     B2_REQUIRE(query || (in && wp && out), "conv3d: null pointer");
     B2_REQUIRE(N >= 0 && Cin > 0 && Cout > 0 && Di > 0 && Hi > 0 && Wi > 0, "conv3d: bad dims");
     B2_REQUIRE(mode == 0 || mode == 1, "conv3d: mode must be 0 (CONV) or 1 (DECONV)");
@@ -41,16 +41,17 @@ static int conv3d_dispatch(const float* in, const float* wp, float* out, int N, 
         Do = 2 * Di; Ho = 2 * Hi; Wo = 2 * Wi;
     }
     if (stat_rows) *stat_rows = 0;
+    if (addend_ok) *addend_ok = 0;
     if (N == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     if (impl == 1) {
-        B2_REQUIRE(!stat_partial, "conv3d: the SIMT implementation has no statistics epilogue");
+        B2_REQUIRE(!stat_partial && !addend, "conv3d: the SIMT implementation has no fused epilogue");
         if (query) return 0;
         return b2::conv3d_simt_launch(in, wp, out, N, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo, stride, mode, st);
     }
     if (impl == 0)
         return b2::conv3d_tcgen05_launch(in, wp, out, N, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo, stride, mode, st,
-                                         stat_partial, stat_rows, query);
+                                         stat_partial, stat_rows, query, addend, addend_ok);
     b2::set_error("conv3d: unknown impl %d", impl);
     return B2_ERR_BAD_ARG;
 }
@@ -60,15 +61,19 @@ extern "C" int b2_conv3d(const float* in, const float* wp, float* out, int N, in
     return conv3d_dispatch(in, wp, out, N, Cin, Cout, Di, Hi, Wi, stride, mode, impl, stream, nullptr, nullptr, false);
 }
 
-extern "C" int b2_conv3d_stat_rows(int N, int Cin, int Cout, int Di, int Hi, int Wi, int stride, int mode) {
-    int rows = 0;
-    if (conv3d_dispatch(nullptr, nullptr, nullptr, N, Cin, Cout, Di, Hi, Wi, stride, mode, 0, nullptr, nullptr, &rows, true) != 0)
-        return 0;
-    return rows;
+extern "C" int b2_conv3d_fusion_caps(int N, int Cin, int Cout, int Di, int Hi, int Wi, int stride, int mode,
+                                     int* stat_rows, int* addend_ok) {
+    int rows = 0, aok = 0;
+    int rc = conv3d_dispatch(nullptr, nullptr, nullptr, N, Cin, Cout, Di, Hi, Wi, stride, mode, 0, nullptr, nullptr, &rows,
+                             true, nullptr, &aok);
+    if (rc != 0) { rows = 0; aok = 0; }
+    if (stat_rows) *stat_rows = rows;
+    if (addend_ok) *addend_ok = aok;
+    return 0;
 }
 
-extern "C" int b2_conv3d_stats(const float* in, const float* wp, float* out, float* stat_partial, int N, int Cin,
-                               int Cout, int Di, int Hi, int Wi, int stride, int mode, void* stream) {
-    B2_REQUIRE(stat_partial, "conv3d_stats: null statistics table");
-    return conv3d_dispatch(in, wp, out, N, Cin, Cout, Di, Hi, Wi, stride, mode, 0, stream, stat_partial, nullptr, false);
+extern "C" int b2_conv3d_fused(const float* in, const float* wp, float* out, const float* addend, float* stat_partial,
+                               int N, int Cin, int Cout, int Di, int Hi, int Wi, int stride, int mode, void* stream) {
+    return conv3d_dispatch(in, wp, out, N, Cin, Cout, Di, Hi, Wi, stride, mode, 0, stream, stat_partial, nullptr, false,
+                           addend, nullptr);
 }

@@ -58,14 +58,20 @@ def _convbn_3d(cfg, cin, cout, k=3, stride=1, pad=1):
     return nn.Sequential(nn.Conv3d(cin, cout, k, stride, pad, bias=False), _gn(cfg, cout))
 
 
-def run_convbn_3d(seq, x, relu=False, res=None):
+def run_convbn_3d(seq, x, relu=False, res=None, fork=False):
     """conv3d/deconv3d -> GroupNorm (+res) (+ReLU) through the sm_100a kernels.
-    ``seq`` = Sequential(Conv3d | ConvTranspose3d, GroupNorm) used as parameter holder."""
+    ``seq`` = Sequential(Conv3d | ConvTranspose3d, GroupNorm) used as parameter holder.
+    ``fork``: x has other consumers too; returns (y, x2) and those consumers must read x2 -- their
+    gradient is then added inside this conv's data-gradient kernel (``ops.conv3d_fork``)."""
     conv, norm = seq[0], seq[1]
     transposed = isinstance(conv, nn.ConvTranspose3d)
     # the conv epilogue adds up the GroupNorm statistics of its own output where the kernel supports it
-    y, part = ops.conv3d_with_stats(x, conv.weight, stride=conv.stride[0], transposed=transposed)
-    return ops.groupnorm_act(y, norm.weight, norm.bias, norm.num_groups, norm.eps, relu=relu, res=res, partial=part)
+    if fork:
+        y, part, x2 = ops.conv3d_fork(x, conv.weight, stride=conv.stride[0], transposed=transposed)
+    else:
+        y, part = ops.conv3d_with_stats(x, conv.weight, stride=conv.stride[0], transposed=transposed)
+    y = ops.groupnorm_act(y, norm.weight, norm.bias, norm.num_groups, norm.eps, relu=relu, res=res, partial=part)
+    return (y, x2) if fork else y
 
 
 # Stock 2-D convolutions (cuDNN).  'tf32' = PyTorch's default on this hardware; 'tf32x3' = the same
@@ -260,12 +266,16 @@ class Hourglass3d(nn.Module):
             nn.ConvTranspose3d(2 * c, c, 3, 2, 1, output_padding=1, bias=False), _gn(cfg, c))
 
     def forward(self, x, res):
-        """returns conv6(...) + res (the caller's residual fused into the last norm)."""
-        out = run_convbn_3d(self.conv1[0], x, relu=True)
+        """returns conv6(...) + res (the caller's residual fused into the last norm).
+        x and pre each feed a conv AND a residual: the conv forks its input so that the residual's
+        gradient is added inside the conv's data-gradient kernel (no separate accumulation pass)."""
+        out, x2 = run_convbn_3d(self.conv1[0], x, relu=True, fork=True)
+        if res is x:
+            res = x2
         pre = run_convbn_3d(self.conv2, out, relu=True)
-        out = run_convbn_3d(self.conv3[0], pre, relu=True)
+        out, pre2 = run_convbn_3d(self.conv3[0], pre, relu=True, fork=True)
         out = run_convbn_3d(self.conv4[0], out, relu=True)
-        post = run_convbn_3d(self.conv5, out, relu=True, res=pre)
+        post = run_convbn_3d(self.conv5, out, relu=True, res=pre2)
         return run_convbn_3d(self.conv6, post, relu=False, res=res)
 
 
@@ -380,10 +390,10 @@ class StereoNet(nn.Module):
         cost = ops.build_cost_volume(featL, featR, shifts, channels_last=True)
         x = run_convbn_3d(self.dres0[0], cost, relu=True)
         cost0 = run_convbn_3d(self.dres0[2], x, relu=True)
-        x = run_convbn_3d(self.dres1[0], cost0, relu=True)
+        x, cost0 = run_convbn_3d(self.dres1[0], cost0, relu=True, fork=True)     # cost0 also feeds the residual
         cost0 = run_convbn_3d(self.dres1[2], x, relu=False, res=cost0)
         out = self.hg(cost0, res=cost0)
-        x = run_convbn_3d(self.classif1[0], out, relu=True)
+        x, out = run_convbn_3d(self.classif1[0], out, relu=True, fork=True)      # out also feeds the lifting
         cost1 = ops.conv3d_c1(x, self.classif1[2].weight)
         return cost, out, cost1
 

@@ -361,11 +361,27 @@ def _cache_put(key, weight, packed):
 
 
 FUSE_GN_STATS = os.environ.get("B2_FUSE_GN_STATS", "1") != "0"
+FUSE_GRAD_ADD = os.environ.get("B2_FUSE_GRAD_ADD", "1") != "0"
+_CAPS = {}
 
 
-def _conv_call(x, wp, stride, mode, impl, stats=False):
+def _conv_caps(n, cin, cout, di, hi, wi, stride, mode):
+    """(rows of the statistics table or 0, fused addend available) for the kernel serving this shape."""
+    key = (n, cin, cout, di, hi, wi, stride, mode)
+    hit = _CAPS.get(key)
+    if hit is None:
+        rows, aok = ctypes.c_int(0), ctypes.c_int(0)
+        check(_lib.load().b2_conv3d_fusion_caps(n, cin, cout, di, hi, wi, stride, mode, ctypes.byref(rows),
+                                                ctypes.byref(aok)), "conv3d_fusion_caps")
+        hit = _CAPS[key] = (rows.value, bool(aok.value))
+    return hit
+
+
+def _conv_call(x, wp, stride, mode, impl, stats=False, addend=None):
     """``stats``: also return the conv epilogue's GroupNorm partial sums of the output
-    ([rows, 2, Cout]) or None when this launch configuration cannot produce them."""
+    ([rows, 2, Cout]) or None when this launch configuration cannot produce them.
+    ``addend``: tensor of the output's shape added to the result -- in the epilogue where the kernel
+    can (no extra pass), by a separate add otherwise."""
     lib = _lib.load()
     n, cin, di, hi, wi = x.shape
     cout = wp.shape[1]
@@ -378,16 +394,24 @@ def _conv_call(x, wp, stride, mode, impl, stats=False):
     # algorithmic flops: 2*Cin*Cout*27 per output voxel for CONV; a transposed conv touches
     # 27/8 taps per output voxel on average (= 2*Cin*Cout*27 per INPUT voxel)
     vox = n * do * ho * wo if mode == 0 else n * di * hi * wi
-    rows = lib.b2_conv3d_stat_rows(n, cin, cout, di, hi, wi, stride, mode) if (stats and impl == 0 and FUSE_GN_STATS) else 0
+    rows, aok = _conv_caps(n, cin, cout, di, hi, wi, stride, mode) if impl == 0 else (0, False)
+    rows = rows if (stats and FUSE_GN_STATS) else 0
+    fused_add = addend is not None and aok and FUSE_GRAD_ADD
+    if fused_add:
+        addend = cl3(addend)
+        assert addend.shape == out.shape, (addend.shape, out.shape)
     part = None
     with _op("conv3d_tcgen05" if impl == 0 else "conv3d_simt", 1, 2 * cin * cout * 27 * vox):
-        if rows > 0:
-            part = torch.empty((rows, 2, cout), device=x.device, dtype=torch.float32)
-            check(lib.b2_conv3d_stats(_p(x), _p(wp), _p(out), _p(part), n, cin, cout, di, hi, wi, stride, mode,
-                                      _stream()), "conv3d_stats(mode=%d,stride=%d)" % (mode, stride))
+        if rows > 0 or fused_add:
+            part = torch.empty((rows, 2, cout), device=x.device, dtype=torch.float32) if rows > 0 else None
+            check(lib.b2_conv3d_fused(_p(x), _p(wp), _p(out), _p(addend) if fused_add else None, _p(part), n, cin, cout,
+                                      di, hi, wi, stride, mode, _stream()),
+                  "conv3d_fused(mode=%d,stride=%d)" % (mode, stride))
         else:
             check(lib.b2_conv3d(_p(x), _p(wp), _p(out), n, cin, cout, di, hi, wi, stride, mode, impl, _stream()),
                   "conv3d(mode=%d,stride=%d,impl=%d)" % (mode, stride, impl))
+    if addend is not None and not fused_add:
+        out = out + addend
     return (out, part) if stats else out
 
 
@@ -397,7 +421,7 @@ class Conv3dFn(Function):
     data gradient.  Weights are frozen in an attack: no weight gradient."""
 
     @staticmethod
-    def forward(ctx, x, weight, stride, transposed, impl, stats=False):
+    def forward(ctx, x, weight, stride, transposed, impl, stats=False, fork=False):
         _need_cuda(x, weight)
         if weight.requires_grad:
             raise RuntimeError("attack path: weights are frozen; call requires_grad_(False) on the model "
@@ -414,30 +438,41 @@ class Conv3dFn(Function):
         else:
             out = _conv_call(x, _packed(weight, "conv_fwd"), stride, 0, impl, stats)
         ctx.weight, ctx.cfg = weight, (stride, transposed, impl)
+        ctx.layout = (bool(stats), bool(fork))
+        ctx.set_materialize_grads(False)              # an unused output's gradient stays None (no zero volumes)
+        res = []
         if stats:
             out, part = out
             if part is None:
                 part = out.new_empty(0)               # "no statistics": autograd outputs must be tensors
             ctx.mark_non_differentiable(part)
-            return out, part
-        return out
+            res.append(part)
+        if fork:
+            # second handle on the input for its OTHER consumers: their gradient comes back to this
+            # node, and the data-gradient kernel adds it in its epilogue instead of autograd's add pass
+            res.append(x.view_as(x))
+        return (out, *res) if res else out
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, gout, *_unused):
+    def backward(ctx, gout, *extra):
         stride, transposed, impl = ctx.cfg
+        stats, fork = ctx.layout
+        g_other = extra[int(stats)] if fork else None          # gradient of the forked input handle
+        if gout is None:                                       # only the forked handle was used downstream
+            return g_other, None, None, None, None, None, None
         g = cl3(gout)
         if transposed:
-            gin = _conv_call(g, _packed(ctx.weight, "deconv_dgrad"), 2, 0, impl)
+            gin = _conv_call(g, _packed(ctx.weight, "deconv_dgrad"), 2, 0, impl, addend=g_other)
         elif stride == 1:
-            gin = _conv_call(g, _packed(ctx.weight, "conv_dgrad_s1"), 1, 0, impl)
+            gin = _conv_call(g, _packed(ctx.weight, "conv_dgrad_s1"), 1, 0, impl, addend=g_other)
         else:
-            gin = _conv_call(g, _packed(ctx.weight, "conv_dgrad_s2"), 2, 1, impl)
-        return gin, None, None, None, None, None
+            gin = _conv_call(g, _packed(ctx.weight, "conv_dgrad_s2"), 2, 1, impl, addend=g_other)
+        return gin, None, None, None, None, None, None
 
 
 def conv3d(x, weight, stride=1, transposed=False, impl=None):
-    return Conv3dFn.apply(x, weight, stride, transposed, impl, False)
+    return Conv3dFn.apply(x, weight, stride, transposed, impl, False, False)
 
 
 def conv3d_with_stats(x, weight, stride=1, transposed=False, impl=None):
@@ -445,8 +480,18 @@ def conv3d_with_stats(x, weight, stride=1, transposed=False, impl=None):
     (y, partial): ``partial`` [rows, 2, Cout] goes to ``groupnorm_act(..., partial=)``; it is None
     when the kernel that serves this shape has no statistics epilogue (GroupNorm then runs its own
     statistics pass)."""
-    y, part = Conv3dFn.apply(x, weight, stride, transposed, impl, True)
+    y, part = Conv3dFn.apply(x, weight, stride, transposed, impl, True, False)
     return y, (part if part.numel() else None)
+
+
+def conv3d_fork(x, weight, stride=1, transposed=False, impl=None):
+    """For an input with SEVERAL consumers.  Returns (y, partial, x2): y, partial as
+    ``conv3d_with_stats``; x2 is the same data as x and must be what every other consumer of x reads.
+    In the backward the gradient those consumers send to x2 arrives at this node and is added by the
+    data-gradient kernel's epilogue (out = dgrad + other) -- autograd's separate accumulation pass
+    (two reads and a write of the full volume) disappears."""
+    y, part, x2 = Conv3dFn.apply(x, weight, stride, transposed, impl, True, True)
+    return y, (part if part.numel() else None), x2
 
 
 class Conv3dC1Fn(Function):

@@ -162,15 +162,20 @@ int b2_grid_sample_bwd(const float* gout, const int32_t* row_ptr, const void* en
 int b2_conv3d(const float* in, const float* wp, float* out, int N, int Cin, int Cout,
               int Di, int Hi, int Wi, int stride, int mode, int impl, void* stream);
 
-/* conv3d (impl 0) whose epilogue ALSO produces the GroupNorm statistics of its output (upstream
- * convbn_3d = conv + norm): every CTA adds sum and sum of squares per channel of the voxels it
- * writes, in a fixed order, into its row of stat_partial [rows][2][Cout]; b2_groupnorm_fwd_ext
- * then skips its own statistics pass (one full read of the volume).  rows =
- * b2_conv3d_stat_rows(...), which is 0 when the launch configuration cannot do it (N != 1,
- * stride-2 CONV, widths that are not multiples of 32): call b2_conv3d instead. */
-int b2_conv3d_stat_rows(int N, int Cin, int Cout, int Di, int Hi, int Wi, int stride, int mode);
-int b2_conv3d_stats(const float* in, const float* wp, float* out, float* stat_partial, int N, int Cin,
-                    int Cout, int Di, int Hi, int Wi, int stride, int mode, void* stream);
+/* conv3d (impl 0) with a fused epilogue; both extras are optional (NULL = off):
+ *   addend       [same shape as out]: out = conv(in) + addend -- the other gradient that autograd
+ *                would add to a data gradient in a separate full pass (a tensor with two consumers);
+ *   stat_partial [rows][2][Cout]: the GroupNorm statistics of the written output (upstream
+ *                convbn_3d = conv + norm): every CTA adds sum and sum of squares per channel of the
+ *                voxels it writes, in a fixed order, into its row; b2_groupnorm_fwd_ext then skips
+ *                its own statistics pass (one full read of the volume).
+ * b2_conv3d_fusion_caps reports what the kernel serving this shape can do: *stat_rows = rows of
+ * the table (0: not available -- N != 1, stride-2 CONV, widths that are not multiples of 32),
+ * *addend_ok = 1/0 (stride-1 CONV and DECONV kernels). */
+int b2_conv3d_fusion_caps(int N, int Cin, int Cout, int Di, int Hi, int Wi, int stride, int mode,
+                          int* stat_rows, int* addend_ok);
+int b2_conv3d_fused(const float* in, const float* wp, float* out, const float* addend, float* stat_partial,
+                    int N, int Cin, int Cout, int Di, int Hi, int Wi, int stride, int mode, void* stream);
 
 /* Cout == 1 head (classif1's last layer) and its data gradient: bandwidth-bound,
  * SIMT.  w1 [27][Cin].  fwd: in [N,D,H,W,Cin] -> out [N,D,H,W];
@@ -195,7 +200,7 @@ int64_t b2_groupnorm_workspace_bytes(int N, int C);
 int b2_groupnorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,
                      float* y, float* stats, int N, int C, int64_t S, int G, float eps,
                      int relu, void* workspace, void* stream);
-/* forward with the per-channel partial sums supplied by the producer (b2_conv3d_stats):
+/* forward with the per-channel partial sums supplied by the producer (b2_conv3d_fused):
  * ext_partial [ext_rows][2][C] (sum, sum of squares), N == 1. */
 int b2_groupnorm_fwd_ext(const float* x, const float* res, const float* gamma, const float* beta,
                          float* y, float* stats, int N, int C, int64_t S, int G, float eps,

@@ -105,6 +105,34 @@ def test_conv_epilogue_groupnorm_statistics(ops, n, cin, cout, stride, transpose
     assert torch.equal(part, part2)                                  # fixed summation order
 
 
+@pytest.mark.parametrize("cin,cout,stride,transposed,sp", [
+    (64, 64, 1, False, (12, 24, 40)),        # dgrad = stride-1 kernel, fused add
+    (64, 96, 1, False, (5, 7, 9)),           # dgrad has Nt = 32 from 64 channels; ragged tiles
+    (64, 128, 2, False, (12, 24, 40)),       # dgrad = class-stacked transposed kernel, fused add
+    (128, 64, 2, True, (6, 12, 20)),         # dgrad = stride-2 conv (generic kernel): separate add
+])
+def test_conv3d_fork_adds_the_other_gradient_in_the_epilogue(ops, cin, cout, stride, transposed, sp):
+    """x feeds a conv and a second consumer: with conv3d_fork the second consumer's gradient is added by
+    the data-gradient kernel (out = acc + addend), bit-identical to autograd's separate accumulation."""
+    g = torch.Generator().manual_seed(cin + cout + sp[2])
+    x = _cl3((1, cin) + sp, g).requires_grad_(True)
+    wshape = (cin, cout, 3, 3, 3) if transposed else (cout, cin, 3, 3, 3)
+    w = (torch.randn(wshape, generator=g) * (27 * cin) ** -0.5).cuda()
+    y0 = ops.conv3d(x, w, stride=stride, transposed=transposed)
+    gy, gr = _cl3(tuple(y0.shape), g), _cl3(tuple(x.shape), g)
+    (ref,) = torch.autograd.grad((y0 * gy).sum() + (x * gr).sum(), x)
+    y, part, x2 = ops.conv3d_fork(x, w, stride=stride, transposed=transposed)
+    assert torch.equal(y, y0) and x2.data_ptr() == x.data_ptr()
+    (got,) = torch.autograd.grad((y * gy).sum() + (x2 * gr).sum(), x)
+    assert torch.equal(got, ref)
+    # either output alone
+    (g1,) = torch.autograd.grad((ops.conv3d_fork(x, w, stride=stride, transposed=transposed)[2] * gr).sum(), x)
+    assert torch.equal(g1, gr)
+    (g2,) = torch.autograd.grad((ops.conv3d_fork(x, w, stride=stride, transposed=transposed)[0] * gy).sum(), x)
+    (g2r,) = torch.autograd.grad((ops.conv3d(x, w, stride=stride, transposed=transposed) * gy).sum(), x)
+    assert torch.equal(g2, g2r)
+
+
 def test_conv3d_c1_adjoint_at_kitti_size(ops):
     g = torch.Generator().manual_seed(5)
     x = _cl3((1, 64, 48, 96, 312), g).requires_grad_(True)
