@@ -41,8 +41,8 @@ SIGNATURES = {
     "b2_conv3d": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_int, c_vp]),
     "b2_conv3d_fusion_caps": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
-    "b2_conv3d_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                                c_int, c_vp]),
+    "b2_conv3d_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_int, c_int, c_vp]),
     "b2_conv3d_c1_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
     "b2_conv3d_c1_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "b2_conv3d_c1_dgrad": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),
@@ -53,6 +53,8 @@ SIGNATURES = {
                                      c_f32, c_int, c_vp, c_int, c_vp, c_vp]),
     "b2_groupnorm_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64,
                                  c_int, c_int, c_vp, c_vp]),
+    "b2_groupnorm_bwd_ext": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_i64,
+                                     c_int, c_int, c_vp, c_int, c_vp, c_vp]),
     "b2_bev_pool_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "b2_bev_pool_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "b2_depth_head_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),

@@ -38,6 +38,18 @@ inline int stream_grid(int64_t work_items, int per_block, int max_waves_blocks =
     return (int)need;
 }
 
+// What the epilogue of the stride-1 / transposed kernels can do besides writing the tile.
+struct EpiFusion {
+    const float* addend;      // out = acc + addend (nullptr: off)
+    float* stat_partial;      // per-CTA partial sums [grid][2][Cout] (nullptr: off)
+    int stat_mode;            // 1: GroupNorm FORWARD statistics of the written output v: (sum v, sum v^2)
+                              // 2: GroupNorm BACKWARD sums of the norm that produced this conv's input, v being
+                              //    the gradient w.r.t. that norm's output: (sum v*x, sum v)
+                              // 3: as 2 with that norm's ReLU mask recomputed: v counts where fmaf(x, scale_c, shift_c) > 0
+    const float* gn_x;        // modes 2, 3: the norm's input x, same shape as out
+    const float* gn_coef;     // mode 3: the norm's forward scale[Cout], shift[Cout]
+};
+
 __device__ __forceinline__ float4 ldg_stream(const float4* p) { return __ldcs(p); }
 __device__ __forceinline__ void stg_stream(float4* p, float4 v) { __stcs(p, v); }
 

@@ -139,20 +139,91 @@ __device__ __forceinline__ void warp_transpose_sum32(float (&v)[32], int lane) {
     }
 }
 
-// out = accumulator + addend (the other gradient that autograd would add in a separate pass):
-// NQ float4 of the addend row are loaded first, then added to the drained accumulator registers.
-template <int NQ>
-__device__ __forceinline__ void epilogue_add(uint32_t* rr, const float* __restrict__ arow) {
-    float4 a[NQ];
+constexpr int kEpiMaxC = 128;              // widest norm whose scale / shift the epilogue keeps in smem (stat_mode 3)
+constexpr int kEpiStageBytes = 1024;       // per epilogue warp: hand-over of the statistics totals at kernel end
+
+// Row access of the epilogue: lane = voxel row (how tcgen05.ld delivers a tile), 32 channels = 128 B
+// contiguous per lane.  (A warp-transposed variant through smem -- 8 lanes per 128 B segment, 4 full
+// lines per instruction -- was measured SLOWER: plain launches unchanged, fused-operand launches
+// +50 %; the epilogue is bound by the dependent-load latency of each step, not by LSU wavefronts.)
+// ptr_of(r) -> pointer to the 32-channel segment of warp row r (0..31), nullptr when the row is outside the volume
+template <typename PtrFn>
+__device__ __forceinline__ void epi_store32(float4*, int lane, const uint32_t (&rr)[32], PtrFn ptr_of) {
+    float* gp = ptr_of(lane);
+    if (!gp) return;
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) a[q] = __ldg(reinterpret_cast<const float4*>(arow) + q);
+    for (int q = 0; q < 8; ++q)
+        *reinterpret_cast<float4*>(gp + 4 * q) = make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
+                                                             __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
+}
+
+template <typename PtrFn>
+__device__ __forceinline__ void epi_load32(float4*, int lane, float (&xv)[32], PtrFn ptr_of) {
+    const float* gp = ptr_of(lane);
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        rr[4 * q] = __float_as_uint(__uint_as_float(rr[4 * q]) + a[q].x);
-        rr[4 * q + 1] = __float_as_uint(__uint_as_float(rr[4 * q + 1]) + a[q].y);
-        rr[4 * q + 2] = __float_as_uint(__uint_as_float(rr[4 * q + 2]) + a[q].z);
-        rr[4 * q + 3] = __float_as_uint(__uint_as_float(rr[4 * q + 3]) + a[q].w);
+    for (int q = 0; q < 8; ++q) {
+        const float4 t = gp ? __ldg(reinterpret_cast<const float4*>(gp) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        xv[4 * q] = t.x; xv[4 * q + 1] = t.y; xv[4 * q + 2] = t.z; xv[4 * q + 3] = t.w;
     }
+}
+
+// One 32-channel chunk of one tile row set: fused addend, statistics, store.
+// off_of(r) -> element offset of warp row r's segment (negative when the row is outside); ok = this lane's row is inside.
+template <typename OffFn>
+__device__ __forceinline__ void epi_chunk32(const EpiFusion& ef, float* __restrict__ out, uint32_t (&rr)[32], float4* stage,
+                                            int lane, bool ok, OffFn off_of, float (&s0)[32], float (&s1)[32], int cbase,
+                                            const float* coef_sh) {
+    const long long myoff = off_of(lane);
+    float av[32], xv[32];
+    // both operand rows are requested up front (16 independent 16-byte loads in flight per lane)
+    if (ef.addend) epi_load32(stage, lane, av, [&](int) { return myoff < 0 ? (const float*)nullptr : ef.addend + myoff; });
+    if (ef.stat_mode >= 2) epi_load32(stage, lane, xv, [&](int) { return myoff < 0 ? (const float*)nullptr : ef.gn_x + myoff; });
+    if (ef.addend) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rr[i] = __float_as_uint(__uint_as_float(rr[i]) + av[i]);
+    }
+    if (ef.stat_mode == 1) {
+        if (ok) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float v = __uint_as_float(rr[i]);
+                s0[i] += v;
+                s1[i] = fmaf(v, v, s1[i]);
+            }
+        }
+    } else if (ef.stat_mode >= 2) {
+        if (ok) {
+            const bool mask = ef.stat_mode == 3;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float v = __uint_as_float(rr[i]);
+                if (mask && !(fmaf(xv[i], coef_sh[cbase + i], coef_sh[kEpiMaxC + cbase + i]) > 0.f)) v = 0.f;
+                s0[i] = fmaf(v, xv[i], s0[i]);
+                s1[i] += v;
+            }
+        }
+    }
+    epi_store32(stage, lane, rr, [&](int r) { const long long o = off_of(r); return o < 0 ? (float*)nullptr : out + o; });
+}
+
+// 16-channel tail (Nt = 16 or 48): direct per-row access, addend only (no statistics)
+__device__ __forceinline__ void epi_tail16(const EpiFusion& ef, float* __restrict__ out, uint32_t (&rr)[16], bool ok, long long off) {
+    if (!ok) return;
+    if (ef.addend) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float4 a = __ldg(reinterpret_cast<const float4*>(ef.addend + off) + q);
+            rr[4 * q] = __float_as_uint(__uint_as_float(rr[4 * q]) + a.x);
+            rr[4 * q + 1] = __float_as_uint(__uint_as_float(rr[4 * q + 1]) + a.y);
+            rr[4 * q + 2] = __float_as_uint(__uint_as_float(rr[4 * q + 2]) + a.z);
+            rr[4 * q + 3] = __float_as_uint(__uint_as_float(rr[4 * q + 3]) + a.w);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<float4*>(out + off + 4 * q) =
+            make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]), __uint_as_float(rr[4 * q + 2]),
+                        __uint_as_float(rr[4 * q + 3]));
 }
 
 // Per-lane running totals of one epilogue warp: slot = n_tile * 2 + (32-channel chunk), lane = channel
@@ -172,8 +243,9 @@ struct StatTotals {
 
 // After the CTA-wide barrier: one warp adds the four epilogue warps' totals in a fixed order and writes
 // this CTA's row of the partial-sum table [gridDim.x][2][Cout] (sum, sum of squares per channel).
-__device__ __forceinline__ void stat_store_row(const float (*sh)[8][32], float* __restrict__ stat_partial, int Cout,
+__device__ __forceinline__ void stat_store_row(const float* shp, float* __restrict__ stat_partial, int Cout,
                                                int nt, int n_tiles, int lane) {
+    const float (*sh)[8][32] = reinterpret_cast<const float (*)[8][32]>(shp);
     float* row = stat_partial + (long long)blockIdx.x * 2 * Cout;
     for (int nti = 0; nti < n_tiles; ++nti)
         for (int ch = 0; ch < nt / 32; ++ch) {
@@ -642,16 +714,24 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                          float* __restrict__ out, const S1Params p, float* __restrict__ stat_partial,
-                          const float* __restrict__ addend) {
+                          float* __restrict__ out, const S1Params p, const EpiFusion ef) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kS1NA + 2 * kS1MaxNB + 4];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float stat_sh[4][8][32];          // [epilogue warp][sum slots 0..3, square slots 4..7][lane]
+    __shared__ float coef_sh[2 * kEpiMaxC];      // stat_mode 3: forward scale / shift of the preceding norm
+    float* __restrict__ stat_partial = ef.stat_partial;
+    if (ef.stat_mode == 3)
+        for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+            coef_sh[i] = ef.gn_coef[i];
+            coef_sh[kEpiMaxC + i] = ef.gn_coef[p.Cout + i];
+        }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t a_base = smem_base, b_base = smem_base + kS1NA * kS1ABytes;
+    // epilogue staging (4 warps x 2 KB) behind the rings; reused for the statistics hand-over at the end
+    float* const stage_all = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + kS1NA * kS1ABytes +
+                                                      p.nb * p.b_bytes);
     const uint32_t bar0 = smem_u32(bars);
     auto fullA = [&](int s) { return bar0 + 8u * s; };
     auto emptyA = [&](int s) { return bar0 + 8u * (kS1NA + s); };
@@ -766,6 +846,7 @@ conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
         mbar_arrive(tempty(0));
         mbar_arrive(tempty(1));
         const bool stats = stat_partial != nullptr;       // fused GroupNorm statistics of the output
+        float4* const stage = reinterpret_cast<float4*>(stage_all + lane_grp * (kEpiStageBytes / 4));
         StatTotals tot;
         tot.clear();
         long long it = 0;
@@ -776,10 +857,14 @@ conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             const bool ok_hw = r < p.R && w < p.W;
             mbar_wait(tfull(accbuf), (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            auto row_off = [&](int j) {
-                const int pl = tc.d0 + j;
-                const int d = p.swap ? r : pl, h = p.swap ? pl : r;
-                return ((((long long)tc.n * p.D + d) * p.H + h) * p.W + w) * p.Cout + tc.nti * p.nt;
+            const long long tile_off = (long long)tc.n * p.D * p.H * p.W * p.Cout + tc.nti * p.nt;
+            // element offset of warp row rw (0..31) of plane j, or -1 outside the volume
+            auto off_of = [&](int rw, int j) -> long long {
+                const int m2 = lane_grp * 32 + rw;
+                const int r2 = tc.h0 + (m2 >> 3), w2 = tc.w0 + (m2 & 7), pl = tc.d0 + j;
+                if (r2 >= p.R || w2 >= p.W || pl >= p.P) return -1;
+                const int d = p.swap ? r2 : pl, h = p.swap ? pl : r2;
+                return tile_off + (((long long)d * p.H + h) * p.W + w2) * p.Cout;
             };
             int c0 = 0;
             for (; c0 + 32 <= p.nt; c0 += 32) {           // 32-channel chunk outer, the 4 planes inner
@@ -789,29 +874,14 @@ conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
 #pragma unroll 1
                 for (int j = 0; j < kS1Planes; ++j) {
                     const bool ok = ok_hw && tc.d0 + j < p.P;
-                    const long long off = row_off(j);
-                    float* orow = out + off;
                     const uint32_t taddr = lane_addr + (uint32_t)((accbuf * kS1Planes + j) * p.nt);
                     uint32_t rr[32];
                     tmem_ld32(taddr + c0, rr);
                     tmem_ld_wait();
                     tmem_st32_zero(taddr + c0);
-                    if (ok) {
-                        if (addend) epilogue_add<8>(rr, addend + off + c0);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *reinterpret_cast<float4*>(orow + c0 + 4 * q) =
-                                make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
-                                            __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
-                        if (stats) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float v = __uint_as_float(rr[i]);
-                                ssum[i] += v;
-                                ssq[i] = fmaf(v, v, ssq[i]);
-                            }
-                        }
-                    }
+                    epi_chunk32(ef, out, rr, stage, lane, ok,
+                                [&](int rw) { const long long o = off_of(rw, j); return o < 0 ? o : o + c0; },
+                                ssum, ssq, tc.nti * p.nt + c0, coef_sh);
                 }
                 if (stats) {
                     warp_transpose_sum32(ssum, lane);
@@ -822,36 +892,30 @@ conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
             if (c0 < p.nt) {                               // 16-channel tail (Nt = 16 or 48; no statistics)
                 for (int j = 0; j < kS1Planes; ++j) {
                     const bool ok = ok_hw && tc.d0 + j < p.P;
-                    const long long off = row_off(j);
-                    float* orow = out + off;
                     const uint32_t taddr = lane_addr + (uint32_t)((accbuf * kS1Planes + j) * p.nt);
                     uint32_t rr[16];
                     tmem_ld16(taddr + c0, rr);
                     tmem_ld_wait();
                     tmem_st16_zero(taddr + c0);
-                    if (ok) {
-                        if (addend) epilogue_add<4>(rr, addend + off + c0);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<float4*>(orow + c0 + 4 * q) =
-                                make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
-                                            __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
-                    }
+                    epi_tail16(ef, out, rr, ok, off_of(lane, j) + c0);
                 }
             }
             tmem_st_wait();
             tc_fence_before();
             mbar_arrive(tempty(accbuf));
         }
-        if (stats) {
+        if (stats) {                                       // [warp][sum slots 0..3, second-sum slots 4..7][lane]
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { stat_sh[lane_grp][i][lane] = tot.s[i]; stat_sh[lane_grp][4 + i][lane] = tot.q[i]; }
+            for (int i = 0; i < 4; ++i) {
+                stage_all[(lane_grp * 8 + i) * 32 + lane] = tot.s[i];
+                stage_all[(lane_grp * 8 + 4 + i) * 32 + lane] = tot.q[i];
+            }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (stat_partial != nullptr && warp == 2) stat_store_row(stat_sh, stat_partial, p.Cout, p.nt, p.n_tiles, lane);
+    if (stat_partial != nullptr && warp == 2) stat_store_row(stage_all, stat_partial, p.Cout, p.nt, p.n_tiles, lane);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -862,8 +926,10 @@ conv3d_s1n_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
 // [grid][2][Cout]; *stat_rows (if given) receives the number of rows (= grid), 0 when this launch
 // configuration cannot produce them.  query = only compute *stat_rows, launch nothing.
 static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* wp, float* out, int N, int Cin,
-                            int Cout, int D, int H, int W, cudaStream_t st, float* stat_partial, int* stat_rows,
-                            bool query, const float* addend, int* addend_ok) {
+                            int Cout, int D, int H, int W, cudaStream_t st, const EpiFusion& ef, int* stat_rows,
+                            bool query, int* addend_ok) {
+    const float* addend = ef.addend;
+    float* stat_partial = ef.stat_partial;
     S1Params p{};
     p.N = N; p.Cin = Cin; p.Cout = Cout; p.D = D; p.H = H; p.W = W;
     p.nt = Cout <= 64 ? Cout : Cout / 2;
@@ -899,6 +965,7 @@ static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* 
     if (query) return 0;
     if (stat_partial && !stats_ok) { set_error("conv3d(tcgen05,s1): statistics not available for this shape"); return B2_ERR_UNSUPPORTED; }
     if (addend && !use_nstack) { set_error("conv3d(tcgen05,s1): fused addend not available for this shape"); return B2_ERR_UNSUPPORTED; }
+    if (ef.stat_mode == 3 && Cout > kEpiMaxC) { set_error("conv3d(tcgen05,s1): stat_mode 3 needs Cout <= %d", kEpiMaxC); return B2_ERR_UNSUPPORTED; }
 
     CUtensorMap map_a, map_b;
     {
@@ -926,7 +993,7 @@ static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* 
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3d(tcgen05,s1): cuTensorMapEncodeTiled(B) failed: %d", (int)r); return B2_ERR_DRIVER; }
     }
-    const int smem = kS1NA * kS1ABytes + p.nb * p.b_bytes + 1024;
+    const int smem = kS1NA * kS1ABytes + p.nb * p.b_bytes + 4 * kEpiStageBytes + 1024;
     static int attr_smem = 0;
     if (smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(conv3d_s1_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -936,7 +1003,7 @@ static int conv3d_s1_launch(EncodeTiledFn encode, const float* in, const float* 
         attr_smem = smem;
     }
     if (use_nstack)
-        conv3d_s1n_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p, stat_partial, addend);
+        conv3d_s1n_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p, ef);
     else
         conv3d_s1_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p);
     return check_launch("conv3d(tcgen05,s1)");
@@ -994,16 +1061,23 @@ __device__ __forceinline__ DcUnit dc_decode(const DcParams& p, long long t) {
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                         float* __restrict__ out, const DcParams p, float* __restrict__ stat_partial,
-                         const float* __restrict__ addend) {
+                         float* __restrict__ out, const DcParams p, const EpiFusion ef) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[2 * kDcMaxStages + 4];
     __shared__ uint32_t tmem_base_slot;
-    __shared__ float stat_sh[4][8][32];          // [epilogue warp][sum slots 0..3, square slots 4..7][lane]
+    __shared__ float coef_sh[2 * kEpiMaxC];      // stat_mode 3: forward scale / shift of the preceding norm
+    float* __restrict__ stat_partial = ef.stat_partial;
+    if (ef.stat_mode == 3)
+        for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+            coef_sh[i] = ef.gn_coef[i];
+            coef_sh[kEpiMaxC + i] = ef.gn_coef[p.Cout + i];
+        }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar0 = smem_u32(bars);
+    // epilogue staging (4 warps x 2 KB) behind the pipeline stages; reused for the statistics hand-over
+    float* const stage_all = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * p.stage_bytes);
     auto full_bar = [&](int s) { return bar0 + 8u * s; };
     auto empty_bar = [&](int s) { return bar0 + 8u * (kDcMaxStages + s); };
     auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kDcMaxStages + a); };
@@ -1125,6 +1199,7 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
         const int hl = m / kTileW, wl = m % kTileW;
         const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
         const bool stats = stat_partial != nullptr;       // fused GroupNorm statistics of the output
+        float4* const stage = reinterpret_cast<float4*>(stage_all + lane_grp * (kEpiStageBytes / 4));
         StatTotals tot;
         tot.clear();
         long long it = 0;
@@ -1136,10 +1211,15 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             const int op = 2 * u.d + u.pd;
             mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
             tc_fence_after();
-            auto row_off = [&](int c) {
-                const int orow = 2 * h + (c >> 1), ow = 2 * w + (c & 1);
+            const long long unit_off = (long long)u.n * p.Do * p.Ho * p.Wo * p.Cout + u.nti * p.nt;
+            // element offset of warp row rw (0..31) of parity class c, or -1 outside the volume
+            auto off_of = [&](int rw, int c) -> long long {
+                const int m2 = lane_grp * 32 + rw;
+                const int h2 = u.h0 + (m2 >> 3), w2 = u.w0 + (m2 & 7);
+                if (h2 >= p.Rt || w2 >= p.Wt) return -1;
+                const int orow = 2 * h2 + (c >> 1), ow = 2 * w2 + (c & 1);
                 const int od = p.swap ? orow : op, oh = p.swap ? op : orow;
-                return ((((long long)u.n * p.Do + od) * p.Ho + oh) * p.Wo + ow) * p.Cout + u.nti * p.nt;
+                return unit_off + (((long long)od * p.Ho + oh) * p.Wo + ow) * p.Cout;
             };
             int c0 = 0;
             for (; c0 + 32 <= p.nt; c0 += 32) {           // 32-channel chunk outer, the 4 parity classes inner
@@ -1148,28 +1228,13 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
                 for (int i = 0; i < 32; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
 #pragma unroll 1
                 for (int c = 0; c < 4; ++c) {
-                    const long long off = row_off(c);
-                    float* optr = out + off;
                     const uint32_t taddr = lane_addr + (uint32_t)((acc * 4 + c) * p.nt);
                     uint32_t rr[32];
                     tmem_ld32(taddr + c0, rr);
                     tmem_ld_wait();
-                    if (ok) {
-                        if (addend) epilogue_add<8>(rr, addend + off + c0);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            *reinterpret_cast<float4*>(optr + c0 + 4 * q) =
-                                make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
-                                            __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
-                        if (stats) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) {
-                                const float v = __uint_as_float(rr[i]);
-                                ssum[i] += v;
-                                ssq[i] = fmaf(v, v, ssq[i]);
-                            }
-                        }
-                    }
+                    epi_chunk32(ef, out, rr, stage, lane, ok,
+                                [&](int rw) { const long long o = off_of(rw, c); return o < 0 ? o : o + c0; },
+                                ssum, ssq, u.nti * p.nt + c0, coef_sh);
                 }
                 if (stats) {
                     warp_transpose_sum32(ssum, lane);
@@ -1179,34 +1244,28 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
             }
             if (c0 < p.nt) {                               // 16-channel tail (no statistics)
                 for (int c = 0; c < 4; ++c) {
-                    const long long off = row_off(c);
-                    float* optr = out + off;
                     const uint32_t taddr = lane_addr + (uint32_t)((acc * 4 + c) * p.nt);
                     uint32_t rr[16];
                     tmem_ld16(taddr + c0, rr);
                     tmem_ld_wait();
-                    if (ok) {
-                        if (addend) epilogue_add<4>(rr, addend + off + c0);
-#pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            *reinterpret_cast<float4*>(optr + c0 + 4 * q) =
-                                make_float4(__uint_as_float(rr[4 * q]), __uint_as_float(rr[4 * q + 1]),
-                                            __uint_as_float(rr[4 * q + 2]), __uint_as_float(rr[4 * q + 3]));
-                    }
+                    epi_tail16(ef, out, rr, ok, off_of(lane, c) + c0);
                 }
             }
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
         }
-        if (stats) {
+        if (stats) {                                       // [warp][sum slots 0..3, second-sum slots 4..7][lane]
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { stat_sh[lane_grp][i][lane] = tot.s[i]; stat_sh[lane_grp][4 + i][lane] = tot.q[i]; }
+            for (int i = 0; i < 4; ++i) {
+                stage_all[(lane_grp * 8 + i) * 32 + lane] = tot.s[i];
+                stage_all[(lane_grp * 8 + 4 + i) * 32 + lane] = tot.q[i];
+            }
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (stat_partial != nullptr && warp == 2) stat_store_row(stat_sh, stat_partial, p.Cout, p.nt, p.n_tiles, lane);
+    if (stat_partial != nullptr && warp == 2) stat_store_row(stage_all, stat_partial, p.Cout, p.nt, p.n_tiles, lane);
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -1214,8 +1273,11 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 }
 
 static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* wp, float* out, int N, int Cin,
-                            int Cout, int Di, int Hi, int Wi, cudaStream_t st, float* stat_partial, int* stat_rows,
-                            bool query, const float* addend, int* addend_ok) {
+                            int Cout, int Di, int Hi, int Wi, cudaStream_t st, const EpiFusion& ef, int* stat_rows,
+                            bool query, int* addend_ok) {
+    const float* addend = ef.addend;
+    float* stat_partial = ef.stat_partial;
+    (void)addend;
     DcParams p{};
     p.N = N; p.Cin = Cin; p.Cout = Cout;
     p.Do = 2 * Di; p.Ho = 2 * Hi; p.Wo = 2 * Wi;
@@ -1245,6 +1307,7 @@ static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* 
     if (addend_ok) *addend_ok = 1;
     if (query) return 0;
     if (stat_partial && !stats_ok) { set_error("conv3d(tcgen05,deconv): statistics not available for this shape"); return B2_ERR_UNSUPPORTED; }
+    if (ef.stat_mode == 3 && Cout > kEpiMaxC) { set_error("conv3d(tcgen05,deconv): stat_mode 3 needs Cout <= %d", kEpiMaxC); return B2_ERR_UNSUPPORTED; }
 
     CUtensorMap map_a, map_b;
     {
@@ -1272,20 +1335,22 @@ static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* 
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv3d(tcgen05,deconv): cuTensorMapEncodeTiled(B) failed: %d", (int)r); return B2_ERR_DRIVER; }
     }
-    const int smem = p.stages * p.stage_bytes + 1024;
+    const int smem = p.stages * p.stage_bytes + 4 * kEpiStageBytes + 1024;
     static int attr_smem = 0;
     if (smem > attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(conv3d_dc_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) { set_error("conv3d(tcgen05,deconv): cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return (int)e; }
         attr_smem = smem;
     }
-    conv3d_dc_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p, stat_partial, addend);
+    conv3d_dc_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p, ef);
     return check_launch("conv3d(tcgen05,deconv)");
 }
 
 int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
                           int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st,
-                          float* stat_partial, int* stat_rows, bool query, const float* addend, int* addend_ok) {
+                          const EpiFusion& ef, int* stat_rows, bool query, int* addend_ok) {
+    const float* addend = ef.addend;
+    float* stat_partial = ef.stat_partial;
     if (stat_rows) *stat_rows = 0;
     if (addend_ok) *addend_ok = 0;
     if (Cin % 32 != 0 || Cout % 32 != 0 || Cout > 256 || Cout < 32) {
@@ -1303,14 +1368,12 @@ int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, i
         if (simple < 0) { const char* e = getenv("B2_CONV_S1_SIMPLE"); simple = (e && e[0] == '1') ? 1 : 0; }
         const int nt = Cout <= 64 ? Cout : Cout / 2;
         if (mode == 0 && stride == 1 && !simple && nt % 16 == 0)
-            return conv3d_s1_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st, stat_partial, stat_rows, query, addend,
-                                    addend_ok);
+            return conv3d_s1_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st, ef, stat_rows, query, addend_ok);
         // transposed convs take the class-stacked kernel; B2_CONV_DC_SIMPLE=1 forces the generic one
         static int dc_simple = -1;
         if (dc_simple < 0) { const char* e = getenv("B2_CONV_DC_SIMPLE"); dc_simple = (e && e[0] == '1') ? 1 : 0; }
         if (mode == 1 && !dc_simple && nt % 16 == 0 && 4 * nt <= 256)
-            return conv3d_dc_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st, stat_partial, stat_rows, query, addend,
-                                    addend_ok);
+            return conv3d_dc_launch(encode, in, wp, out, N, Cin, Cout, Di, Hi, Wi, st, ef, stat_rows, query, addend_ok);
     }
 
     if (query) return 0;                                   // the generic kernel has no statistics epilogue

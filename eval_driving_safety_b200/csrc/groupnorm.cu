@@ -318,27 +318,48 @@ extern "C" int b2_groupnorm_fwd_ext(const float* x, const float* res, const floa
     return groupnorm_fwd_impl(x, res, gamma, beta, y, stats, N, C, S, G, eps, relu, ext_partial, ext_rows, workspace, stream);
 }
 
-extern "C" int b2_groupnorm_bwd(const float* gy, const float* x, const float* y, const float* gamma,
-                                const float* stats, float* gx, float* gres, int N, int C, int64_t S,
-                                int G, int relu, void* workspace, void* stream) {
+static int groupnorm_bwd_impl(const float* gy, const float* x, const float* y, const float* gamma,
+                              const float* stats, float* gx, float* gres, int N, int C, int64_t S,
+                              int G, int relu, const float* ext_partial, int ext_rows, void* workspace, void* stream) {
     B2_REQUIRE(gy && x && gamma && stats && gx && workspace, "groupnorm_bwd: null pointer");
     B2_REQUIRE(relu != 1 || y, "groupnorm_bwd: relu == 1 needs the saved output y (relu == 2 recomputes the mask)");
     B2_REQUIRE(relu >= 0 && relu <= 2, "groupnorm_bwd: relu must be 0, 1 or 2");
     if (int e = gn_check("groupnorm_bwd", N, C, S, G)) return e;
     B2_REQUIRE(aligned16(gy) && aligned16(x) && aligned16(gx), "groupnorm_bwd: pointers must be 16B aligned");
+    B2_REQUIRE(!ext_partial || (N == 1 && ext_rows >= 1 && relu != 1),
+               "groupnorm_bwd: external partial sums need N == 1, >= 1 row and relu in {0, 2}");
     if (N == 0 || S == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     GnLayout l = gn_layout(C);
     float* partial = (float*)workspace;
     float* coef = partial + gn_partial_floats(N, C);
-    int nblocks = gn_nblocks(S);
-    gn_partials_kernel<1><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
-        (const float4*)gy, (const float4*)x, (const float4*)y, partial, C, S, l.lpr, l.rpb, relu,
-        stats, G);
-    gn_finalize_bwd<<<dim3(G, N), kGnFinThreads, 0, st>>>(partial, gamma, stats, coef, C, S, G, nblocks);
+    if (ext_partial) {
+        // (sum gz*x, sum gz) per channel already added up by the kernel that produced gy
+        gn_finalize_bwd<<<dim3(G, N), kGnFinThreads, 0, st>>>(ext_partial, gamma, stats, coef, C, S, G, ext_rows);
+    } else {
+        int nblocks = gn_nblocks(S);
+        gn_partials_kernel<1><<<dim3(nblocks, N), l.threads, 2 * l.rpb * l.lpr * sizeof(float4), st>>>(
+            (const float4*)gy, (const float4*)x, (const float4*)y, partial, C, S, l.lpr, l.rpb, relu,
+            stats, G);
+        gn_finalize_bwd<<<dim3(G, N), kGnFinThreads, 0, st>>>(partial, gamma, stats, coef, C, S, G, nblocks);
+    }
     int gxd = stream_grid(S * l.lpr, 256 * 4, kNumSMs * 8);
     gn_apply_bwd<<<dim3(gxd, N), 256, 5 * C * sizeof(float), st>>>((const float4*)gy, (const float4*)x,
                                                                    (const float4*)y, coef, (float4*)gx,
                                                                    (float4*)gres, C, S, relu, stats, G);
     return check_launch("groupnorm_bwd");
+}
+
+extern "C" int b2_groupnorm_bwd(const float* gy, const float* x, const float* y, const float* gamma,
+                                const float* stats, float* gx, float* gres, int N, int C, int64_t S,
+                                int G, int relu, void* workspace, void* stream) {
+    return groupnorm_bwd_impl(gy, x, y, gamma, stats, gx, gres, N, C, S, G, relu, nullptr, 0, workspace, stream);
+}
+
+extern "C" int b2_groupnorm_bwd_ext(const float* gy, const float* x, const float* y, const float* gamma,
+                                    const float* stats, float* gx, float* gres, int N, int C, int64_t S,
+                                    int G, int relu, const float* ext_partial, int ext_rows, void* workspace,
+                                    void* stream) {
+    B2_REQUIRE(ext_partial, "groupnorm_bwd_ext: null partial-sum table");
+    return groupnorm_bwd_impl(gy, x, y, gamma, stats, gx, gres, N, C, S, G, relu, ext_partial, ext_rows, workspace, stream);
 }

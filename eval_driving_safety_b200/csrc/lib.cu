@@ -18,7 +18,7 @@ int conv3d_simt_launch(const float* in, const float* wp, float* out, int N, int 
                        int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st);
 int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
                           int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st,
-                          float* stat_partial, int* stat_rows, bool query, const float* addend, int* addend_ok);
+                          const EpiFusion& ef, int* stat_rows, bool query, int* addend_ok);
 
 }  // namespace b2
 
@@ -27,8 +27,10 @@ extern "C" int b2_version(void) { return 100; }  // 0.1.0
 extern "C" const char* b2_last_error(void) { return b2::g_err; }
 
 static int conv3d_dispatch(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
-                           int Hi, int Wi, int stride, int mode, int impl, void* stream, float* stat_partial,
-                           int* stat_rows, bool query, const float* addend = nullptr, int* addend_ok = nullptr) {
+                           int Hi, int Wi, int stride, int mode, int impl, void* stream, const b2::EpiFusion& ef,
+                           int* stat_rows, bool query, int* addend_ok) {
+    const float* addend = ef.addend;
+    float* stat_partial = ef.stat_partial;
     B2_REQUIRE(query || (in && wp && out), "conv3d: null pointer");
     B2_REQUIRE(N >= 0 && Cin > 0 && Cout > 0 && Di > 0 && Hi > 0 && Wi > 0, "conv3d: bad dims");
     B2_REQUIRE(mode == 0 || mode == 1, "conv3d: mode must be 0 (CONV) or 1 (DECONV)");
@@ -51,21 +53,23 @@ static int conv3d_dispatch(const float* in, const float* wp, float* out, int N, 
     }
     if (impl == 0)
         return b2::conv3d_tcgen05_launch(in, wp, out, N, Cin, Cout, Di, Hi, Wi, Do, Ho, Wo, stride, mode, st,
-                                         stat_partial, stat_rows, query, addend, addend_ok);
+                                         ef, stat_rows, query, addend_ok);
     b2::set_error("conv3d: unknown impl %d", impl);
     return B2_ERR_BAD_ARG;
 }
 
 extern "C" int b2_conv3d(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
                          int Hi, int Wi, int stride, int mode, int impl, void* stream) {
-    return conv3d_dispatch(in, wp, out, N, Cin, Cout, Di, Hi, Wi, stride, mode, impl, stream, nullptr, nullptr, false);
+    const b2::EpiFusion none{nullptr, nullptr, 0, nullptr, nullptr};
+    return conv3d_dispatch(in, wp, out, N, Cin, Cout, Di, Hi, Wi, stride, mode, impl, stream, none, nullptr, false, nullptr);
 }
 
 extern "C" int b2_conv3d_fusion_caps(int N, int Cin, int Cout, int Di, int Hi, int Wi, int stride, int mode,
                                      int* stat_rows, int* addend_ok) {
     int rows = 0, aok = 0;
-    int rc = conv3d_dispatch(nullptr, nullptr, nullptr, N, Cin, Cout, Di, Hi, Wi, stride, mode, 0, nullptr, nullptr, &rows,
-                             true, nullptr, &aok);
+    const b2::EpiFusion none{nullptr, nullptr, 0, nullptr, nullptr};
+    int rc = conv3d_dispatch(nullptr, nullptr, nullptr, N, Cin, Cout, Di, Hi, Wi, stride, mode, 0, nullptr, none, &rows,
+                             true, &aok);
     if (rc != 0) { rows = 0; aok = 0; }
     if (stat_rows) *stat_rows = rows;
     if (addend_ok) *addend_ok = aok;
@@ -73,7 +77,12 @@ extern "C" int b2_conv3d_fusion_caps(int N, int Cin, int Cout, int Di, int Hi, i
 }
 
 extern "C" int b2_conv3d_fused(const float* in, const float* wp, float* out, const float* addend, float* stat_partial,
-                               int N, int Cin, int Cout, int Di, int Hi, int Wi, int stride, int mode, void* stream) {
-    return conv3d_dispatch(in, wp, out, N, Cin, Cout, Di, Hi, Wi, stride, mode, 0, stream, stat_partial, nullptr, false,
-                           addend, nullptr);
+                               int stat_mode, const float* gn_x, const float* gn_coef, int N, int Cin, int Cout,
+                               int Di, int Hi, int Wi, int stride, int mode, void* stream) {
+    B2_REQUIRE(stat_partial ? (stat_mode >= 1 && stat_mode <= 3) : stat_mode == 0,
+               "conv3d_fused: stat_mode must be 1..3 with a statistics table and 0 without");
+    B2_REQUIRE(stat_mode < 2 || gn_x, "conv3d_fused: stat_mode 2/3 needs gn_x");
+    B2_REQUIRE(stat_mode != 3 || (gn_coef && Cout <= 256), "conv3d_fused: stat_mode 3 needs gn_coef and Cout <= 256");
+    const b2::EpiFusion ef{addend, stat_partial, stat_mode, gn_x, gn_coef};
+    return conv3d_dispatch(in, wp, out, N, Cin, Cout, Di, Hi, Wi, stride, mode, 0, stream, ef, nullptr, false, nullptr);
 }

@@ -362,7 +362,22 @@ def _cache_put(key, weight, packed):
 
 FUSE_GN_STATS = os.environ.get("B2_FUSE_GN_STATS", "1") != "0"
 FUSE_GRAD_ADD = os.environ.get("B2_FUSE_GRAD_ADD", "1") != "0"
+FUSE_GN_BWD = os.environ.get("B2_FUSE_GN_BWD", "1") != "0"
+BSTAT_ON_DECONV = os.environ.get("B2_BSTAT_ON_DECONV", "0") == "1"
 _CAPS = {}
+
+
+class GnLink:
+    """Hand-off between a GroupNorm node and the conv that consumes its output.  The norm's forward
+    fills in what its backward statistics need (x, stats, activation mode); the conv's DATA-GRADIENT
+    launch -- which produces exactly the gradient w.r.t. the norm's output -- adds up the norm's
+    backward sums in its epilogue and leaves them here together with the identity of the gradient
+    tensor it wrote; the norm's backward uses them only if that very tensor, unmodified, arrives."""
+    __slots__ = ("x", "stats", "groups", "mode", "bwd_partial", "gy_key")
+
+    def __init__(self):
+        self.x = self.stats = self.bwd_partial = self.gy_key = None
+        self.groups = self.mode = 0
 
 
 def _conv_caps(n, cin, cout, di, hi, wi, stride, mode):
@@ -377,11 +392,13 @@ def _conv_caps(n, cin, cout, di, hi, wi, stride, mode):
     return hit
 
 
-def _conv_call(x, wp, stride, mode, impl, stats=False, addend=None):
+def _conv_call(x, wp, stride, mode, impl, stats=False, addend=None, bstat=None):
     """``stats``: also return the conv epilogue's GroupNorm partial sums of the output
     ([rows, 2, Cout]) or None when this launch configuration cannot produce them.
     ``addend``: tensor of the output's shape added to the result -- in the epilogue where the kernel
-    can (no extra pass), by a separate add otherwise."""
+    can (no extra pass), by a separate add otherwise.
+    ``bstat``: GnLink of the norm whose output gradient this launch computes; its backward sums are
+    added up in the epilogue when possible."""
     lib = _lib.load()
     n, cin, di, hi, wi = x.shape
     cout = wp.shape[1]
@@ -401,10 +418,28 @@ def _conv_call(x, wp, stride, mode, impl, stats=False, addend=None):
         addend = cl3(addend)
         assert addend.shape == out.shape, (addend.shape, out.shape)
     part = None
+    brows = 0
+    # (only on the stride-1 kernel: its 4-plane tiles take ~24 us of MMAs, which hides the epilogue's extra
+    # row reads; the transposed kernel's 3-6 us units do not -- measured 0.203 -> 0.344 ms, more than the
+    # 0.107 ms statistics pass it would replace.  tools/bench_epilogue.py)
+    if (bstat is not None and FUSE_GN_BWD and impl == 0 and not stats and bstat.mode in (0, 2)
+            and (mode == 0 and stride == 1 or BSTAT_ON_DECONV)
+            and (addend is None or fused_add) and bstat.x is not None and tuple(bstat.x.shape) == tuple(out.shape)):
+        brows = _conv_caps(n, cin, cout, di, hi, wi, stride, mode)[0]
     with _op("conv3d_tcgen05" if impl == 0 else "conv3d_simt", 1, 2 * cin * cout * 27 * vox):
-        if rows > 0 or fused_add:
+        if brows > 0:
+            bpart = torch.empty((brows, 2, cout), device=x.device, dtype=torch.float32)
+            coef = ctypes.c_void_p(bstat.stats.data_ptr() + 4 * 2 * bstat.groups) if bstat.mode == 2 else None
+            check(lib.b2_conv3d_fused(_p(x), _p(wp), _p(out), _p(addend) if fused_add else None, _p(bpart),
+                                      3 if bstat.mode == 2 else 2, _p(bstat.x), coef, n, cin, cout,
+                                      di, hi, wi, stride, mode, _stream()),
+                  "conv3d_fused(mode=%d,stride=%d,bstat)" % (mode, stride))
+            bstat.bwd_partial = bpart
+            bstat.gy_key = (out.data_ptr(), out._version, tuple(out.shape))
+        elif rows > 0 or fused_add:
             part = torch.empty((rows, 2, cout), device=x.device, dtype=torch.float32) if rows > 0 else None
-            check(lib.b2_conv3d_fused(_p(x), _p(wp), _p(out), _p(addend) if fused_add else None, _p(part), n, cin, cout,
+            check(lib.b2_conv3d_fused(_p(x), _p(wp), _p(out), _p(addend) if fused_add else None, _p(part),
+                                      1 if rows > 0 else 0, None, None, n, cin, cout,
                                       di, hi, wi, stride, mode, _stream()),
                   "conv3d_fused(mode=%d,stride=%d)" % (mode, stride))
         else:
@@ -421,8 +456,9 @@ class Conv3dFn(Function):
     data gradient.  Weights are frozen in an attack: no weight gradient."""
 
     @staticmethod
-    def forward(ctx, x, weight, stride, transposed, impl, stats=False, fork=False):
+    def forward(ctx, x, weight, stride, transposed, impl, stats=False, fork=False, gn_link=None):
         _need_cuda(x, weight)
+        ctx.gn_link = gn_link
         if weight.requires_grad:
             raise RuntimeError("attack path: weights are frozen; call requires_grad_(False) on the model "
                                "(the reference wastes its wgrad, attack/DSGN/pgd_attack.py:333)")
@@ -460,19 +496,20 @@ class Conv3dFn(Function):
         stats, fork = ctx.layout
         g_other = extra[int(stats)] if fork else None          # gradient of the forked input handle
         if gout is None:                                       # only the forked handle was used downstream
-            return g_other, None, None, None, None, None, None
+            return g_other, None, None, None, None, None, None, None
         g = cl3(gout)
+        link = ctx.gn_link
         if transposed:
-            gin = _conv_call(g, _packed(ctx.weight, "deconv_dgrad"), 2, 0, impl, addend=g_other)
+            gin = _conv_call(g, _packed(ctx.weight, "deconv_dgrad"), 2, 0, impl, addend=g_other, bstat=link)
         elif stride == 1:
-            gin = _conv_call(g, _packed(ctx.weight, "conv_dgrad_s1"), 1, 0, impl, addend=g_other)
+            gin = _conv_call(g, _packed(ctx.weight, "conv_dgrad_s1"), 1, 0, impl, addend=g_other, bstat=link)
         else:
-            gin = _conv_call(g, _packed(ctx.weight, "conv_dgrad_s2"), 2, 1, impl, addend=g_other)
-        return gin, None, None, None, None, None, None
+            gin = _conv_call(g, _packed(ctx.weight, "conv_dgrad_s2"), 2, 1, impl, addend=g_other, bstat=link)
+        return gin, None, None, None, None, None, None, None
 
 
 def conv3d(x, weight, stride=1, transposed=False, impl=None):
-    return Conv3dFn.apply(x, weight, stride, transposed, impl, False, False)
+    return Conv3dFn.apply(x, weight, stride, transposed, impl, False, False, getattr(x, "_b2_gn", None))
 
 
 def conv3d_with_stats(x, weight, stride=1, transposed=False, impl=None):
@@ -480,7 +517,7 @@ def conv3d_with_stats(x, weight, stride=1, transposed=False, impl=None):
     (y, partial): ``partial`` [rows, 2, Cout] goes to ``groupnorm_act(..., partial=)``; it is None
     when the kernel that serves this shape has no statistics epilogue (GroupNorm then runs its own
     statistics pass)."""
-    y, part = Conv3dFn.apply(x, weight, stride, transposed, impl, True, False)
+    y, part = Conv3dFn.apply(x, weight, stride, transposed, impl, True, False, getattr(x, "_b2_gn", None))
     return y, (part if part.numel() else None)
 
 
@@ -490,7 +527,7 @@ def conv3d_fork(x, weight, stride=1, transposed=False, impl=None):
     In the backward the gradient those consumers send to x2 arrives at this node and is added by the
     data-gradient kernel's epilogue (out = dgrad + other) -- autograd's separate accumulation pass
     (two reads and a write of the full volume) disappears."""
-    y, part, x2 = Conv3dFn.apply(x, weight, stride, transposed, impl, True, True)
+    y, part, x2 = Conv3dFn.apply(x, weight, stride, transposed, impl, True, True, getattr(x, "_b2_gn", None))
     return y, (part if part.numel() else None), x2
 
 
@@ -557,7 +594,7 @@ class GroupNormActFn(Function):
     """y = act(GroupNorm(x) (+ res)) on channels-last 3-D volumes or 2-D maps; data gradient only."""
 
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, groups, eps, relu, partial=None):
+    def forward(ctx, x, res, gamma, beta, groups, eps, relu, partial=None, link=None):
         _need_cuda(x, res, gamma, beta)
         lib = _lib.load()
         x = _cl(x)
@@ -583,6 +620,10 @@ class GroupNormActFn(Function):
         keep_y = relu and res is not None
         ctx.save_for_backward(x, y if keep_y else None, gamma, stats)
         ctx.cfg = (groups, relu, res is not None)
+        ctx.link = link
+        if link is not None:
+            link.x, link.stats, link.groups = x, stats, groups
+            link.mode = 0 if not relu else (1 if res is not None else 2)
         return y
 
     @staticmethod
@@ -598,18 +639,38 @@ class GroupNormActFn(Function):
         gres = _empty_cl_like(x) if (has_res and relu) else None
         ws = _workspace(lib.b2_groupnorm_workspace_bytes(n, c), x.device)
         mode = 0 if not relu else (1 if has_res else 2)
-        with _op("groupnorm_bwd", 3, 4 * x.numel() * (5 + 2 * int(mode == 1) + (gres is not None))):
-            check(lib.b2_groupnorm_bwd(_p(gy), _p(x), _p(y), _p(gamma), _p(stats), _p(gx), _p(gres), n, c, s, groups,
-                                       mode, _p(ws), _stream()), "groupnorm_bwd")
+        ext = None
+        link = ctx.link
+        if link is not None and link.bwd_partial is not None:
+            # the conv that consumed y added up (sum gz*x, sum gz) while writing gy: valid only if that
+            # very tensor arrives here untouched (no other consumer's gradient was accumulated into it)
+            if link.gy_key == (gy.data_ptr(), gy._version, tuple(gy.shape)) and mode != 1:
+                ext = link.bwd_partial
+            link.bwd_partial = link.gy_key = None
+        if ext is not None:
+            with _op("groupnorm_bwd", 2, 4 * x.numel() * (3 + (gres is not None))):
+                check(lib.b2_groupnorm_bwd_ext(_p(gy), _p(x), _p(y), _p(gamma), _p(stats), _p(gx), _p(gres), n, c, s,
+                                               groups, mode, _p(ext), ext.shape[0], _p(ws), _stream()),
+                      "groupnorm_bwd_ext")
+        else:
+            with _op("groupnorm_bwd", 3, 4 * x.numel() * (5 + 2 * int(mode == 1) + (gres is not None))):
+                check(lib.b2_groupnorm_bwd(_p(gy), _p(x), _p(y), _p(gamma), _p(stats), _p(gx), _p(gres), n, c, s,
+                                           groups, mode, _p(ws), _stream()), "groupnorm_bwd")
         if has_res and not relu:
             gres = gy
-        return gx, gres, None, None, None, None, None, None
+        return gx, gres, None, None, None, None, None, None, None
 
 
 def groupnorm_act(x, gamma, beta, groups, eps=1e-5, relu=False, res=None, partial=None):
     """``partial``: per-channel partial sums of x from the producing conv's epilogue
-    (``conv3d_with_stats``); the statistics pass over x is skipped."""
-    return GroupNormActFn.apply(x, res, gamma, beta, groups, eps, relu, partial)
+    (``conv3d_with_stats``); the statistics pass over x is skipped.
+    A single-sample 3-D output carries a ``GnLink`` so that a conv consuming it can add up this
+    norm's backward sums while it writes the gradient (see ``GnLink``)."""
+    link = GnLink() if (x.dim() == 5 and x.shape[0] == 1 and FUSE_GN_BWD) else None
+    y = GroupNormActFn.apply(x, res, gamma, beta, groups, eps, relu, partial, link)
+    if link is not None:
+        y._b2_gn = link
+    return y
 
 
 class BevPoolFn(Function):

@@ -162,20 +162,27 @@ int b2_grid_sample_bwd(const float* gout, const int32_t* row_ptr, const void* en
 int b2_conv3d(const float* in, const float* wp, float* out, int N, int Cin, int Cout,
               int Di, int Hi, int Wi, int stride, int mode, int impl, void* stream);
 
-/* conv3d (impl 0) with a fused epilogue; both extras are optional (NULL = off):
+/* conv3d (impl 0) with a fused epilogue; every extra is optional (NULL / 0 = off):
  *   addend       [same shape as out]: out = conv(in) + addend -- the other gradient that autograd
  *                would add to a data gradient in a separate full pass (a tensor with two consumers);
- *   stat_partial [rows][2][Cout]: the GroupNorm statistics of the written output (upstream
- *                convbn_3d = conv + norm): every CTA adds sum and sum of squares per channel of the
- *                voxels it writes, in a fixed order, into its row; b2_groupnorm_fwd_ext then skips
- *                its own statistics pass (one full read of the volume).
+ *   stat_partial [rows][2][Cout] + stat_mode: per-channel sums over the voxels each CTA writes, in a
+ *                fixed order, one table row per CTA, v = the written value (after the addend):
+ *       1  GroupNorm FORWARD statistics of this conv's output (upstream convbn_3d = conv + norm):
+ *          (sum v, sum v^2); b2_groupnorm_fwd_ext then skips its statistics pass;
+ *       2  GroupNorm BACKWARD sums of the norm that produced this conv's INPUT in the forward, when
+ *          this launch is that conv's data gradient (v = gradient w.r.t. the norm's output, gn_x =
+ *          the norm's input, same shape as out): (sum v*x, sum v); b2_groupnorm_bwd_ext then skips
+ *          its statistics pass (a read of gy and of x);
+ *       3  as 2 for a norm followed by ReLU: v counts only where fmaf(x, scale_c, shift_c) > 0,
+ *          gn_coef = that norm's forward scale[Cout], shift[Cout] (the tail of its stats row).
  * b2_conv3d_fusion_caps reports what the kernel serving this shape can do: *stat_rows = rows of
  * the table (0: not available -- N != 1, stride-2 CONV, widths that are not multiples of 32),
  * *addend_ok = 1/0 (stride-1 CONV and DECONV kernels). */
 int b2_conv3d_fusion_caps(int N, int Cin, int Cout, int Di, int Hi, int Wi, int stride, int mode,
                           int* stat_rows, int* addend_ok);
 int b2_conv3d_fused(const float* in, const float* wp, float* out, const float* addend, float* stat_partial,
-                    int N, int Cin, int Cout, int Di, int Hi, int Wi, int stride, int mode, void* stream);
+                    int stat_mode, const float* gn_x, const float* gn_coef, int N, int Cin, int Cout,
+                    int Di, int Hi, int Wi, int stride, int mode, void* stream);
 
 /* Cout == 1 head (classif1's last layer) and its data gradient: bandwidth-bound,
  * SIMT.  w1 [27][Cin].  fwd: in [N,D,H,W,Cin] -> out [N,D,H,W];
@@ -209,6 +216,12 @@ int b2_groupnorm_fwd_ext(const float* x, const float* res, const float* gamma, c
 int b2_groupnorm_bwd(const float* gy, const float* x, const float* y, const float* gamma,
                      const float* stats, float* gx, float* gres, int N, int C, int64_t S, int G,
                      int relu, void* workspace, void* stream);
+/* backward with (sum gz*x, sum gz) per channel supplied by the kernel that produced gy
+ * (b2_conv3d_fused stat_mode 2 / 3): ext_partial [ext_rows][2][C], N == 1, relu 0 or 2. */
+int b2_groupnorm_bwd_ext(const float* gy, const float* x, const float* y, const float* gamma,
+                         const float* stats, float* gx, float* gres, int N, int C, int64_t S, int G,
+                         int relu, const float* ext_partial, int ext_rows, void* workspace,
+                         void* stream);
 
 /* Voxel -> BEV hand-off: AvgPool3d((1,p,1)) over the height axis + fold (C, Y/p) into channels
  * (upstream StereoNet, behind attack/DSGN/pgd_attack.py:308/:336).  v [N,Z,Y,X,C] channels-last ->

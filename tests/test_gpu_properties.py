@@ -133,6 +133,51 @@ def test_conv3d_fork_adds_the_other_gradient_in_the_epilogue(ops, cin, cout, str
     assert torch.equal(g2, g2r)
 
 
+@pytest.mark.parametrize("relu,with_res,second_consumer,sp,c", [
+    (True, False, False, (12, 24, 40), 64),     # norm+ReLU -> conv: mask recomputed in the conv epilogue
+    (False, True, False, (12, 24, 40), 64),     # norm + residual, no activation
+    (True, False, True, (5, 7, 9), 64),         # the norm's output also feeds a second consumer through the fork
+    (True, False, False, (6, 10, 12), 128),     # two N tiles
+    (True, True, False, (6, 10, 12), 64),       # ReLU + residual needs the saved output: not fused, still right
+])
+def test_groupnorm_backward_sums_from_the_consuming_convs_dgrad(ops, relu, with_res, second_consumer, sp, c):
+    """conv_a -> GroupNorm -> conv_b: conv_b's data-gradient launch adds up the norm's backward sums
+    (sum gz*x, sum gz) in its epilogue; the input gradient equals the unfused path."""
+    g = torch.Generator().manual_seed(sp[0] * 7 + c)
+    x = _cl3((1, c) + sp, g).requires_grad_(True)
+    wa = (torch.randn(c, c, 3, 3, 3, generator=g) * (27 * c) ** -0.5).cuda()
+    wb = (torch.randn(c, c, 3, 3, 3, generator=g) * (27 * c) ** -0.5).cuda()
+    gamma = (torch.rand(c, generator=g) + 0.5).cuda()
+    beta = (torch.randn(c, generator=g) * 0.3).cuda()
+    res = _cl3((1, c) + sp, g) if with_res else None
+    gy, g2 = _cl3((1, c) + sp, g), _cl3((1, c) + sp, g)
+
+    def run(fuse):
+        old = ops.FUSE_GN_BWD
+        ops.FUSE_GN_BWD = fuse
+        try:
+            n0 = ops.LAUNCH_COUNT
+            ya = ops.conv3d(x, wa)
+            h = ops.groupnorm_act(ya, gamma, beta, 32, 1e-5, relu=relu, res=res)
+            if second_consumer:
+                yb, _, h2 = ops.conv3d_fork(h, wb)
+                loss = (yb * gy).sum() + (h2 * g2).sum()
+            else:
+                loss = (ops.conv3d(h, wb) * gy).sum()
+            (gx,) = torch.autograd.grad(loss, x)
+            return gx, ops.LAUNCH_COUNT - n0
+        finally:
+            ops.FUSE_GN_BWD = old
+
+    ref, n_ref = run(False)
+    got, n_got = run(True)
+    fusable = not (relu and with_res)
+    assert n_got == n_ref - (1 if fusable else 0)          # the norm's backward statistics launch is gone
+    assert (got - ref).abs().max().item() < 2e-5 * ref.abs().max().item() + 1e-7
+    got2, _ = run(True)
+    assert torch.equal(got, got2)                          # reproducible
+
+
 def test_conv3d_c1_adjoint_at_kitti_size(ops):
     g = torch.Generator().manual_seed(5)
     x = _cl3((1, 64, 48, 96, 312), g).requires_grad_(True)
