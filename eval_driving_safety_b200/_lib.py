@@ -57,10 +57,11 @@ SIGNATURES = {
                                      c_int, c_int, c_vp, c_int, c_vp, c_vp]),
     "b2_bev_pool_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "b2_bev_pool_bwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
-    "b2_depth_head_fwd": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_f32, c_vp]),
+    "b2_depth_head_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_f32,
+                                  c_vp]),
     "b2_depth_head_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
-    "b2_depth_head_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32, c_f32,
-                                  c_vp, c_vp]),
+    "b2_depth_head_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32,
+                                  c_f32, c_vp, c_vp]),
     "b2_roi_align_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),
     "b2_roi_align_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),
 }

@@ -40,17 +40,21 @@ __device__ __forceinline__ float dh_col(const float* __restrict__ cn, int d, con
 template <int MODE>
 __global__ void __launch_bounds__(256)
 depth_head_pixel_kernel(const float* __restrict__ cost, const float* __restrict__ gdepth,
-                        float* __restrict__ depth, float* __restrict__ G, DhGeom g) {
+                        float* __restrict__ depth, float* __restrict__ G, DhGeom g,
+                        float2* __restrict__ sm_out, const float2* __restrict__ sm_in,
+                        const float* __restrict__ depth_in) {
     const int64_t total = (int64_t)g.N * g.H * g.W;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         const int x = (int)(i % g.W), y = (int)((i / g.W) % g.H), n = (int)(i / ((int64_t)g.W * g.H));
         const Lerp ly = lerp_src(y, g.sh, g.Hc), lx = lerp_src(x, g.sw, g.Wc);
         const float* cn = cost + (int64_t)n * g.D * g.Hc * g.Wc;
-        // pass A: running max / sum / weighted sum
+        // pass A: running max / sum / weighted sum (skipped in the backward when the forward saved them)
         float m = -INFINITY, s = 0.f, t = 0.f;
         int cur = -1; float c0 = 0.f, c1 = 0.f;
-        for (int j = 0; j < g.J; ++j) {
+        const bool saved = MODE == 1 && sm_in != nullptr;
+        if (saved) { const float2 ms = __ldg(sm_in + i); m = ms.x; s = ms.y; }
+        for (int j = 0; !saved && j < g.J; ++j) {
             const Lerp ld = lerp_src(j, g.sd, g.D);
             if (ld.i0 != cur) {
                 c0 = (ld.i0 == cur + 1 && cur >= 0) ? c1 : dh_col(cn, ld.i0, ly, lx, g.Hc, g.Wc);
@@ -63,8 +67,12 @@ depth_head_pixel_kernel(const float* __restrict__ cost, const float* __restrict_
             const float e = __expf(v - m);
             s += e; t += e * z;
         }
-        const float dep = t / s;
-        if (MODE == 0) { depth[i] = dep; continue; }
+        const float dep = saved ? __ldg(depth_in + i) : t / s;
+        if (MODE == 0) {
+            depth[i] = dep;
+            if (sm_out) sm_out[i] = make_float2(m, s);
+            continue;
+        }
         // pass B: g_up[j] = g * p_j * (z_j - depth); accumulate onto the two source planes
         const float go = __ldg(gdepth + i) / s;
         float* Gp = G + (int64_t)n * g.D * g.H * g.W + (int64_t)y * g.W + x;
@@ -143,14 +151,14 @@ static DhGeom dh_geom(int N, int D, int Hc, int Wc, int H, int W, int J, float z
 
 using namespace b2;
 
-extern "C" int b2_depth_head_fwd(const float* cost, float* depth, int N, int D, int Hc, int Wc, int H, int W,
-                                 int J, float z0, float dz, void* stream) {
+extern "C" int b2_depth_head_fwd(const float* cost, float* depth, float* sm_stats, int N, int D, int Hc, int Wc,
+                                 int H, int W, int J, float z0, float dz, void* stream) {
     B2_REQUIRE(cost && depth, "depth_head_fwd: null pointer");
     B2_REQUIRE(D >= 1 && Hc >= 1 && Wc >= 1 && H >= Hc && W >= Wc && J >= D, "depth_head_fwd: upsampling only");
     int64_t total = (int64_t)N * H * W;
     if (total == 0) return 0;
     depth_head_pixel_kernel<0><<<stream_grid(total, 256, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(
-        cost, nullptr, depth, nullptr, dh_geom(N, D, Hc, Wc, H, W, J, z0, dz));
+        cost, nullptr, depth, nullptr, dh_geom(N, D, Hc, Wc, H, W, J, z0, dz), (float2*)sm_stats, nullptr, nullptr);
     return check_launch("depth_head_fwd");
 }
 
@@ -158,16 +166,18 @@ extern "C" int64_t b2_depth_head_workspace_bytes(int N, int D, int H, int W) {
     return (int64_t)N * D * H * W * (int64_t)sizeof(float);
 }
 
-extern "C" int b2_depth_head_bwd(const float* cost, const float* gdepth, float* gcost, int N, int D, int Hc,
-                                 int Wc, int H, int W, int J, float z0, float dz, void* workspace, void* stream) {
+extern "C" int b2_depth_head_bwd(const float* cost, const float* gdepth, float* gcost, const float* sm_stats,
+                                 const float* depth, int N, int D, int Hc, int Wc, int H, int W, int J, float z0,
+                                 float dz, void* workspace, void* stream) {
     B2_REQUIRE(cost && gdepth && gcost && workspace, "depth_head_bwd: null pointer");
+    B2_REQUIRE(!sm_stats == !depth, "depth_head_bwd: sm_stats and depth (both saved by the forward) go together");
     B2_REQUIRE(D >= 1 && Hc >= 1 && Wc >= 1 && H >= Hc && W >= Wc && J >= D, "depth_head_bwd: upsampling only");
     int64_t total = (int64_t)N * H * W;
     if (total == 0) return 0;
     DhGeom g = dh_geom(N, D, Hc, Wc, H, W, J, z0, dz);
     cudaStream_t st = (cudaStream_t)stream;
-    depth_head_pixel_kernel<1><<<stream_grid(total, 256, kNumSMs * 16), 256, 0, st>>>(cost, gdepth, nullptr,
-                                                                                      (float*)workspace, g);
+    depth_head_pixel_kernel<1><<<stream_grid(total, 256, kNumSMs * 16), 256, 0, st>>>(
+        cost, gdepth, nullptr, (float*)workspace, g, nullptr, (const float2*)sm_stats, depth);
     int64_t cells = (int64_t)N * D * Hc * Wc;
     depth_head_gather_kernel<<<stream_grid(cells, 256, kNumSMs * 16), 256, 0, st>>>((const float*)workspace, gcost, g);
     return check_launch("depth_head_bwd");

@@ -716,10 +716,12 @@ class DepthHeadFn(Function):
         n, _, d, hc, wc = cost1.shape
         j, h, w = size
         depth = torch.empty((n, h, w), device=cost1.device, dtype=torch.float32)
+        # softmax (max, sum) per pixel, kept for the backward (which then skips its own softmax pass)
+        sm = torch.empty((n, h, w, 2), device=cost1.device, dtype=torch.float32) if ctx.needs_input_grad[0] else None
         with _op("depth_head_fwd", 1, 4 * (cost1.numel() + depth.numel())):
-            check(lib.b2_depth_head_fwd(_p(cost1), _p(depth), n, d, hc, wc, h, w, j, float(z0), float(dz), _stream()),
-                  "depth_head_fwd")
-        ctx.save_for_backward(cost1)
+            check(lib.b2_depth_head_fwd(_p(cost1), _p(depth), _p(sm), n, d, hc, wc, h, w, j, float(z0), float(dz),
+                                        _stream()), "depth_head_fwd")
+        ctx.save_for_backward(cost1, sm, depth if sm is not None else None)
         ctx.cfg = (n, d, hc, wc, h, w, j, float(z0), float(dz))
         return depth
 
@@ -727,14 +729,14 @@ class DepthHeadFn(Function):
     @once_differentiable
     def backward(ctx, gdepth):
         lib = _lib.load()
-        (cost1,) = ctx.saved_tensors
+        cost1, sm, depth = ctx.saved_tensors
         n, d, hc, wc, h, w, j, z0, dz = ctx.cfg
         g = gdepth.contiguous()
         gcost = torch.empty_like(cost1)
         ws = torch.empty(lib.b2_depth_head_workspace_bytes(n, d, h, w), device=g.device, dtype=torch.uint8)
         with _op("depth_head_bwd", 2, 4 * (cost1.numel() * 2 + g.numel()) + 2 * ws.numel()):
-            check(lib.b2_depth_head_bwd(_p(cost1), _p(g), _p(gcost), n, d, hc, wc, h, w, j, z0, dz, _p(ws), _stream()),
-                  "depth_head_bwd")
+            check(lib.b2_depth_head_bwd(_p(cost1), _p(g), _p(gcost), _p(sm), _p(depth), n, d, hc, wc, h, w, j, z0, dz,
+                                        _p(ws), _stream()), "depth_head_bwd")
         return gcost, None, None, None
 
 

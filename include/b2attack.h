@@ -234,12 +234,16 @@ int b2_bev_pool_bwd(const float* gbev, float* gv, int N, int C, int Z, int Y, in
  * softmax over the J planes, expectation over z_j = z0 + (j+0.5)*dz  ->  depth [N,H,W].
  * Replaces F.interpolate + F.softmax + (prob*z).sum of upstream StereoNet, whose output is read
  * at attack/DSGN/pgd_attack.py:310-317.  bwd: gdepth [N,H,W] -> gcost [N,D,Hc,Wc];
- * workspace b2_depth_head_workspace_bytes(N,D,H,W) bytes. */
-int b2_depth_head_fwd(const float* cost, float* depth, int N, int D, int Hc, int Wc, int H, int W,
-                      int J, float z0, float dz, void* stream);
+ * workspace b2_depth_head_workspace_bytes(N,D,H,W) bytes.
+ * sm_stats [N,H,W,2] (optional, NULL = off): the forward saves the softmax (max, sum) per pixel and
+ * the backward, given them and the forward's depth, skips its own softmax pass (same values, so
+ * the gradient is bit-identical either way). */
+int b2_depth_head_fwd(const float* cost, float* depth, float* sm_stats, int N, int D, int Hc, int Wc,
+                      int H, int W, int J, float z0, float dz, void* stream);
 int64_t b2_depth_head_workspace_bytes(int N, int D, int H, int W);
-int b2_depth_head_bwd(const float* cost, const float* gdepth, float* gcost, int N, int D, int Hc, int Wc,
-                      int H, int W, int J, float z0, float dz, void* workspace, void* stream);
+int b2_depth_head_bwd(const float* cost, const float* gdepth, float* gcost, const float* sm_stats,
+                      const float* depth, int N, int D, int Hc, int Wc, int H, int W, int J, float z0,
+                      float dz, void* workspace, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * RoIAlign forward / deterministic backward (Stereo R-CNN, config 5) -- replaces
