@@ -256,7 +256,13 @@ def run_b200(args):
         "gpu_launches": launches,
         "roofline": {"kernel": "conv3d_tcgen05_kernel (all 3x3x3 conv/deconv fwd+dgrad launches of the timed region)",
                      "bound": "tensor", "achieved": conv["per_s"] / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",
-                     "frac": conv["per_s"] / 1e12 / tf32_peak if tf32_peak else None, "traffic": None,
+                     "frac": conv["per_s"] / 1e12 / tf32_peak if tf32_peak else None,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the dominant shape (64->64 at
+                     # 48x96x312, algorithmic 736 MB) from the committed ncu --set full capture; `achieved` averages
+                     # all conv launches of the step, whose shapes differ
+                     "traffic": 709.2e6,
+                     "traffic_source": "profiles/r1_conv3d_final_ncu.txt (conv3d_s1n_tcgen05_kernel, 64->64 48x96x312: "
+                                       "389.3 MB read + 319.8 MB written vs 736 MB algorithmic)",
                      "peak_source": "%s bf16_tflops_sustained/2 (TF32 rate; kernel timed inside a long step)" % peaks["source"],
                      "frac_of_bf16_peak": conv["per_s"] / 1e12 / peaks["bf16_tflops_sustained"],
                      "launches": conv["calls"], "avg_launch_ms": conv["ms"] / max(conv["calls"], 1),
