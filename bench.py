@@ -266,6 +266,9 @@ def run_b200(args):
                      "peak_source": "%s bf16_tflops_sustained/2 (TF32 rate; kernel timed inside a long step)" % peaks["source"],
                      "frac_of_bf16_peak": conv["per_s"] / 1e12 / peaks["bf16_tflops_sustained"],
                      "launches": conv["calls"], "avg_launch_ms": conv["ms"] / max(conv["calls"], 1),
+                     "note": "conv flops only: about a third of the launches also add up GroupNorm statistics / backward "
+                             "sums or a second gradient in their epilogue (work of other kernels, not counted here); "
+                             "B2_FUSE_GN_STATS=0 B2_FUSE_GRAD_ADD=0 B2_FUSE_GN_BWD=0 gives the plain-conv figure (607-612)",
                      "share_of_step": (conv["ms"] / prof_pairs) / (ms / (args.steps * PAIRS_PER_GPU)) if ms else None,
                      "measured_in": "eager pass of %d pair-iterations right after the timed region, CUDA event pair "
                                     "around every launch on the launching stream (events cannot bracket kernels "
