@@ -19,24 +19,17 @@ import random
 import numpy as np
 import torch
 
-from . import attack, dsgn, engine, parallel, synthetic
+from . import attack, dsgn, engine, kitti_io, parallel, synthetic
 
 
-def tensor2im(img_norm):
-    """attack/DSGN/pgd_attack.py:157-178: [3,H,W] normalised tensor -> HxWx3 uint8 (truncation)."""
-    a = img_norm.detach().cpu().float().numpy().copy()
-    for i in range(3):
-        a[i] = a[i] * attack.IMAGENET_STD[i] + attack.IMAGENET_MEAN[i]
-    a = a * 255
-    return np.transpose(a, (1, 2, 0)).astype(np.uint8)
+tensor2im = kitti_io.tensor2im        # attack/DSGN/pgd_attack.py:157-178 (truncating uint8 cast)
 
 
 def save_pair(save_dir, k, index, imgL, imgR, w, h):
-    from PIL import Image
-    for sub, img in (("image_2", imgL), ("image_3", imgR)):
-        d = os.path.join(save_dir, "dsgn_pgd_iters_%d" % k, sub)
-        os.makedirs(d, exist_ok=True)
-        Image.fromarray(tensor2im(img[0])).crop((0, 0, w, h)).save(os.path.join(d, "%06d.png" % index))
+    """Per-iteration hand-off images, attack/DSGN/pgd_attack.py:357-374."""
+    for path, img in zip(kitti_io.iteration_paths(save_dir, k, index), (imgL, imgR)):
+        os.makedirs(os.path.dirname(path), exist_ok=True)
+        kitti_io.save_image(img[0], path, w, h)
 
 
 def _setup(args):

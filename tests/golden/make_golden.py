@@ -147,7 +147,46 @@ def roi_levels():
     return {"roi_levels": dict(rois=rois, levels=env["roi_level"])}
 
 
+def handoff():
+    """Hand-off formats, by executing the reference's own lines:
+    tensor2im attack/DSGN/pgd_attack.py:153-178, detection line attack/DSGN/predict_and_save_pgd.py:273-283."""
+    import io
+    import json
+    ns = {"np": np, "torch": torch}
+    exec(ref_lines("attack/DSGN/pgd_attack.py", 153, 154), ns)
+    exec(ref_lines("attack/DSGN/pgd_attack.py", 157, 178), ns)
+    g = torch.Generator().manual_seed(7)
+    img = (torch.rand(3, 5, 7, generator=g) - torch.tensor(ns["mean"]).view(3, 1, 1)) / torch.tensor(ns["std"]).view(3, 1, 1)
+    img[0, 0, 0] = (1.0 - 0.485) / 0.229          # exactly 1.0 after denormalisation -> 255
+    img[1, 0, 1] = (0.999 - 0.456) / 0.224
+    im = ns["tensor2im"](img.clone())
+    body = ref_lines("attack/DSGN/predict_and_save_pgd.py", 273, 283)
+    cases = []
+    rnd = random.Random(3)
+    for k in range(8):
+        cls = [1, 2, 3, 2, 1, 2, 0, 2][k]
+        bbox = [rnd.uniform(0, 1200) for _ in range(4)]
+        h, w, l = (rnd.uniform(0.5, 4.5) for _ in range(3))
+        c3 = [rnd.uniform(-30, 30), rnd.uniform(-2, 3), rnd.uniform(2, 60)]
+        ry = rnd.uniform(-3.2, 3.2)
+        score = rnd.random()
+        if k == 6:                                  # the reference's "no 3-D box" defaults (:267-270)
+            h, w, l, c3, ry = 0., 0., 0., [0., 0., 0.], 0.
+        f = io.StringIO()
+        env = dict(np=np, cls=cls, bbox=torch.tensor(bbox), h=h, w=w, l=l, box_center3d=torch.tensor(c3), ry=ry,
+                   score=torch.tensor(score), f=f)
+        exec(body, env)
+        cases.append(dict(cls=cls, bbox=[float(v) for v in torch.tensor(bbox)], hwl=[h, w, l],
+                          center3d=[float(v) for v in torch.tensor(c3)], ry=ry, score=float(torch.tensor(score)),
+                          line=f.getvalue()))
+    path = os.path.join(OUT, "handoff.json")
+    with open(path, "w") as fh:
+        json.dump(dict(tensor2im=dict(img=img.tolist(), out=im.tolist()), detections=cases), fh)
+    print("wrote", path, os.path.getsize(path), "bytes")
+
+
 def main():
+    handoff()
     allc = {}
     for fn in (dsgn_pgd, stereo_rcnn_pgd, dsgn_patch, stereo_rcnn_patch_clamp, roi_levels):
         allc.update(fn())
