@@ -73,3 +73,26 @@ def test_product_never_imports_oracle():
         if f.endswith(".py"):
             src = open(os.path.join(pkg, f)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+def test_conv_fusion_caps_is_a_pure_host_query(built_lib):
+    """b2_conv3d_fusion_caps tells which kernel serves a shape and what its epilogue can fuse; it
+    launches nothing, so it must answer on a machine without a GPU."""
+    def caps(n, cin, cout, d, h, w, stride, mode):
+        rows, aok = ctypes.c_int(-1), ctypes.c_int(-1)
+        assert built_lib.b2_conv3d_fusion_caps(n, cin, cout, d, h, w, stride, mode, ctypes.byref(rows), ctypes.byref(aok)) == 0
+        return rows.value, aok.value
+
+    assert caps(1, 64, 64, 48, 96, 312, 1, 0) == (148, 1)      # stride-1 kernel, one CTA per SM
+    assert caps(1, 96, 64, 192, 20, 304, 1, 0) == (148, 1)
+    assert caps(1, 128, 128, 24, 48, 156, 1, 0) == (148, 1)    # two N tiles share a CTA row
+    assert caps(1, 128, 64, 24, 48, 156, 2, 1) == (148, 1)     # transposed (DECONV) kernel
+    assert caps(1, 64, 128, 48, 96, 312, 2, 0) == (0, 0)       # stride-2 CONV: generic kernel, nothing fused
+    assert caps(2, 64, 64, 8, 16, 16, 1, 0) == (0, 1)          # N > 1: no statistics (a CTA row would mix samples)
+    assert caps(1, 64, 96, 8, 16, 16, 1, 0) == (0, 1)          # Nt = 48: 16-channel tail has no statistics
+    assert caps(1, 64, 64, 1, 16, 8, 1, 0) == (1, 1)           # a single tile: one CTA, one row
+    assert caps(1, 48, 64, 8, 16, 16, 1, 0) == (0, 0)          # Cin not a multiple of 32: not served by tcgen05
+    # the fused entry point validates its arguments before touching the device
+    from eval_driving_safety_b200 import _lib
+    rc = built_lib.b2_conv3d_fused(None, None, None, None, None, 1, None, None, 1, 64, 64, 8, 8, 8, 1, 0, None)
+    assert rc != 0 and "stat_mode" in _lib.last_error()
