@@ -1,4 +1,6 @@
-import sys; sys.path.insert(0, "/root/repo")
+"""bev_pool forward / backward at the KITTI voxel-grid size (CUDA events, L2 flushed between launches)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from eval_driving_safety_b200 import ops
 g = torch.Generator().manual_seed(0)
