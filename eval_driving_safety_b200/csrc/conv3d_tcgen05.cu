@@ -1275,9 +1275,7 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
 static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* wp, float* out, int N, int Cin,
                             int Cout, int Di, int Hi, int Wi, cudaStream_t st, const EpiFusion& ef, int* stat_rows,
                             bool query, int* addend_ok) {
-    const float* addend = ef.addend;
     float* stat_partial = ef.stat_partial;
-    (void)addend;
     DcParams p{};
     p.N = N; p.Cin = Cin; p.Cout = Cout;
     p.Do = 2 * Di; p.Ho = 2 * Hi; p.Wo = 2 * Wi;

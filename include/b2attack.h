@@ -4,7 +4,7 @@
  * against DSGN and Stereo R-CNN).
  *
  * The reference has no FFI of its own for this path: it is inline PyTorch code
- * in attack/DSGN/{pgd,patch}_attack.py and attack/Stereo-RCNN/*.py that reaches
+ * in attack/DSGN/{pgd,patch}_attack.py and attack/Stereo-RCNN/ (*.py) that reaches
  * ATen kernels and the upstream extensions dsgn._C / model.roi_layers.  Each
  * entry point below names the reference lines (or upstream op) it replaces.
  * INTEGRATION.md shows the ctypes / autograd.Function binding a maintainer adds.
