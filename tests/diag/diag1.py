@@ -1,10 +1,10 @@
 """GPU diagnostics (scratch): tcgen05 conv vs SIMT conv, pyramid roi per level, e2e backward per stage."""
 import sys, os, time
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import torch, torch.nn.functional as F
 from eval_driving_safety_b200 import ops, dsgn, synthetic, stereo_rcnn
 from oracle import dsgn_ref as R, attack_ref as A
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from helpers import rel_err, max_err
 
 what = sys.argv[1:] or ["conv", "roi", "e2e"]

@@ -1,6 +1,6 @@
 """GPU diagnostics (scratch): is the affine-GN gradient gap conditioning or a bug?  fp64 CPU oracle as arbiter."""
 import sys, os, copy
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import torch, torch.nn.functional as F
 from eval_driving_safety_b200 import ops, dsgn, synthetic

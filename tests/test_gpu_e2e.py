@@ -46,7 +46,7 @@ def setup(built_lib):
     """Whole-model tests: seeded default init.  (With perturbed 2-D GroupNorm affine
     parameters the stock torch CUDA 2-D extractor alone differs from its own CPU
     result by ~1e-2 in the input gradient on this tiny config -- measured, fp64
-    arbiter, tools/diag1.py -- which would mask what these tests are about.)"""
+    arbiter, tests/diag/diag1.py -- which would mask what these tests are about.)"""
     return _setup(False)
 
 
