@@ -26,6 +26,10 @@ SIGNATURES = {
     "b2_patch_apply": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, _IP, c_int, c_vp]),
     "b2_patch_update": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_f32, c_f32, _FP, _FP, c_vp, c_vp]),
+    "b2_patch_apply_dev": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp, c_int, c_vp]),
+    "b2_patch_update_dev": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_vp, c_int, c_f32, c_f32, _FP, _FP, c_vp,
+                                    c_vp]),
+    "b2_patch_axpy": (c_int, [c_vp, c_vp, c_int, c_int, _FP, _FP, c_vp]),
     "b2_cost_volume_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "b2_cost_volume_bwd_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
     "b2_cost_volume_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
@@ -43,6 +47,10 @@ SIGNATURES = {
     "b2_conv3d_fusion_caps": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "b2_conv3d_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int,
                                 c_int, c_int, c_int, c_vp]),
+    "b2_conv2d": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                          c_int, c_int, c_vp]),
+    "b2_conv2d_first_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+    "b2_conv2d_first_dgrad": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "b2_conv3d_c1_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
     "b2_conv3d_c1_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "b2_conv3d_c1_dgrad": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),

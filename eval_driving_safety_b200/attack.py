@@ -120,12 +120,20 @@ def generate_round_mask(radius, rng=None, height=384, width=1248):
 
 def patch_apply(img, patch, center, radius):
     """In-place blend of the circular patch into ``img`` [N,C,H,W] at ``center``
-    (one (row, col) or a list of N of them)."""
+    (one (row, col), a list of N of them, or an int32 CUDA tensor [N,2] -- read at run time, so a captured
+    CUDA graph can be replayed with other positions)."""
     lib = _lib.load()
     _need_cuda(img, patch)
     n, c, h, w = img.shape
     if not img.is_contiguous():
         raise RuntimeError("patch_apply: img must be contiguous NCHW")
+    if isinstance(center, torch.Tensor):
+        if not (center.is_cuda and center.dtype == torch.int32 and center.numel() == 2 * n and center.is_contiguous()):
+            raise RuntimeError("patch_apply: device centres must be a contiguous int32 CUDA tensor [N,2]")
+        patch = patch.reshape(c, 2 * radius + 1, 2 * radius + 1).contiguous()
+        check(lib.b2_patch_apply_dev(_p(img), _p(patch), n, c, h, w, c_vp(center.data_ptr()), int(radius), _stream()),
+              "patch_apply_dev")
+        return img
     centers = [center] * n if isinstance(center[0], int) else list(center)
     flat = (ctypes.c_int * (2 * n))(*[int(v) for cc in centers for v in cc])
     patch = patch.reshape(c, 2 * radius + 1, 2 * radius + 1).contiguous()
@@ -135,16 +143,102 @@ def patch_apply(img, patch, center, radius):
 
 def patch_update(patch, grad_l, grad_r, center_l, center_r, radius, alpha, eps, lo=None, hi=None,
                  delta_out=None):
-    """In-place patch step from the two image gradients [1,C,H,W]."""
+    """In-place patch step from the two image gradients [1,C,H,W].  ``center_l`` may be an int32 CUDA tensor
+    (cyL, cxL, cyR, cxR) read at run time (``center_r`` is then ignored): graph-replayable."""
     lib = _lib.load()
     _need_cuda(patch, grad_l, grad_r)
     _, c, h, w = grad_l.shape
     if not (patch.is_contiguous() and grad_l.is_contiguous() and grad_r.is_contiguous()):
         raise RuntimeError("patch_update: tensors must be contiguous")
+    if isinstance(center_l, torch.Tensor):
+        if not (center_l.is_cuda and center_l.dtype == torch.int32 and center_l.numel() == 4 and center_l.is_contiguous()):
+            raise RuntimeError("patch_update: device centres must be a contiguous int32 CUDA tensor (cyL,cxL,cyR,cxR)")
+        check(lib.b2_patch_update_dev(_p(patch), _p(grad_l), _p(grad_r), c, h, w, c_vp(center_l.data_ptr()), int(radius),
+                                      float(alpha), float(eps), f32_array(lo), f32_array(hi), _p(delta_out), _stream()),
+              "patch_update_dev")
+        return patch
     check(lib.b2_patch_update(_p(patch), _p(grad_l), _p(grad_r), c, h, w, int(center_l[0]), int(center_l[1]),
                               int(center_r[0]), int(center_r[1]), int(radius), float(alpha), float(eps),
                               f32_array(lo), f32_array(hi), _p(delta_out), _stream()), "patch_update")
     return patch
+
+
+def patch_axpy(patch, delta, lo=None, hi=None):
+    """patch = clamp(patch - delta, lo_c, hi_c) in place: second half of the split update of the multi-GPU
+    universal patch (``patch_update(..., delta_out=)`` -> all_reduce -> this)."""
+    lib = _lib.load()
+    _need_cuda(patch, delta)
+    c, dim = patch.shape[-3], patch.shape[-1]
+    if not (patch.is_contiguous() and delta.is_contiguous()) or delta.numel() != patch.numel():
+        raise RuntimeError("patch_axpy: patch and delta must be contiguous tensors of the same size")
+    check(lib.b2_patch_axpy(_p(patch), _p(delta), c, dim, f32_array(lo), f32_array(hi), _stream()), "patch_axpy")
+    return patch
+
+
+# ---------------------------------------------------------------------------
+# Targets of the universal patch attack and patch initialisation (host side)
+# ---------------------------------------------------------------------------
+# attack/DSGN/patch_attack.py:342-354 -- the fake ground truth every image is given: a car at 29 m
+FAKE_GT_BBOX = (569.33, 180.88, 613.91, 225.02)                       # (x1, y1, x2, y2), :343-346
+FAKE_GT_BOX3D = (1.65, 1.67, 3.64, -0.78, 1.98, 29.11, -1.60)         # (h, w, l, x, y, z, theta), :349-355
+
+
+def inject_fake_gt(bbox, box3d):
+    """attack/DSGN/patch_attack.py:336-354: zero every ground-truth box of the image and make box 0 the fake
+    car.  ``bbox`` [K,4], ``box3d`` [K,7] (the ``.data`` of ``targets[0].bbox`` / ``.box3d``), modified in place
+    and returned."""
+    for i in range(len(bbox)):
+        bbox[i] = torch.zeros(size=bbox[i].shape)
+        box3d[i] = torch.zeros(size=box3d[i].shape)
+    for j, v in enumerate(FAKE_GT_BBOX):
+        bbox[0, j] = v
+    for j, v in enumerate(FAKE_GT_BOX3D):
+        box3d[0, j] = v
+    return bbox, box3d
+
+
+def stereo_rcnn_fake_gt(center_l, center_r, radius, max_boxes=30):
+    """attack/Stereo-RCNN/patch_attack.py:187-207: the only ground-truth box of the image is the patch's own
+    bounding square (left, right and merged = left), num_boxes = 1.  Returns (gt_left, gt_right, gt_merge)
+    [1,max_boxes,5] and num_boxes."""
+    gl, gr, gm = (torch.zeros(1, max_boxes, 5) for _ in range(3))
+    for t, c in ((gl, center_l), (gr, center_r), (gm, center_l)):
+        t[0, 0, 0] = c[1] - radius
+        t[0, 0, 1] = c[0] - radius
+        t[0, 0, 2] = c[1] + radius
+        t[0, 0, 3] = c[0] + radius
+    return gl, gr, gm, torch.tensor(1)
+
+
+def resize_patch(patch, dim):
+    """attack/DSGN/patch_attack.py:222-227: a patch trained at another size (e.g. on Stereo R-CNN) is resized
+    with ``cv2.resize(..., INTER_LINEAR)``; bilinear with half-pixel centres and edge clamping is exactly
+    ``F.interpolate(mode='bilinear', align_corners=False)`` (no OpenCV dependency in the product; pinned against
+    cv2 in tests/test_host_logic.py)."""
+    patch = torch.as_tensor(patch, dtype=torch.float32)
+    if patch.shape[-1] == dim and patch.shape[-2] == dim:
+        return patch.clone()
+    return torch.nn.functional.interpolate(patch, size=(dim, dim), mode='bilinear', align_corners=False)
+
+
+def init_patch(patch_ratio, save_dir, short_side=384, resize=True):
+    """attack/DSGN/patch_attack.py:211-234 (``short_side`` 384, resume + resize) and
+    attack/Stereo-RCNN/patch_attack.py:58-76 (600, ``resize=False``: loaded as is).  Resumes from
+    ``<save_dir>/epoch0/patch.npy`` when that directory exists, else creates it with a zero patch.
+    Returns (patch_dim, radius, patch [1,3,dim,dim] float32 numpy array)."""
+    import os
+    import numpy as np
+    d0 = os.path.join(save_dir, 'epoch0')
+    patch_dim, radius = patch_dim_radius(short_side, patch_ratio)
+    if os.path.isdir(d0):
+        patch = np.load(os.path.join(d0, 'patch.npy'))
+        if resize:
+            patch = resize_patch(patch, patch_dim).numpy()
+    else:
+        os.makedirs(d0)
+        patch = np.zeros((1, 3, patch_dim, patch_dim), dtype=np.float32)
+        np.save(os.path.join(d0, 'patch.npy'), patch)
+    return patch_dim, radius, patch
 
 
 # ---------------------------------------------------------------------------
@@ -182,7 +276,7 @@ def pgd_attack(model, loss_fn, imgL, imgR, calib, iters, alpha, eps, norm='linf'
 
 
 def patch_attack_step(model, loss_fn, imgL, imgR, calib, patch, center_l, center_r, radius, iters=2,
-                      alpha=1e3, eps=8.0 / 255, delta_hook=None):
+                      alpha=1e3, eps=8.0 / 255, delta_hook=None, lo=None, hi=None):
     """Inner loop of the universal patch attack for one pair
     (attack/DSGN/patch_attack.py:367-430): blend, forward/backward, crop, clipped
     descent.  ``delta_hook(delta) -> delta`` lets the multi-GPU driver all-reduce
@@ -196,11 +290,11 @@ def patch_attack_step(model, loss_fn, imgL, imgR, calib, patch, center_l, center
         loss = loss_fn(outputs)
         gL, gR = torch.autograd.grad(loss, [xL, xR])
         if delta_hook is None:
-            patch_update(patch, gL.contiguous(), gR.contiguous(), center_l, center_r, radius, alpha, eps)
+            patch_update(patch, gL.contiguous(), gR.contiguous(), center_l, center_r, radius, alpha, eps, lo, hi)
         else:
             delta = torch.empty_like(patch)
             patch_update(patch, gL.contiguous(), gR.contiguous(), center_l, center_r, radius, alpha, eps,
                          delta_out=delta)
-            patch.sub_(delta_hook(delta))
+            patch_axpy(patch, delta_hook(delta), lo, hi)
         losses.append(loss.detach())
     return patch, torch.stack(losses)

@@ -28,6 +28,25 @@ inline int check_launch(const char* what) {
         }                                    \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: remember what has been
+// granted per (call site, device) instead of once per process, so a process that drives a second GPU opts in
+// there too.  ``granted`` is the call site's own static table (zero-initialised).  Racing host threads at worst
+// repeat the (idempotent) driver call.
+constexpr int kMaxDevices = 64;
+struct SmemOptIn { int granted[kMaxDevices]; };
+
+template <typename Kernel>
+inline cudaError_t ensure_dynamic_smem(SmemOptIn& tab, Kernel kernel, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= kMaxDevices) return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (bytes <= tab.granted[dev]) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) tab.granted[dev] = bytes;
+    return e;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // Grid for a grid-stride streaming kernel: whole waves of the 148 SMs.

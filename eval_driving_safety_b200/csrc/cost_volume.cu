@@ -40,7 +40,7 @@ cost_volume_fwd_cl(const float4* __restrict__ left, const float4* __restrict__ r
     __shared__ float s_f[kCvMaxD];
     const int n = blockIdx.y;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        float s = __ldg(shifts + n * D + d), s0 = floorf(s);
+        float s = fmaxf(__ldg(shifts + n * D + d), 0.f), s0 = floorf(s);
         s_s0[d] = (int)s0;
         s_f[d] = __fsub_rn(s, s0);
     }
@@ -94,7 +94,7 @@ cost_volume_fwd_ncdhw(const float* __restrict__ left, const float* __restrict__ 
         int d = (int)((i / ((int64_t)W * H)) % D);
         int c2 = (int)((i / ((int64_t)W * H * D)) % (2 * C));
         int n = (int)(i / ((int64_t)W * H * D * 2 * C));
-        float s = __ldg(shifts + n * D + d);
+        float s = fmaxf(__ldg(shifts + n * D + d), 0.f);
         float s0 = floorf(s);
         float f = __fsub_rn(s, s0);
         int x0 = w - (int)s0;
@@ -128,7 +128,7 @@ cost_volume_bwd_cl(const float4* __restrict__ gcost, const float* __restrict__ s
     __shared__ float s_f[kCvMaxD];
     const int n = blockIdx.y;
     for (int d = threadIdx.x; d < D; d += blockDim.x) {
-        float s = __ldg(shifts + n * D + d), s0 = floorf(s);
+        float s = fmaxf(__ldg(shifts + n * D + d), 0.f), s0 = floorf(s);
         s_s0[d] = (int)s0;
         s_f[d] = s - s0;
     }
@@ -187,13 +187,13 @@ cost_volume_bwd_ncdhw(const float* __restrict__ gcost, const float* __restrict__
         float acc = 0.f;
         if (c2 < C) {
             for (int d = 0; d < D; ++d) {
-                int s0 = (int)floorf(__ldg(sh + d));
+                int s0 = (int)floorf(fmaxf(__ldg(sh + d), 0.f));
                 if (w - s0 >= 0) acc += __ldcs(gb + (int64_t)d * H * W + w);
             }
             gleft[(((int64_t)n * C + c2) * H + h) * W + w] = acc;
         } else {
             for (int d = 0; d < D; ++d) {
-                float s = __ldg(sh + d);
+                float s = fmaxf(__ldg(sh + d), 0.f);
                 float s0f = floorf(s);
                 float f = s - s0f;
                 int wa = w + (int)s0f;
@@ -237,7 +237,7 @@ cost_volume_fwd_row(const float4* __restrict__ left, const float4* __restrict__ 
     const int64_t row = ((int64_t)n * H + h) * W;
     for (int i = threadIdx.x; i < W * C4; i += kCvRowThreads) s_r[i] = __ldg(right + row * C4 + i);
     for (int d = d_lo + threadIdx.x; d < d_hi; d += kCvRowThreads) {
-        float s = __ldg(shifts + n * D + d), s0 = floorf(s);
+        float s = fmaxf(__ldg(shifts + n * D + d), 0.f), s0 = floorf(s);
         s_s0[d] = (int)s0;
         s_f[d] = __fsub_rn(s, s0);
     }
@@ -293,7 +293,7 @@ cost_volume_bwd_row(const float4* __restrict__ gcost, const float* __restrict__ 
     const int h = blockIdx.x, n = blockIdx.y, seg = blockIdx.z;
     const int d_lo = seg * dseg, d_hi = min(D, d_lo + dseg);
     for (int d = d_lo + threadIdx.x; d < d_hi; d += kCvRowThreads) {
-        float s = __ldg(shifts + n * D + d), s0 = floorf(s);
+        float s = fmaxf(__ldg(shifts + n * D + d), 0.f), s0 = floorf(s);
         s_s0[d] = (int)s0;
         s_f[d] = s - s0;
     }
@@ -386,11 +386,9 @@ extern "C" int b2_cost_volume_fwd(const float* left, const float* right, const f
         B2_REQUIRE(D <= kCvMaxD, "cost_volume_fwd: at most %d planes", kCvMaxD);
         const int row_bytes = W * C * 4;
         if (C == 32 && W <= 32 * kCvMaxW32 && H <= 65535 && N <= 65535) {      // row-staged kernel (DSGN: 32 ch)
-            static bool attr = false;
-            if (!attr) {
-                cudaFuncSetAttribute(cost_volume_fwd_row<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-                attr = true;
-            }
+            static SmemOptIn optin;
+            cudaError_t ea = ensure_dynamic_smem(optin, cost_volume_fwd_row<8>, 64 * 1024);
+            if (ea != cudaSuccess) { set_error("cost_volume_fwd: cudaFuncSetAttribute: %s", cudaGetErrorString(ea)); return (int)ea; }
             const int dseg = D >= 16 ? 4 : D;
             cost_volume_fwd_row<8><<<dim3(H, N, (D + dseg - 1) / dseg), kCvRowThreads, row_bytes, st>>>(
                 (const float4*)left, (const float4*)right, shifts, (float4*)cost, D, H, W, dseg);
@@ -426,11 +424,9 @@ extern "C" int b2_cost_volume_bwd(const float* gcost, const float* shifts, float
         B2_REQUIRE(D <= kCvMaxD, "cost_volume_bwd: at most %d planes", kCvMaxD);
         const int row_bytes = W * C * 4;
         if (workspace && C == 32 && W <= 32 * kCvMaxW32 && H <= 65535 && N <= 65535 && aligned16(workspace)) {
-            static bool attr = false;
-            if (!attr) {
-                cudaFuncSetAttribute(cost_volume_bwd_row<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-                attr = true;
-            }
+            static SmemOptIn optin;
+            cudaError_t ea = ensure_dynamic_smem(optin, cost_volume_bwd_row<8>, 100 * 1024);
+            if (ea != cudaSuccess) { set_error("cost_volume_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(ea)); return (int)ea; }
             const int nseg = D >= 2 * kCvBwdSegs ? kCvBwdSegs : 1;
             const int dseg = (D + nseg - 1) / nseg;
             cost_volume_bwd_row<8><<<dim3(H, N, nseg), kCvRowThreads, 2 * row_bytes, st>>>(

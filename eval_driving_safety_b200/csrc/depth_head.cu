@@ -155,6 +155,7 @@ extern "C" int b2_depth_head_fwd(const float* cost, float* depth, float* sm_stat
                                  int H, int W, int J, float z0, float dz, void* stream) {
     B2_REQUIRE(cost && depth, "depth_head_fwd: null pointer");
     B2_REQUIRE(D >= 1 && Hc >= 1 && Wc >= 1 && H >= Hc && W >= Wc && J >= D, "depth_head_fwd: upsampling only");
+    B2_REQUIRE(H % Hc == 0 && W % Wc == 0 && J % D == 0, "depth_head_fwd: integer upsampling ratios only (%dx%dx%d -> %dx%dx%d)", D, Hc, Wc, J, H, W);
     int64_t total = (int64_t)N * H * W;
     if (total == 0) return 0;
     depth_head_pixel_kernel<0><<<stream_grid(total, 256, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(
@@ -172,6 +173,8 @@ extern "C" int b2_depth_head_bwd(const float* cost, const float* gdepth, float* 
     B2_REQUIRE(cost && gdepth && gcost && workspace, "depth_head_bwd: null pointer");
     B2_REQUIRE(!sm_stats == !depth, "depth_head_bwd: sm_stats and depth (both saved by the forward) go together");
     B2_REQUIRE(D >= 1 && Hc >= 1 && Wc >= 1 && H >= Hc && W >= Wc && J >= D, "depth_head_bwd: upsampling only");
+    B2_REQUIRE(H % Hc == 0 && W % Wc == 0 && J % D == 0, "depth_head_bwd: integer upsampling ratios only (the gather window of the "
+               "backward is derived from them); got %dx%dx%d -> %dx%dx%d", D, Hc, Wc, J, H, W);
     int64_t total = (int64_t)N * H * W;
     if (total == 0) return 0;
     DhGeom g = dh_geom(N, D, Hc, Wc, H, W, J, z0, dz);

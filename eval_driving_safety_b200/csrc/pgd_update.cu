@@ -186,8 +186,12 @@ l2_project(const float* c, float* out, int64_t per_img, int64_t hw, int C, float
 // ---------------------------------------------------------------------------
 struct Centers { int cy[8]; int cx[8]; };
 
+// centers_dev != nullptr: the centres are read from device memory ([n_img][2] = (cy, cx)) instead of the
+// launch arguments, so a captured CUDA graph can be replayed for images with other patch positions
 __global__ void patch_apply_kernel(float* img, const float* patch, int n_img, int C, int H, int W,
-                                   Centers ctr, int radius) {
+                                   Centers ctr, int radius, const int* __restrict__ centers_dev) {
+    if (centers_dev)
+        for (int n = 0; n < n_img && n < 8; ++n) { ctr.cy[n] = centers_dev[2 * n]; ctr.cx[n] = centers_dev[2 * n + 1]; }
     const int dim = 2 * radius + 1;
     const int64_t total = (int64_t)n_img * C * dim * dim;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -210,7 +214,18 @@ __global__ void patch_apply_kernel(float* img, const float* patch, int n_img, in
 __global__ void patch_update_kernel(float* patch, const float* gL, const float* gR, int C, int H,
                                     int W, int cyL, int cxL, int cyR, int cxR, int radius,
                                     float half_alpha, float eps, int has_range, ChanParams cp,
-                                    float* delta_out) {
+                                    float* delta_out, const int* __restrict__ centers_dev) {
+    if (centers_dev) {                  // (cyL, cxL, cyR, cxR) from device memory: graph-replayable
+        cyL = centers_dev[0]; cxL = centers_dev[1]; cyR = centers_dev[2]; cxR = centers_dev[3];
+        if (cyL - radius < 0 || cyL + radius >= H || cxL - radius < 0 || cxL + radius >= W ||
+            cyR - radius < 0 || cyR + radius >= H || cxR - radius < 0 || cxR + radius >= W) {
+            // a box that leaves the frame cannot be validated on the host here: contribute a zero step
+            const int tot = C * (2 * radius + 1) * (2 * radius + 1);
+            if (delta_out)
+                for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += gridDim.x * blockDim.x) delta_out[i] = 0.f;
+            return;
+        }
+    }
     const int dim = 2 * radius + 1;
     const int total = C * dim * dim;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -222,6 +237,16 @@ __global__ void patch_update_kernel(float* patch, const float* gL, const float* 
         if (delta_out) { delta_out[i] = d; continue; }
         float v = __fsub_rn(patch[i], d);
         if (has_range) v = fminf(fmaxf(v, cp.lo[c]), cp.hi[c]);
+        patch[i] = v;
+    }
+}
+
+// patch -= delta (the all-reduced clipped step), then the optional per-channel range clamp
+__global__ void patch_axpy_kernel(float* patch, const float* delta, int C, int per_c, int has_range, ChanParams cp) {
+    const int total = C * per_c;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        float v = __fsub_rn(patch[i], delta[i]);
+        if (has_range) { const int c = i / per_c; v = fminf(fmaxf(v, cp.lo[c]), cp.hi[c]); }
         patch[i] = v;
     }
 }
@@ -297,8 +322,21 @@ extern "C" int b2_patch_apply(float* img, const float* patch, int n_img, int C, 
     int dim = 2 * radius + 1;
     int64_t total = (int64_t)n_img * C * dim * dim;
     int grid = stream_grid(total, 256);
-    patch_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, patch, n_img, C, H, W, ctr, radius);
+    patch_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, patch, n_img, C, H, W, ctr, radius, nullptr);
     return check_launch("patch_apply");
+}
+
+extern "C" int b2_patch_apply_dev(float* img, const float* patch, int n_img, int C, int H, int W,
+                                  const int* centers_dev, int radius, void* stream) {
+    B2_REQUIRE(img && patch && centers_dev, "patch_apply_dev: null pointer");
+    B2_REQUIRE(n_img >= 1 && n_img <= 8, "patch_apply_dev: n_img must be 1..8 (got %d)", n_img);
+    B2_REQUIRE(radius >= 0, "patch_apply_dev: negative radius");
+    Centers ctr{};
+    int dim = 2 * radius + 1;
+    int64_t total = (int64_t)n_img * C * dim * dim;
+    int grid = stream_grid(total, 256);
+    patch_apply_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, patch, n_img, C, H, W, ctr, radius, centers_dev);
+    return check_launch("patch_apply_dev");
 }
 
 extern "C" int b2_patch_update(float* patch, const float* gL, const float* gR, int C, int H, int W,
@@ -318,6 +356,33 @@ extern "C" int b2_patch_update(float* patch, const float* gL, const float* gR, i
     float half_alpha = (float)(0.5 * (double)alpha);
     patch_update_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
         patch, gL, gR, C, H, W, cyL, cxL, cyR, cxR, radius, half_alpha, eps, (lo && hi) ? 1 : 0, cp,
-        delta_out);
+        delta_out, nullptr);
     return check_launch("patch_update");
+}
+
+extern "C" int b2_patch_update_dev(float* patch, const float* gL, const float* gR, int C, int H, int W,
+                                   const int* centers_dev, int radius, float alpha, float eps, const float* lo,
+                                   const float* hi, float* delta_out, void* stream) {
+    B2_REQUIRE(patch && gL && gR && centers_dev, "patch_update_dev: null pointer");
+    B2_REQUIRE(C >= 1 && C <= 4, "patch_update_dev: C must be 1..4");
+    B2_REQUIRE(radius >= 0 && 2 * radius + 1 <= H && 2 * radius + 1 <= W, "patch_update_dev: patch larger than the frame");
+    ChanParams cp;
+    if (int e = fill_chan(cp, C, 0, nullptr, nullptr, lo, hi)) return e;
+    int dim = 2 * radius + 1;
+    int total = C * dim * dim;
+    float half_alpha = (float)(0.5 * (double)alpha);
+    patch_update_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        patch, gL, gR, C, H, W, 0, 0, 0, 0, radius, half_alpha, eps, (lo && hi) ? 1 : 0, cp, delta_out, centers_dev);
+    return check_launch("patch_update_dev");
+}
+
+extern "C" int b2_patch_axpy(float* patch, const float* delta, int C, int dim, const float* lo, const float* hi,
+                             void* stream) {
+    B2_REQUIRE(patch && delta, "patch_axpy: null pointer");
+    B2_REQUIRE(C >= 1 && C <= 4 && dim >= 1, "patch_axpy: C must be 1..4, dim >= 1");
+    ChanParams cp;
+    if (int e = fill_chan(cp, C, 0, nullptr, nullptr, lo, hi)) return e;
+    const int total = C * dim * dim;
+    patch_axpy_kernel<<<(total + 255) / 256, 256, 0, (cudaStream_t)stream>>>(patch, delta, C, dim * dim, (lo && hi) ? 1 : 0, cp);
+    return check_launch("patch_axpy");
 }

@@ -74,47 +74,40 @@ def run_convbn_3d(seq, x, relu=False, res=None, fork=False):
     return (y, x2) if fork else y
 
 
-# Stock 2-D convolutions (cuDNN).  'tf32' = PyTorch's default on this hardware; 'tf32x3' = the same
-# TF32 tensor-core kernels run on an error-compensated split (x = x_hi + x_lo, w = w_hi + w_lo,
-# y ~ x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, every factor exactly representable in TF32) -> fp32-class
-# accuracy at 3x the (small) 2-D conv cost.  cuDNN's true-fp32 channels-last kernels are ~10x slower.
-BACKBONE_PRECISION = os.environ.get("B2_BACKBONE", "tf32")
+# 2-D convolutions.  'b2' (default): our tcgen05 kernels with the error-compensated 3xTF32 split done
+# in-kernel (fp32-class accuracy, ops.conv2d).  'cudnn' / 'cudnn_tf32x3': the stock cuDNN kernels of
+# round 1, kept for A/B measurements only (TF32 per torch.backends flags / split stacked on the host).
+BACKBONE_IMPL = os.environ.get("B2_BACKBONE", "b2")
 
 
-def set_backbone_precision(mode):
-    global BACKBONE_PRECISION
-    assert mode in ("tf32", "tf32x3")
-    BACKBONE_PRECISION = mode
-
-
-def _tf32_split(t):
-    hi = (t.view(torch.int32) & ~0x1FFF).view(torch.float32)      # exactly TF32-representable
-    return hi, t - hi                                              # lo has <= 13 significant bits
+def set_backbone_impl(mode):
+    global BACKBONE_IMPL
+    assert mode in ("b2", "cudnn", "cudnn_tf32x3")
+    BACKBONE_IMPL = mode
 
 
 _W3_CACHE = {}
 
 
 def _w3(w, dim):
-    """[w_hi, w_lo, w_hi] stacked along ``dim`` (1: input channels for the forward, 0: output channels
-    for the data gradient); cached per frozen weight."""
+    """[w_hi, w_lo, w_hi] stacked along ``dim`` (cuDNN A/B mode only)."""
     key = (id(w), dim)
     hit = _W3_CACHE.get(key)
     if hit is not None and hit[0] is w and hit[1] == w._version:
         return hit[2]
-    wh, wl = _tf32_split(w.detach())
+    wh, wl = ops.tf32_split(w.detach())
     w3 = torch.cat([wh, wl, wh], dim).contiguous(memory_format=torch.channels_last)
     _W3_CACHE[key] = (w, w._version, w3)
     return w3
 
 
 class Conv2dTf32x3Fn(torch.autograd.Function):
-    """conv2d(x, w) with frozen w: three TF32 convolutions fused into one call by stacking the split
-    operands along the input channels; the data gradient is the same trick on the output gradient."""
+    """A/B mode 'cudnn_tf32x3': three TF32 cuDNN convolutions fused into one call by stacking the split
+    operands along the input channels (round 1's high-fidelity mode)."""
 
     @staticmethod
     def forward(ctx, x, w, bias, stride, padding, dilation):
-        xh, xl = _tf32_split(x)
+        xh, xl = ops.tf32_split(x)
         x3 = torch.cat([xh, xh, xl], 1).contiguous(memory_format=torch.channels_last)
         y = F.conv2d(x3, _w3(w, 1), bias, stride, padding, dilation)
         ctx.save_for_backward(w)
@@ -126,24 +119,39 @@ class Conv2dTf32x3Fn(torch.autograd.Function):
     def backward(ctx, g):
         (w,) = ctx.saved_tensors
         shape, stride, padding, dilation = ctx.cfg
-        gh, gl = _tf32_split(g)
+        gh, gl = ops.tf32_split(g)
         g3 = torch.cat([gh, gh, gl], 1).contiguous(memory_format=torch.channels_last)
-        gx = torch.nn.grad.conv2d_input(shape, _w3(w, 0), g3, stride, padding, dilation)   # stacked along Cout
+        gx = torch.nn.grad.conv2d_input(shape, _w3(w, 0), g3, stride, padding, dilation)
         return gx, None, None, None, None, None
 
 
-def conv2d_stock(conv, x):
-    if BACKBONE_PRECISION == "tf32x3" and x.is_cuda and conv.in_channels >= 16:
-        return Conv2dTf32x3Fn.apply(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation)
-    return conv(x)
+def conv2d_any(conv, x, fork=False):
+    """``conv`` = nn.Conv2d used as parameter holder.  Returns y, or (y, x2) with ``fork`` (x2 = x for its
+    other consumers; with our kernels their gradient is added inside the data-gradient launch)."""
+    if BACKBONE_IMPL == "b2":
+        k, pad, dil = conv.kernel_size[0], conv.padding[0], conv.dilation[0]
+        if conv.kernel_size[0] != conv.kernel_size[1] or pad != dil * (k // 2) or conv.groups != 1 \
+                or conv.stride[0] != conv.stride[1]:
+            raise RuntimeError("conv2d: unsupported layer %r" % (conv,))
+        if fork:
+            return ops.conv2d_fork(x, conv.weight, conv.bias, conv.stride[0], dil)
+        return ops.conv2d(x, conv.weight, conv.bias, conv.stride[0], dil)
+    x = x.contiguous(memory_format=torch.channels_last)
+    if BACKBONE_IMPL == "cudnn_tf32x3" and conv.in_channels >= 16:
+        y = Conv2dTf32x3Fn.apply(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation)
+    else:
+        y = conv(x)
+    return (y, x) if fork else y
 
 
-def run_convbn_2d(seq, x, relu=False, res=None):
-    """cuDNN conv2d (channels-last) -> our GroupNorm (+res) (+ReLU) kernel.
-    ``seq`` = Sequential(Conv2d, GroupNorm)."""
+def run_convbn_2d(seq, x, relu=False, res=None, fork=False):
+    """conv2d -> GroupNorm (+res) (+ReLU), all on the sm_100a kernels.  ``seq`` = Sequential(Conv2d, GroupNorm)."""
     conv, norm = seq[0], seq[1]
-    y = conv2d_stock(conv, x)
-    return ops.groupnorm_act(y, norm.weight, norm.bias, norm.num_groups, norm.eps, relu=relu, res=res)
+    y = conv2d_any(conv, x, fork)
+    if fork:
+        y, x2 = y
+    y = ops.groupnorm_act(y, norm.weight, norm.bias, norm.num_groups, norm.eps, relu=relu, res=res)
+    return (y, x2) if fork else y
 
 
 class BasicBlock(nn.Module):
@@ -156,8 +164,10 @@ class BasicBlock(nn.Module):
             self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), _gn(cfg, cout))
 
     def forward(self, x):
-        out = run_convbn_2d(self.conv1[0], x, relu=True)
-        short = x if self.downsample is None else run_convbn_2d(self.downsample, x)
+        # x feeds conv1 AND the shortcut: conv1 forks it, so the shortcut's gradient is added inside conv1's
+        # data-gradient kernel (no autograd accumulation pass)
+        out, x2 = run_convbn_2d(self.conv1[0], x, relu=True, fork=True)
+        short = x2 if self.downsample is None else run_convbn_2d(self.downsample, x2)
         return run_convbn_2d(self.conv2, out, relu=False, res=short)      # GN(conv2) + shortcut, one pass
 
 
@@ -222,8 +232,7 @@ class FeatureExtraction(nn.Module):
     def forward(self, x, rpn_samples=None):
         """``rpn_samples``: compute the image-feature head only for the first that many samples
         (the model runs left and right images as one batch; only the left needs that head)."""
-        x = x.contiguous(memory_format=torch.channels_last)
-        out = x
+        out = x                                   # NCHW image batch: the first layer's kernel reads it as is
         for i in (0, 2, 4):
             out = run_convbn_2d(self.firstconv[i], out, relu=True)
         out = self.layer1(out)
@@ -247,9 +256,9 @@ class FeatureExtraction(nn.Module):
                 y = run_convbn_2d(br[1], br[0](skip), relu=True)
                 cat.append(upsample_bilinear_matmul(y, size))
         cat = torch.cat(cat, 1).contiguous(memory_format=torch.channels_last)
-        f = conv2d_stock(self.lastconv[2], run_convbn_2d(self.lastconv[0], cat, relu=True))
+        f = conv2d_any(self.lastconv[2], run_convbn_2d(self.lastconv[0], cat, relu=True))
         n_rpn = cat.shape[0] if rpn_samples is None else rpn_samples
-        r = conv2d_stock(self.rpnconv[2], run_convbn_2d(self.rpnconv[0], cat[:n_rpn], relu=True))
+        r = conv2d_any(self.rpnconv[2], run_convbn_2d(self.rpnconv[0], cat[:n_rpn], relu=True))
         return f, r
 
 
@@ -322,8 +331,13 @@ def lifting_grid(cfg, proj, feat_hw):
 
 class StereoNet(nn.Module):
     """``StereoNet(cfg)(imgL, imgR, calibs_fu, calibs_baseline, calibs_Proj,
-    calibs_Proj_R=)`` -> dict(depth_preds [N,H,W], bbox_cls, bbox_reg,
-    bbox_centerness) -- attack/DSGN/pgd_attack.py:136, 308-323."""
+    calibs_Proj_R=)`` -> dict(depth_preds, bbox_cls, bbox_reg, bbox_centerness)
+    -- attack/DSGN/pgd_attack.py:136, 308-323.
+
+    ``depth_preds`` follows upstream's EVAL-mode convention (the attack scripts call ``model.eval()``,
+    pgd_attack.py:140): ONE [N,H,W] tensor, not the training-mode list of per-scale maps.  The
+    reference's loss lines (:311-317) iterate it, i.e. they walk the batch dimension -- correct only
+    for the batch size of 1 the scripts use; ``attack_loss`` documents how N > 1 is treated here."""
 
     def __init__(self, cfg=None):
         super().__init__()
@@ -349,12 +363,13 @@ class StereoNet(nn.Module):
         self.bbox_centerness = nn.Conv2d(b, cfg.num_anchors, 3, 1, 1)
         self._lift_cache = {}
         self._shift_cache = {}
+        self._head_cache = None
 
     # the attack never needs parameter gradients
     def freeze(self):
         for p in self.parameters():
             p.requires_grad_(False)
-        # 2-D parts run channels-last end to end (cuDNN NHWC kernels, our GroupNorm kernel)
+        # (cuDNN A/B modes only: channels-last weights for its NHWC kernels)
         for m in self.modules():
             if isinstance(m, nn.Conv2d):
                 m.weight.data = m.weight.data.contiguous(memory_format=torch.channels_last)
@@ -364,13 +379,19 @@ class StereoNet(nn.Module):
         sd = {(k[7:] if k.startswith('module.') else k): v for k, v in state_dict.items()}
         return super().load_state_dict(sd, strict=strict, **kw)
 
-    # -- cached calibration-only quantities ---------------------------------
+    # -- cached calibration-only quantities (a few calibrations stay resident: KITTI has one per recording
+    # day; building an entry syncs with the host, so it must happen outside any graph capture -- the engine
+    # warms every new calibration up eagerly before it captures) ---------------------------------
+    CALIB_CACHE = 4
+
     def _shifts(self, fu, baseline, device):
         key = (tuple(fu.flatten().tolist()), tuple(baseline.flatten().tolist()))
         hit = self._shift_cache.get(key)
         if hit is None:
             hit = plane_shifts(self.cfg, fu.cpu(), baseline.cpu()).to(device)
-            self._shift_cache = {key: hit}
+            if len(self._shift_cache) >= self.CALIB_CACHE:
+                self._shift_cache.pop(next(iter(self._shift_cache)))
+            self._shift_cache[key] = hit
         return hit
 
     def _lift_plan(self, proj, psv_spatial, img_spatial, device):
@@ -381,7 +402,9 @@ class StereoNet(nn.Module):
             n, z, y, x, _ = grid3.shape
             grid2 = grid3[..., :2].contiguous().view(n, z * y, x, 2)
             hit = (grid3, ops.GridPlan(grid3, psv_spatial, True), ops.GridPlan(grid2, img_spatial, True))
-            self._lift_cache = {key: hit}
+            if len(self._lift_cache) >= self.CALIB_CACHE:
+                self._lift_cache.pop(next(iter(self._lift_cache)))
+            self._lift_cache[key] = hit
         return hit
 
     # -- stages --------------------------------------------------------------
@@ -412,7 +435,30 @@ class StereoNet(nn.Module):
         bev = ops.bev_pool(v, cfg.y_pool)          # AvgPool3d over Y + (C, Y/p) -> channels, one pass
         bev = run_convbn_2d(self.bev_conv[0], bev, relu=True)
         bev = run_convbn_2d(self.bev_conv[2], bev, relu=True)
-        return conv2d_stock(self.bbox_cls, bev), conv2d_stock(self.bbox_reg, bev), conv2d_stock(self.bbox_centerness, bev)
+        return self.heads(bev)
+
+    def heads(self, bev):
+        """bbox_cls / bbox_reg / bbox_centerness (three 3x3 convs with bias on the same map) as ONE
+        128 -> 64 conv (4 + 28 + 4 channels, zero-padded to the tensor core's N granularity)."""
+        convs = (self.bbox_cls, self.bbox_reg, self.bbox_centerness)
+        if BACKBONE_IMPL != "b2":
+            return tuple(conv2d_any(c, bev) for c in convs)
+        key = tuple((c.weight._version, c.weight.data_ptr(), c.bias._version) for c in convs)
+        if self._head_cache is None or self._head_cache[0] != key:
+            widths = [c.out_channels for c in convs]
+            tot = sum(widths)
+            pad = (-tot) % 32
+            w = torch.cat([c.weight.detach() for c in convs] +
+                          [convs[0].weight.new_zeros(pad, *convs[0].weight.shape[1:])], 0).contiguous()
+            b = torch.cat([c.bias.detach() for c in convs] + [convs[0].bias.new_zeros(pad)], 0).contiguous()
+            self._head_cache = (key, w, b, widths)
+        _, w, b, widths = self._head_cache
+        y = ops.conv2d(bev, w, b, 1, 1)
+        outs, o = [], 0
+        for n in widths:
+            outs.append(y[:, o:o + n])
+            o += n
+        return tuple(outs)
 
     def forward(self, imgL, imgR, calibs_fu, calibs_baseline, calibs_Proj, calibs_Proj_R=None):
         if not imgL.is_cuda:
@@ -435,7 +481,14 @@ class StereoNet(nn.Module):
 def attack_loss(cfg, outputs, disp_true, labels):
     """Scalar ascended by the attack: the reference's depth term
     (attack/DSGN/pgd_attack.py:269, 310-319) plus the fixed differentiable
-    stand-in for the unavailable upstream RPN3DLoss."""
+    stand-in for the unavailable upstream RPN3DLoss.
+
+    ``outputs['depth_preds']`` is the eval-mode [N,H,W] tensor (see ``StereoNet.forward``).  The reference's
+    lines iterate it (``for o in outputs['depth_preds']``), which for its batch size of 1 yields the single
+    [H,W] map with weight ``[0.5, 0.7, 1.0][2]`` = 1.0 and ``mask[0]``; for N > 1 those lines would weight
+    the SAMPLES 0.5/0.7/1.0 and mask every sample with sample 0's mask.  Here every pair
+    gets what the reference gives its one pair: weight 1.0, its own mask, mean over its valid pixels;
+    the per-pair terms are summed.  tests/test_gpu_e2e.py executes the reference's lines on this dict."""
     loss = 0.
     if cfg.loss_disp:
         pred = outputs['depth_preds']
@@ -443,7 +496,9 @@ def attack_loss(cfg, outputs, disp_true, labels):
         # mean over the valid pixels, written without boolean indexing (no host sync -> the
         # iteration stays CUDA-graph capturable); same value as smooth_l1(pred[mask], gt[mask]).mean()
         per = F.smooth_l1_loss(pred, disp_true, reduction='none')
-        loss = loss + (per * mask).sum() / mask.sum().clamp_min(1.0)
+        num = (per * mask).flatten(1).sum(1)
+        den = mask.flatten(1).sum(1).clamp_min(1.0)
+        loss = loss + (num / den).sum()
     if cfg.RPN3D_ENABLE:
         cls, reg, ctr = outputs['bbox_cls'], outputs['bbox_reg'], outputs['bbox_centerness']
         tgt = labels['cls']

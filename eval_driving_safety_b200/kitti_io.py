@@ -39,6 +39,80 @@ def save_image(img_norm, path, w, h):
     Image.fromarray(tensor2im(img_norm)).crop((0, 0, w, h)).save(path)
 
 
+class AsyncImageWriter:
+    """Per-iteration image dump WITHOUT stalling the attack loop.  The reference copies both
+    images to the host and PNG-encodes them inside every iteration (attack/DSGN/pgd_attack.py:357-374: a forced
+    device sync + ~30 ms of encoding per image).  Here ``submit`` only enqueues a device-to-pinned-host copy on a
+    side stream (ordered after the producing work by an event) and returns; worker threads wait for that copy,
+    convert with the reference's ``tensor2im`` (truncating uint8 cast, (0,0,w,h) crop) and write the PNG.  The
+    bytes on disk are identical to ``save_image``.  ``close()`` drains the queue."""
+
+    def __init__(self, workers=4, max_pending=64):
+        import queue
+        import threading
+        self._q = queue.Queue(maxsize=max_pending)
+        self._threads = [threading.Thread(target=self._run, daemon=True) for _ in range(max(1, workers))]
+        self._err = None
+        self._stream = None
+        for t in self._threads:
+            t.start()
+
+    def submit(self, img_norm, path, w, h):
+        """``img_norm`` [3,H,W] (or [1,3,H,W]) normalised image, CUDA or CPU tensor; snapshotted at call time."""
+        import torch
+        if self._err is not None:
+            raise self._err
+        t = img_norm.detach()
+        if t.dim() == 4:
+            t = t[0]
+        if t.is_cuda:
+            if self._stream is None:
+                self._stream = torch.cuda.Stream(device=t.device)
+            host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            snap = t.clone()                       # device-side snapshot: the loop updates the image in place next
+            self._stream.wait_stream(torch.cuda.current_stream(t.device))
+            with torch.cuda.stream(self._stream):
+                host.copy_(snap, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(self._stream)
+            snap.record_stream(self._stream)
+        else:
+            host, done = t.clone(), None
+        self._q.put((host, done, path, w, h))
+
+    def _run(self):
+        while True:
+            item = self._q.get()
+            try:
+                if item is None:
+                    return
+                host, done, path, w, h = item
+                if done is not None:
+                    done.synchronize()
+                os.makedirs(os.path.dirname(path), exist_ok=True)
+                save_image(host, path, w, h)
+            except Exception as e:          # surfaced by the next submit() / close()
+                self._err = e
+            finally:
+                self._q.task_done()
+
+    def close(self):
+        self._q.join()
+        for _ in self._threads:
+            self._q.put(None)
+        for t in self._threads:
+            t.join()
+        if self._err is not None:
+            raise self._err
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
+
+
 def iteration_paths(save_dir, k, index):
     """(left, right) file names of iteration k, pgd_attack.py:357-374."""
     base = os.path.join(save_dir, "dsgn_pgd_iters_%d" % k)

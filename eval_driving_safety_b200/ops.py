@@ -531,6 +531,159 @@ def conv3d_fork(x, weight, stride=1, transposed=False, impl=None):
     return y, (part if part.numel() else None), x2
 
 
+# ---------------------------------------------------------------------------
+# 2-D convolutions (feature extractor, BEV head): tcgen05 with in-kernel 3xTF32
+# ---------------------------------------------------------------------------
+# True: error-compensated 3xTF32 (fp32-class accuracy -- the reference computes in fp32); False: plain TF32
+CONV2D_SPLIT = int(os.environ.get("B2_CONV2D_SPLIT", "1"))
+
+
+def set_conv2d_split(flag):
+    """False / 0: plain TF32; True / 1: 3xTF32; 2: 3xTF32 with the activation tile rewritten in place as its
+    truncated value (verification of the tensor core's truncation, same results)."""
+    global CONV2D_SPLIT
+    CONV2D_SPLIT = int(flag)
+
+
+def tf32_split(t):
+    """t = hi + lo exactly; hi has its low 13 mantissa bits cleared (what kind::tf32 reads), lo = t - hi."""
+    hi = (t.view(torch.int32) & ~0x1FFF).view(torch.float32)
+    return hi, t - hi
+
+
+def _packed2d(weight, kind, split):
+    """Packed weights [S][k*k][Nout][K] for b2_conv2d (S = 2: w_hi, w_lo when ``split``).
+    kind: fwd (Nout=Co, K=Ci), dgrad_s1 (CONV on gout, flipped taps, Nout=Ci, K=Co), dgrad_s2 (DECONV on gout)."""
+    key = (id(weight), kind, bool(split))
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == (weight._version, weight.data_ptr()):
+        return hit[2]
+    w = weight.detach()
+    if kind == "fwd":
+        wp = w.permute(2, 3, 0, 1)
+    elif kind == "dgrad_s1":
+        wp = w.flip(2, 3).permute(2, 3, 1, 0)
+    elif kind == "dgrad_s2":
+        wp = w.permute(2, 3, 1, 0)
+    else:
+        raise ValueError(kind)
+    wp = wp.reshape(wp.shape[0] * wp.shape[1], wp.shape[2], wp.shape[3]).contiguous()
+    if split:
+        hi, lo = tf32_split(wp)
+        wp = torch.stack([hi, lo]).contiguous()
+    _cache_put(key, weight, wp)
+    return wp
+
+
+def _plain_weight(weight):
+    """Contiguous [Co,Ci,kh,kw] copy of a (possibly channels-last) frozen weight, cached."""
+    if weight.is_contiguous():
+        return weight.detach()
+    key = (id(weight), "plain")
+    hit = _PACK_CACHE.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == (weight._version, weight.data_ptr()):
+        return hit[2]
+    w = weight.detach().contiguous()
+    _cache_put(key, weight, w)
+    return w
+
+
+def _conv2d_call(x, wp, bias, addend, n, cin, cout, hi, wi, ks, stride, dil, mode, split):
+    lib = _lib.load()
+    if mode == 0:
+        ho, wo = (hi - 1) // stride + 1, (wi - 1) // stride + 1
+    else:
+        ho, wo = 2 * hi, 2 * wi
+    out = empty_cl2(n, cout, ho, wo, x.device)
+    if addend is not None:
+        addend = cl2(addend)
+        assert addend.shape == out.shape, (addend.shape, out.shape)
+    pix = n * ho * wo if mode == 0 else n * hi * wi
+    with _op("conv2d_tcgen05", 1, 2 * cin * cout * ks * ks * pix):
+        check(lib.b2_conv2d(_p(x), _p(wp), _p(bias), _p(addend), _p(out), n, cin, cout, hi, wi, ks, stride, dil,
+                            mode, int(split), _stream()),
+              "conv2d(k=%d,stride=%d,dil=%d,mode=%d,%d->%d)" % (ks, stride, dil, mode, cin, cout))
+    return out
+
+
+class Conv2dFn(Function):
+    """nn.Conv2d(k 1|3, stride 1|2, padding = dilation*(k//2), dilation 1|2, groups 1) forward and data
+    gradient on the sm_100a kernels; channels-last maps.  The 3-channel first layer (k3, s2) takes the exact
+    fp32 SIMT pair and reads / writes the NCHW image tensors of the attack directly.
+    ``fork``: also return a second handle on x for its other consumers (see ``conv3d_fork``)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride, dilation, fork):
+        _need_cuda(x, weight, bias)
+        if weight.requires_grad or (bias is not None and bias.requires_grad):
+            raise RuntimeError("attack path: weights are frozen; call requires_grad_(False) on the model")
+        lib = _lib.load()
+        co, ci, kh, kw = weight.shape
+        n, _, hi, wi = x.shape
+        if kh != kw or kh not in (1, 3) or stride not in (1, 2) or dilation not in (1, 2) or x.shape[1] != ci:
+            raise RuntimeError("conv2d: unsupported configuration k=%dx%d stride=%d dilation=%d" % (kh, kw, stride, dilation))
+        first = ci == 3
+        split = CONV2D_SPLIT
+        if first:
+            if not (kh == 3 and stride == 2 and dilation == 1 and bias is None):
+                raise RuntimeError("conv2d: the 3-channel layer must be k3/s2/p1/bias-free")
+            x = x.contiguous()
+            ho, wo = (hi - 1) // 2 + 1, (wi - 1) // 2 + 1
+            out = empty_cl2(n, co, ho, wo, x.device)
+            w = _plain_weight(weight)
+            with _op("conv2d_first_fwd", 1, 4 * (x.numel() + out.numel())):
+                check(lib.b2_conv2d_first_fwd(_p(x), _p(w), _p(out), n, co, hi, wi, _stream()), "conv2d_first_fwd")
+        else:
+            x = cl2(x)
+            if stride == 2 and (hi % 2 or wi % 2):
+                raise RuntimeError("conv2d: stride 2 needs even spatial dims, got %dx%d" % (hi, wi))
+            b = bias.detach() if bias is not None else None
+            out = _conv2d_call(x, _packed2d(weight, "fwd", split), b, None, n, ci, co, hi, wi, kh, stride, dilation, 0,
+                               split)
+        ctx.weight = weight
+        ctx.cfg = (n, ci, co, hi, wi, kh, stride, dilation, first, split, bool(fork))
+        ctx.set_materialize_grads(False)
+        if fork:
+            return out, x.view_as(x)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout, *extra):
+        n, ci, co, hi, wi, ks, stride, dil, first, split, fork = ctx.cfg
+        g_other = extra[0] if fork else None
+        if gout is None:
+            return g_other, None, None, None, None, None
+        lib = _lib.load()
+        g = cl2(gout)
+        if first:
+            gin = torch.empty((n, 3, hi, wi), device=g.device, dtype=torch.float32)
+            w = _plain_weight(ctx.weight)
+            with _op("conv2d_first_dgrad", 1, 4 * (g.numel() + gin.numel())):
+                check(lib.b2_conv2d_first_dgrad(_p(g), _p(w), _p(gin), n, co, hi, wi, _stream()), "conv2d_first_dgrad")
+            if g_other is not None:
+                gin = gin + g_other
+            return gin, None, None, None, None, None
+        ho, wo = g.shape[2:]
+        if stride == 1:
+            gin = _conv2d_call(g, _packed2d(ctx.weight, "dgrad_s1", split), None, g_other, n, co, ci, ho, wo, ks, 1, dil,
+                               0, split)
+        else:
+            gin = _conv2d_call(g, _packed2d(ctx.weight, "dgrad_s2", split), None, g_other, n, co, ci, ho, wo, ks, 2, 1,
+                               1, split)
+        return gin, None, None, None, None, None
+
+
+def conv2d(x, weight, bias=None, stride=1, dilation=1):
+    return Conv2dFn.apply(x, weight, bias, stride, dilation, False)
+
+
+def conv2d_fork(x, weight, bias=None, stride=1, dilation=1):
+    """(y, x2): x2 is x for its OTHER consumers; their gradient is added inside this conv's data-gradient
+    kernel (no separate accumulation pass), exactly as ``conv3d_fork``."""
+    return Conv2dFn.apply(x, weight, bias, stride, dilation, True)
+
+
 class Conv3dC1Fn(Function):
     """Conv3d(Cin -> 1, k3, p1, bias-free): bandwidth-bound SIMT head."""
 

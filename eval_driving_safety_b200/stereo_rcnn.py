@@ -146,3 +146,40 @@ def pgd_attack(model, im_left, im_right, rois_left, rois_right, targets, iters, 
         xr = attack.stereo_rcnn_pgd_step(xr.detach(), gr.contiguous(), clean_r, alpha, eps255)
         losses.append(loss.detach())
     return xl, xr, torch.stack(losses)
+
+
+def patch_attack_image(model, im_left, im_right, rois_left, rois_right, targets, patch, center_l, center_r, radius,
+                       iters=2, alpha=1e3, eps=0.1, means=(102.9801, 115.9465, 122.7717), delta_hook=None):
+    """Inner loop of the Stereo R-CNN universal-patch attack for one image,
+    attack/Stereo-RCNN/patch_attack.py:219-281 (defaults :43-46, alpha :102): blend the patch into both 600x1987
+    frames (:225-230), forward + backward, crop both gradients at the patch boxes (:260-266), clipped DESCENT
+    step (:268-270), per-channel clamp of the patch to the valid mean-subtracted 0-255 range (:272-281).
+    The image's only ground-truth box is the patch's own square (``attack.stereo_rcnn_fake_gt``, :187-207):
+    RoI 0 of both views is that square and its class target is 1.  ``patch`` [1,3,dim,dim] is updated in
+    place; ``delta_hook`` all-reduces the clipped step over the ranks.  Returns the per-iteration losses."""
+    from . import attack
+    lo = [0 - m for m in means]
+    hi = [255 - m for m in means]
+    gl, gr, _, _ = attack.stereo_rcnn_fake_gt(center_l, center_r, radius)
+    rois_left, rois_right = rois_left.clone(), rois_right.clone()
+    rois_left[0, 1:] = gl[0, 0, :4].to(rois_left)
+    rois_right[0, 1:] = gr[0, 0, :4].to(rois_right)
+    targets = dict(targets)
+    targets['cls'] = targets['cls'].clone()
+    targets['cls'][0] = 1
+    losses = []
+    for _ in range(iters):
+        attack.patch_apply(im_left, patch, center_l, radius)
+        attack.patch_apply(im_right, patch, center_r, radius)
+        xl, xr = im_left.detach().requires_grad_(True), im_right.detach().requires_grad_(True)
+        loss = model(xl, xr, rois_left, rois_right, targets)
+        g_l, g_r = torch.autograd.grad(loss, [xl, xr])
+        if delta_hook is None:
+            attack.patch_update(patch, g_l.contiguous(), g_r.contiguous(), center_l, center_r, radius, alpha, eps, lo, hi)
+        else:
+            delta = torch.empty_like(patch)
+            attack.patch_update(patch, g_l.contiguous(), g_r.contiguous(), center_l, center_r, radius, alpha, eps,
+                                delta_out=delta)
+            attack.patch_axpy(patch, delta_hook(delta), lo, hi)
+        losses.append(loss.detach())
+    return torch.stack(losses)

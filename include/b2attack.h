@@ -17,9 +17,9 @@
  *     cudaStream_t passed as `void* stream` (graph-capturable).
  *   - return 0 on success, non-zero (cudaError_t or B2_ERR_*) otherwise; the text
  *     of the last error on the calling thread is b2_last_error().  Never throws.
- *   - no global state except one-time per-process cudaFuncSetAttribute flags (dynamic smem
- *     opt-in); one process drives one GPU (the torchrun model), calls on one stream are
- *     ordered by that stream.
+ *   - no global state except a per-device table of granted cudaFuncSetAttribute dynamic-smem
+ *     opt-ins; the intended model is one process per GPU (torchrun), but a process may drive
+ *     several devices; calls on one stream are ordered by that stream.
  */
 #ifndef B2ATTACK_H
 #define B2ATTACK_H
@@ -86,6 +86,22 @@ int b2_patch_update(float* patch, const float* gL, const float* gR, int C, int H
                     int cyL, int cxL, int cyR, int cxR, int radius, float alpha, float eps,
                     const float* lo, const float* hi, float* delta_out, void* stream);
 
+/* Graph-replayable variants: the patch centres are read from DEVICE memory at run time (patch_apply_dev:
+ * int32 [n_img][2] = (cy,cx); patch_update_dev: int32 [4] = (cyL,cxL,cyR,cxR)), so one captured CUDA graph of the
+ * patch iteration serves images with different patch positions.  A box that leaves the frame cannot be rejected on
+ * the host here: patch_update_dev then leaves the patch unchanged (writes a zero step to delta_out). */
+int b2_patch_apply_dev(float* img, const float* patch, int n_img, int C, int H, int W,
+                       const int* centers_dev, int radius, void* stream);
+int b2_patch_update_dev(float* patch, const float* gL, const float* gR, int C, int H, int W,
+                        const int* centers_dev, int radius, float alpha, float eps,
+                        const float* lo, const float* hi, float* delta_out, void* stream);
+
+/* Second half of the split patch update (multi-GPU universal patch, BASELINE config 4): after the ranks have
+ * all-reduced (sum) the clipped steps written through delta_out, patch = clamp(patch - delta, lo_c, hi_c)
+ * (lo/hi HOST arrays or NULL = no clamp).  patch, delta [C,dim,dim].  With one rank
+ * b2_patch_update(delta_out) + b2_patch_axpy == b2_patch_update(NULL) bit for bit. */
+int b2_patch_axpy(float* patch, const float* delta, int C, int dim, const float* lo, const float* hi, void* stream);
+
 /* ------------------------------------------------------------------------- *
  * (1) Plane-sweep cost volume -- replaces upstream dsgn._C
  *     build_cost_volume_{forward,backward} reached from
@@ -93,7 +109,8 @@ int b2_patch_update(float* patch, const float* gL, const float* gR, int C, int H
  * layout 0 (NCDHW, the upstream layout): left/right [N,C,H,W] -> cost [N,2C,D,H,W]
  * layout 1 (channels-last, the fast internal layout): left/right [N,H,W,C],
  *          cost [N,D,H,W,2C]; C % 4 == 0.
- * shifts: device [N,D] plane disparities in feature px (>= 0, fractional ok).
+ * shifts: device [N,D] plane disparities in feature px (>= 0, fractional ok; a negative value is
+ *         treated as 0 by every kernel, so no gather can leave its row).
  * Backward is gather-form (no atomics) and therefore bitwise deterministic.
  * ------------------------------------------------------------------------- */
 int b2_cost_volume_fwd(const float* left, const float* right, const float* shifts, float* cost,
@@ -183,6 +200,36 @@ int b2_conv3d_fusion_caps(int N, int Cin, int Cout, int Di, int Hi, int Wi, int 
 int b2_conv3d_fused(const float* in, const float* wp, float* out, const float* addend, float* stat_partial,
                     int stat_mode, const float* gn_x, const float* gn_coef, int N, int Cin, int Cout,
                     int Di, int Hi, int Wi, int stride, int mode, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * 2-D convolutions of the feature extractor and the BEV head (upstream
+ * dsgn feature_extraction / bev_conv / bbox_* layers, stock nn.Conv2d -> cuDNN in
+ * the reference) reached from attack/DSGN/pgd_attack.py:308 / :336: forward and
+ * data gradient on the tcgen05 tensor cores.
+ * Channels-last activations [N,H,W,C]; kernel 1x1 or 3x3, padding = dilation*(k/2).
+ *   mode 0 CONV  : out[o] = sum_k in[o*stride + (k - k/2)*dilation] . wp[k]   (stride 1|2; dilation 2 only
+ *                  with stride 1)
+ *   mode 1 DECONV: ConvTranspose2d(k, stride 2, padding k/2, output_padding 1) = the data gradient of
+ *                  a stride-2 conv on an even-sized input; out dims = 2 * in dims.
+ * wp: packed weights [S][k*k][Cout][Cin] with S = 2 when split != 0: slab 0 = w_hi (low 13 mantissa
+ * bits cleared, exactly TF32-representable), slab 1 = w_lo = w - w_hi; S = 1 (plain w) otherwise.
+ * split != 0: error-compensated 3xTF32 (x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, operands split inside
+ * the kernel) -- fp32-class accuracy, which is what the reference computes in; split = 0: plain TF32;
+ * split = 2: as 1, and the activation tile is also rewritten as its truncated value (verification only).
+ * bias [Cout] (or NULL) and addend [same layout as out] (or NULL; the second gradient of a tensor with
+ * two consumers) are added in the epilogue.  Cin % 32 == 0, Cout % 16 == 0, Cout <= 256.
+ * ------------------------------------------------------------------------- */
+int b2_conv2d(const float* in, const float* wp, const float* bias, const float* addend, float* out,
+              int N, int Cin, int Cout, int Hi, int Wi, int ksize, int stride, int dilation, int mode,
+              int split, void* stream);
+
+/* First extractor layer, Conv2d(3 -> Cout, k3, stride 2, pad 1), exact fp32: img [N,3,H,W] (NCHW, the
+ * attack's image tensor) -> out [N,Ho,Wo,Cout] channels-last, and its data gradient back to the NCHW
+ * pixels (the gradient tensor b2_pgd_update consumes).  w [Cout][3][3][3] (the nn.Conv2d layout). */
+int b2_conv2d_first_fwd(const float* img, const float* w, float* out, int N, int Cout, int H, int W,
+                        void* stream);
+int b2_conv2d_first_dgrad(const float* gout, const float* w, float* gimg, int N, int Cout, int H, int W,
+                          void* stream);
 
 /* Cout == 1 head (classif1's last layer) and its data gradient: bandwidth-bound,
  * SIMT.  w1 [27][Cin].  fwd: in [N,D,H,W,Cin] -> out [N,D,H,W];

@@ -185,7 +185,91 @@ def handoff():
     print("wrote", path, os.path.getsize(path), "bytes")
 
 
+class _Data:
+    """Stand-in for a BoxList field: the reference only touches ``.data``."""
+
+    def __init__(self, t):
+        self.data = t
+
+
+def dsgn_fake_gt():
+    """attack/DSGN/patch_attack.py:336-354: zero the real ground truth, box 0 = the fake car."""
+    import types
+    g = torch.Generator().manual_seed(600)
+    bbox, box3d = torch.rand(5, 4, generator=g) * 1000, torch.randn(5, 7, generator=g) * 10
+    targets = [types.SimpleNamespace(bbox=_Data(bbox.clone()), box3d=_Data(box3d.clone()))]
+    env = dict(torch=torch, targets=targets)
+    exec(ref_lines("attack/DSGN/patch_attack.py", 336, 354), env)
+    return {"fake_gt": dict(bbox_in=bbox, box3d_in=box3d, bbox_out=targets[0].bbox.data, box3d_out=targets[0].box3d.data)}
+
+
+def dsgn_init_patch_resume():
+    """attack/DSGN/patch_attack.py:211-234: resume from epoch0/patch.npy, cv2.INTER_LINEAR resize of a 61x61
+    patch (trained on Stereo R-CNN) to the 77x77 of ratio 0.2; and the fresh zero patch."""
+    import tempfile
+    import cv2
+    ns = {"np": np, "os": os, "cv2": cv2}
+    exec(ref_lines("attack/DSGN/patch_attack.py", 211, 234), ns)
+    g = torch.Generator().manual_seed(601)
+    src = (torch.rand(1, 3, 61, 61, generator=g) - 0.5).numpy().astype(np.float32)
+    with tempfile.TemporaryDirectory() as d:
+        os.makedirs(os.path.join(d, "epoch0"))
+        np.save(os.path.join(d, "epoch0", "patch.npy"), src)
+        dim, radius, out = ns["init_patch"](0.2, d)
+    with tempfile.TemporaryDirectory() as d:
+        dim0, radius0, fresh = ns["init_patch"](0.2, os.path.join(d, "new"))
+    return {"init_patch": dict(src=src, dim=dim, radius=radius, out=np.asarray(out, dtype=np.float32),
+                               fresh_dim=dim0, fresh_radius=radius0, fresh_sum=float(np.abs(fresh).sum()),
+                               fresh_shape=np.array(fresh.shape))}
+
+
+def dsgn_loss_assembly():
+    """attack/DSGN/pgd_attack.py:269 (mask) and :310-319 (depth term) executed on an eval-mode output dict
+    (``depth_preds`` = ONE [1,H,W] tensor, which those lines iterate over the batch dimension)."""
+    import types
+    import warnings
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(602)
+    cfg = types.SimpleNamespace(min_depth=2.0, max_depth=40.4, PlaneSweepVolume=True, loss_disp=True)
+    disp_true = 2.0 + 38.4 * torch.rand(1, 12, 20, generator=g)
+    disp_true = disp_true * (torch.rand(1, 12, 20, generator=g) >= 0.3)
+    disp_true[0, 0, 0] = 40.4           # boundary: included (<=)
+    disp_true[0, 0, 1] = 2.0            # boundary: excluded (>)
+    pred = disp_true + torch.randn(1, 12, 20, generator=g) * 1.5      # residuals on both sides of smooth-L1's |x| = 1
+    env = dict(torch=torch, F=F, cfg=cfg, disp_true=disp_true, outputs={"depth_preds": pred.clone()}, loss=0., losses=dict())
+    exec(ref_lines("attack/DSGN/pgd_attack.py", 269, 270), env)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        exec(ref_lines("attack/DSGN/pgd_attack.py", 310, 319), env)
+    return {"loss_assembly": dict(disp_true=disp_true, pred=pred, mask=env["mask"].float(), loss=env["loss"].detach())}
+
+
+def stereo_rcnn_fake_gt():
+    """attack/Stereo-RCNN/patch_attack.py:188-207: the image's only ground-truth box = the patch square."""
+    g = torch.Generator().manual_seed(603)
+    center_l, center_r, radius = [311, 905], [311, 841], 30
+    data = [None, None, None] + [torch.rand(1, 30, 5, generator=g) * 500 for _ in range(3)] + [None, None, _Data(torch.tensor(7))]
+    env = dict(torch=torch, data=data, center_l=center_l, center_r=center_r, radius=radius)
+    exec(ref_lines("attack/Stereo-RCNN/patch_attack.py", 188, 207), env)
+    return {"srcnn_fake_gt": dict(center_l=np.array(center_l), center_r=np.array(center_r), radius=radius, gt_left=data[3],
+                                  gt_right=data[4], gt_merge=data[5], num_boxes=data[8].data)}
+
+
+def round2():
+    allc = {}
+    for fn in (dsgn_fake_gt, dsgn_init_patch_resume, dsgn_loss_assembly, stereo_rcnn_fake_gt):
+        allc.update(fn())
+    flat = {}
+    for case, d in allc.items():
+        for k, v in d.items():
+            flat["%s/%s" % (case, k)] = v.detach().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+    path = os.path.join(OUT, "attack_round2.npz")
+    np.savez_compressed(path, **flat)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(flat), "arrays")
+
+
 def main():
+    round2()
     handoff()
     allc = {}
     for fn in (dsgn_pgd, stereo_rcnn_pgd, dsgn_patch, stereo_rcnn_patch_clamp, roi_levels):

@@ -1,0 +1,142 @@
+"""GPU parity of the 2-D convolution kernels (feature extractor / BEV head layers behind
+attack/DSGN/pgd_attack.py:308, :336) through the C ABI against stock torch ops on the CPU in fp32
+(what the reference computes): forward and data gradient, every layer class of the extractor."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import max_err, rel_err
+
+pytestmark = pytest.mark.gpu
+
+# tolerances: 3xTF32 split = fp32-class (products exact, fp32 accumulation in another order);
+# plain TF32 = 10-bit mantissa operands
+TOL_SPLIT, TOL_TF32 = 2e-5, 3e-3
+
+
+@pytest.fixture(scope="module")
+def ops(built_lib):
+    from eval_driving_safety_b200 import ops
+    return ops
+
+
+# (n, cin, cout, h, w, k, stride, dilation, bias)
+CASES = [
+    (2, 32, 32, 24, 40, 3, 1, 1, False),       # firstconv[2], layer1
+    (1, 32, 64, 32, 48, 3, 2, 1, False),       # layer2 block 0 conv1 (stride 2)
+    (1, 32, 64, 32, 48, 1, 2, 1, False),       # layer2 block 0 downsample (1x1 stride 2)
+    (2, 64, 64, 19, 27, 3, 1, 1, False),       # layer2, ragged tile edges
+    (1, 64, 128, 17, 9, 1, 1, 1, False),       # layer3 downsample (1x1)
+    (1, 128, 128, 20, 24, 3, 1, 2, False),     # layer4 (dilation 2)
+    (1, 320, 128, 18, 26, 3, 1, 1, False),     # lastconv / bev_conv[0]: dgrad has 320 = 2 x 160 output channels
+    (1, 128, 32, 3, 9, 1, 1, 1, False),        # SPP branch on a tiny map
+    (1, 128, 64, 16, 40, 3, 1, 1, True),       # fused detection heads (bias)
+    (1, 128, 16, 16, 16, 3, 1, 1, True),       # narrowest N tile
+]
+
+
+@pytest.mark.parametrize("split", [True, False])
+@pytest.mark.parametrize("case", CASES)
+def test_conv2d_fwd_dgrad_vs_torch(ops, case, split):
+    n, cin, cout, h, w, k, stride, dil, has_bias = case
+    g = torch.Generator().manual_seed(hash(case) % 1000)
+    x = torch.randn(n, cin, h, w, generator=g, requires_grad=True)
+    wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    b = torch.randn(cout, generator=g) if has_bias else None
+    pad = dil * (k // 2)
+    ref = F.conv2d(x, wt, b, stride, pad, dil)
+    gy = torch.randn(ref.shape, generator=g)
+    (gx_ref,) = torch.autograd.grad(ref, x, gy)
+    ops.set_conv2d_split(split)
+    try:
+        xc = x.detach().cuda().requires_grad_(True)
+        y = ops.conv2d(xc, wt.cuda(), b.cuda() if has_bias else None, stride, dil)
+        gx = torch.autograd.grad(y, xc, gy.cuda())[0] if cout % 32 == 0 else None   # the data gradient's K is Cout
+    finally:
+        ops.set_conv2d_split(True)
+    tol = TOL_SPLIT if split else TOL_TF32
+    assert y.shape == ref.shape
+    assert rel_err(y.cpu(), ref) < tol, rel_err(y.cpu(), ref)
+    assert max_err(y.cpu(), ref) < tol * 50
+    if gx is not None:
+        assert gx.shape == gx_ref.shape
+        assert rel_err(gx.cpu(), gx_ref) < tol, rel_err(gx.cpu(), gx_ref)
+        assert max_err(gx.cpu(), gx_ref) < tol * 50
+
+
+def test_conv2d_tensor_core_truncates_tf32_operands(ops):
+    """The in-kernel split feeds the RAW fp32 activation tile as x_hi and relies on kind::tf32 ignoring the low
+    13 mantissa bits.  split = 2 rewrites the tile as (x & ~0x1fff) first: the results must be bit-identical."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 64, 40, 48, generator=g).cuda()
+    wt = (torch.randn(128, 64, 3, 3, generator=g) / 24.0).cuda()
+    try:
+        ops.set_conv2d_split(1)
+        y1 = ops.conv2d(x, wt)
+        ops.set_conv2d_split(2)
+        y2 = ops.conv2d(x, wt)
+    finally:
+        ops.set_conv2d_split(1)
+    assert torch.equal(y1, y2)
+
+
+def test_conv2d_split_is_fp32_class_on_a_kitti_size_layer(ops):
+    """64 -> 64 3x3 at 96x312 (the layer class that dominates the extractor), L+R batch: against fp64 the
+    3xTF32 result must be as accurate as a stock fp32 convolution; plain TF32 is ~1000x worse."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 64, 96, 312, generator=g)
+    wt = torch.randn(64, 64, 3, 3, generator=g) / 24.0
+    ref64 = F.conv2d(x.double(), wt.double(), None, 1, 1)
+    err32 = rel_err(F.conv2d(x, wt, None, 1, 1), ref64)
+    y3 = ops.conv2d(x.cuda(), wt.cuda())
+    ops.set_conv2d_split(False)
+    try:
+        y1 = ops.conv2d(x.cuda(), wt.cuda())
+    finally:
+        ops.set_conv2d_split(True)
+    e3, e1 = rel_err(y3.cpu(), ref64), rel_err(y1.cpu(), ref64)
+    print("rel. error vs fp64: fp32 CPU %.2e, 3xTF32 %.2e, TF32 %.2e" % (err32, e3, e1))
+    assert e3 < 4 * err32 + 1e-7 and e3 < 2e-6
+    assert e1 > 20 * e3                                   # the split is what buys the accuracy
+    assert torch.equal(y3, ops.conv2d(x.cuda(), wt.cuda()))   # deterministic
+
+
+def test_conv2d_fork_adds_the_other_gradient(ops):
+    g = torch.Generator().manual_seed(9)
+    for (cin, cout, stride, k) in [(64, 64, 1, 3), (32, 64, 2, 3), (32, 64, 2, 1)]:
+        x = torch.randn(1, cin, 24, 32, generator=g).cuda().requires_grad_(True)
+        wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+        y, x2 = ops.conv2d_fork(x, wt, None, stride, 1)
+        other = torch.randn(x.shape, generator=g).cuda()
+        gy = torch.randn(y.shape, generator=g).cuda()
+        (gx,) = torch.autograd.grad([y, (x2 * other).sum()], x, [gy, torch.ones((), device='cuda')])
+        (gplain,) = torch.autograd.grad(ops.conv2d(x, wt, None, stride, 1), x, gy)
+        assert max_err(gx, gplain + other) < 1e-5
+
+
+@pytest.mark.parametrize("dims", [(2, 32, 64), (1, 384, 1248), (1, 31, 45)])
+def test_first_layer_fwd_dgrad_vs_torch(ops, dims):
+    n, h, w = dims
+    g = torch.Generator().manual_seed(h)
+    x = torch.randn(n, 3, h, w, generator=g, requires_grad=True)
+    wt = torch.randn(32, 3, 3, 3, generator=g) / 27 ** 0.5
+    ref = F.conv2d(x, wt, None, 2, 1)
+    gy = torch.randn(ref.shape, generator=g)
+    (gx_ref,) = torch.autograd.grad(ref, x, gy)
+    xc = x.detach().cuda().requires_grad_(True)
+    y = ops.conv2d(xc, wt.cuda(), None, 2, 1)
+    (gx,) = torch.autograd.grad(y, xc, gy.cuda())
+    assert gx.is_contiguous() and gx.shape == x.shape          # NCHW, what b2_pgd_update reads
+    assert max_err(y.cpu(), ref) < 2e-5 and max_err(gx.cpu(), gx_ref) < 2e-5
+
+
+def test_conv2d_rejects_unsupported(ops):
+    x = torch.randn(1, 24, 8, 8).cuda()
+    with pytest.raises(RuntimeError):
+        ops.conv2d(x, torch.randn(32, 24, 3, 3).cuda())          # Cin % 32
+    with pytest.raises(RuntimeError):
+        ops.conv2d(torch.randn(1, 32, 8, 8).cuda(), torch.randn(32, 32, 5, 5).cuda())
+    with pytest.raises(RuntimeError):
+        ops.conv2d(torch.randn(1, 32, 9, 8).cuda(), torch.randn(32, 32, 3, 3).cuda(), None, 2, 1)   # odd dims, stride 2
+    with pytest.raises(RuntimeError):
+        ops.conv2d(torch.randn(1, 32, 8, 8), torch.randn(32, 32, 3, 3))                            # CPU tensors
