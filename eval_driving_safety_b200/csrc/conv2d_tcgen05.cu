@@ -45,6 +45,7 @@ struct C2Params {
     int ks, dil;
     int mode;                  // 0 conv stride 1, 1 conv stride 2, 2 transposed stride 2
     int split;                 // 3xTF32
+    int stack;                 // split: x_hi meets [w_hi ; w_lo] in ONE MMA of N = 2 nt (two accumulator halves)
     int rewrite_hi;            // split: also rewrite the landed A tile as its TF32-truncated value (not needed if the
                                // tensor core ignores the low 13 mantissa bits itself; kept for A/B verification)
     int tiles_w, tiles_h;
@@ -165,7 +166,7 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             // back to back in smem, so ONE MMA of N = 2 nt multiplies x_hi with both (A is read from smem once
             // instead of twice -- the stage is smem-bandwidth bound), a second MMA of N = nt adds x_lo*w_hi
             const uint32_t idesc = umma_idesc_tf32(128, p.nt), idesc2 = umma_idesc_tf32(128, 2 * p.nt);
-            const int acc_cols = p.split ? 2 * p.nt : p.nt;
+            const int acc_cols = p.stack ? 2 * p.nt : p.nt;
             int stage = 0; uint32_t phase = 0;
             long long it = 0;
             for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -181,12 +182,21 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                     tc_fence_after();
                     const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
                     const uint64_t a_hi = umma_desc_sw128(sa), b_hi = umma_desc_sw128(sa + a_region);
-                    if (p.split) {
+                    if (p.split && p.stack) {
                         const uint64_t a_lo = umma_desc_sw128(sa + kC2ABytes);
 #pragma unroll
                         for (int k = 0; k < kC2K / 8; ++k) umma_tf32(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc2, (s | k) != 0);
 #pragma unroll
                         for (int k = 0; k < kC2K / 8; ++k) umma_tf32(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                    } else if (p.split) {                         // one accumulator, small terms first
+                        const uint64_t a_lo = umma_desc_sw128(sa + kC2ABytes),
+                                       b_lo = umma_desc_sw128(sa + a_region + (uint32_t)p.b_bytes);
+#pragma unroll
+                        for (int k = 0; k < kC2K / 8; ++k) umma_tf32(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, (s | k) != 0);
+#pragma unroll
+                        for (int k = 0; k < kC2K / 8; ++k) umma_tf32(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < kC2K / 8; ++k) umma_tf32(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
                     } else {
 #pragma unroll
                         for (int k = 0; k < kC2K / 8; ++k) umma_tf32(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (s | k) != 0);
@@ -220,13 +230,13 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
                 tc_fence_after();
             }
-            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * (p.split ? 2 * p.nt : p.nt));
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * (p.stack ? 2 * p.nt : p.nt));
             const float* bptr = bias ? bias + tc.nti * p.nt : nullptr;
             for (int c0 = 0; c0 < p.nt; c0 += 16) {
                 uint32_t r[16];
                 if (active) {
                     tmem_ld16(taddr + c0, r);
-                    if (p.split) {                                // + the x_hi*w_lo half of the accumulator
+                    if (p.stack) {                                // + the x_hi*w_lo half of the accumulator
                         uint32_t r2[16];
                         tmem_ld16(taddr + p.nt + c0, r2);
                         tmem_ld_wait();
@@ -304,7 +314,7 @@ int conv2d_tcgen05_launch(const float* in, const float* wp, const float* bias, c
                           int N, int Cin, int Cout, int Hi, int Wi, int ks, int stride, int dil, int mode, int split,
                           cudaStream_t st) {
     // N tile: <= 256 columns per MMA; with the split an accumulator is 2 nt columns wide and double buffered
-    const int nt_max = split ? 128 : 256;
+    const int nt_max = (split == 1 || split == 2) ? 128 : 256;
     int n_tiles = 0;
     for (int t = 1; t <= 16 && !n_tiles; ++t)
         if (Cout % t == 0 && (Cout / t) % 16 == 0 && Cout / t <= nt_max) n_tiles = t;
@@ -334,8 +344,9 @@ int conv2d_tcgen05_launch(const float* in, const float* wp, const float* bias, c
     if (p.stages > kC2MaxStages) p.stages = kC2MaxStages;
     if (p.stages < 2) { set_error("conv2d(tcgen05): stage of %d bytes does not fit twice", p.stage_bytes); return B2_ERR_UNSUPPORTED; }
     p.tmem_cols = 32;
-    while (p.tmem_cols < 2 * (p.split ? 2 : 1) * p.nt) p.tmem_cols *= 2;
-    p.rewrite_hi = split == 2 ? 1 : 0;
+    p.stack = (split == 1 || split == 2) ? 1 : 0;
+    p.rewrite_hi = split >= 2 ? 1 : 0;
+    while (p.tmem_cols < 2 * (p.stack ? 2 : 1) * p.nt) p.tmem_cols *= 2;
     p.total_tiles = (long long)p.n_tiles * (p.mode == 2 ? 4 : 1) * N * p.tiles_h * p.tiles_w;
 
     CUtensorMap map_a, map_b;

@@ -69,30 +69,61 @@ class PgdIterationGraph:
                 self.losses = [self._iteration(*self.s)]
             else:
                 cap = torch.cuda.current_stream()
-                self.losses = []
+                self.losses, grads = [], []
+                joint = self.norm == 'linf' and 2 * self.lanes <= 4
                 for st, bufs in zip(self.streams, self.sl):
                     st.wait_stream(cap)
                     with torch.cuda.stream(st):
-                        self.losses.append(self._iteration(*bufs))
+                        if joint:
+                            loss, gL, gR = self._grads(bufs[0], bufs[1], bufs[4])
+                            grads.append((gL, gR))
+                            self.losses.append(loss)
+                        else:
+                            self.losses.append(self._iteration(*bufs))
                 for st in self.streams:
                     cap.wait_stream(st)
+                if joint:
+                    # ONE pixel-update launch for all lanes (L and R image of every pair): 92 MB per launch
+                    # instead of 46 MB -- the kernel is launch-latency bound at one pair
+                    self._update_joint(self.sl, grads)
         self.loss = self.losses[0]
         self.launches_per_step = (ops.LAUNCH_COUNT - n0) // self.lanes
         for bufs in self.sl:
             for dst, src in zip(bufs, (xL, xR, cL, cR, disp)):
                 dst.copy_(src)
 
-    def _iteration(self, xL, xR, cL, cR, disp):
+    def _grads(self, xL, xR, disp):
         a, b = xL.detach().requires_grad_(True), xR.detach().requires_grad_(True)
         out = self.model(a, b, self.calib[0], self.calib[1], self.calib[2], calibs_Proj_R=self.calib[3])
         loss = dsgn.attack_loss(self.cfg, out, disp, self.labels)
         gL, gR = torch.autograd.grad(loss, [a, b])
+        return loss.detach(), gL.contiguous(), gR.contiguous()
+
+    def _update_joint(self, bufs_list, grads):
+        xs, gs, cs = [], [], []
+        for bufs, (gL, gR) in zip(bufs_list, grads):
+            xs += [bufs[0], bufs[1]]; gs += [gL, gR]; cs += [bufs[2], bufs[3]]
+        attack._pgd_update_sets(xs, gs, cs, xs, self.alpha, self.eps, attack.IMAGENET_MEAN, attack.IMAGENET_STD, 0.0, 1.0)
+
+    def iterate_eager(self, pairs):
+        """Eager (no graph) iteration of up to 2 pairs with the launch shapes of the captured graph -- one joint
+        pixel update for all of them.  Used by bench.py's live kernel timing."""
+        assert self.norm == 'linf' and len(pairs) <= 2
+        losses, grads = [], []
+        for p in pairs:
+            loss, gL, gR = self._grads(p[0], p[1], p[4])
+            losses.append(loss); grads.append((gL, gR))
+        self._update_joint(pairs, grads)
+        return losses
+
+    def _iteration(self, xL, xR, cL, cR, disp):
+        loss, gL, gR = self._grads(xL, xR, disp)
         if self.norm == 'linf':
-            attack.pgd_step_pair(xL, gL.contiguous(), cL, xR, gR.contiguous(), cR, self.alpha, self.eps, inplace=True)
+            attack.pgd_step_pair(xL, gL, cL, xR, gR, cR, self.alpha, self.eps, inplace=True)
         else:
-            attack.pgd_step(xL, gL.contiguous(), cL, self.alpha, self.eps, norm=self.norm, out=xL)
-            attack.pgd_step(xR, gR.contiguous(), cR, self.alpha, self.eps, norm=self.norm, out=xR)
-        return loss.detach()
+            attack.pgd_step(xL, gL, cL, self.alpha, self.eps, norm=self.norm, out=xL)
+            attack.pgd_step(xR, gR, cR, self.alpha, self.eps, norm=self.norm, out=xR)
+        return loss
 
     def _for_calib(self, calib, example):
         """The engine that serves ``calib``: this one, or a sibling captured for that calibration."""

@@ -69,8 +69,8 @@ def _conv2d_problem(m):
     if m.in_channels == 3:
         if not (k == 3 and m.stride[0] == 2 and m.bias is None and m.out_channels % 8 == 0 and m.out_channels <= 64):
             return "3-channel layer other than k3 s2 p1 bias-free"
-    elif m.in_channels % 32 or m.out_channels % 32:
-        return "channels %d -> %d (multiples of 32)" % (m.in_channels, m.out_channels)
+    elif m.in_channels % 32:
+        return "%d input channels (multiples of 32, or the 3-channel first layer)" % m.in_channels
     return None
 
 

@@ -45,6 +45,7 @@ def _stream():
 
 # -- launch accounting / live kernel timing (bench.py) -------------------------
 LAUNCH_COUNT = 0          # kernels of libb2attack.so launched so far
+PROFILE_SPIN_CYCLES = int(os.environ.get("B2_PROFILE_SPIN", "200000"))   # ~0.1 ms device-side spin before each timed launch
 _PROFILE = None           # name -> [(start_event, end_event, work)] while profiling
 
 
@@ -60,6 +61,11 @@ class _op:
         if _PROFILE is not None:
             self.e0 = torch.cuda.Event(enable_timing=True)
             self.e1 = torch.cuda.Event(enable_timing=True)
+            # The bracketed launch must already be QUEUED when the stream reaches e0, otherwise the pair also
+            # times the host (Python + ctypes + tensor-map encode, ~30 us) -- a cost the graph-replayed timed path
+            # does not have.  A device-side spin ahead of e0 lets the host run ahead of the GPU.
+            if PROFILE_SPIN_CYCLES:
+                torch.cuda._sleep(PROFILE_SPIN_CYCLES)
             self.e0.record()
         return self
 
@@ -674,7 +680,29 @@ class Conv2dFn(Function):
         return gin, None, None, None, None, None
 
 
+def _padded_out_channels(weight, bias):
+    """Weight / bias zero-padded along the OUTPUT channels to a multiple of 32 (the tensor-core N tile and the data
+    gradient's K chunk), cached per frozen weight: e.g. the 4- and 28-channel detection heads."""
+    key = (id(weight), "padout")
+    hit = _PACK_CACHE.get(key)
+    bver = None if bias is None else (bias._version, bias.data_ptr())
+    if hit is not None and hit[0]() is weight and hit[1] == (weight._version, weight.data_ptr()) and hit[2][2] == bver:
+        return hit[2][0], hit[2][1]
+    co = weight.shape[0]
+    pad = (-co) % 32
+    w = torch.cat([weight.detach(), weight.new_zeros((pad,) + tuple(weight.shape[1:]))], 0).contiguous()
+    b = None if bias is None else torch.cat([bias.detach(), bias.new_zeros(pad)], 0).contiguous()
+    _cache_put(key, weight, (w, b, bver))
+    return w, b
+
+
 def conv2d(x, weight, bias=None, stride=1, dilation=1):
+    co = weight.shape[0]
+    if weight.shape[1] != 3 and co % 32:
+        if weight.requires_grad:
+            raise RuntimeError("attack path: weights are frozen; call requires_grad_(False) on the model")
+        w, b = _padded_out_channels(weight, bias)
+        return Conv2dFn.apply(x, w, b, stride, dilation, False)[:, :co]
     return Conv2dFn.apply(x, weight, bias, stride, dilation, False)
 
 

@@ -74,6 +74,8 @@ def run_pgd(args):
     if writer is not None:
         writer.close()
     stats = parallel.gather_stats(rows, args.pairs)
+    if rank == 0 and getattr(args, "stats_out", None):
+        torch.save(stats.cpu(), args.stats_out)
     if rank == 0:
         print("pair  loss_0  loss_K  linf  l2  frac_changed")
         for r in stats.tolist():
@@ -223,6 +225,7 @@ def main(argv=None):
     a.add_argument("--alpha", type=float, default=1 / 255)               # :54
     a.add_argument("--eps", type=float, default=0.3)                     # :55
     a.add_argument("--norm", default="linf", choices=["linf", "l2"])
+    a.add_argument("--stats-out", default=None, help="rank 0 saves the gathered per-pair statistics [pairs, fields] here")
     b = sub.add_parser("patch")
     b.add_argument("--iter", type=int, default=2)                        # patch_attack.py:53
     b.add_argument("--eps", type=float, default=8 / 255)                 # :54

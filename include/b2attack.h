@@ -215,7 +215,8 @@ int b2_conv3d_fused(const float* in, const float* wp, float* out, const float* a
  * bits cleared, exactly TF32-representable), slab 1 = w_lo = w - w_hi; S = 1 (plain w) otherwise.
  * split != 0: error-compensated 3xTF32 (x_hi*w_hi + x_hi*w_lo + x_lo*w_hi, operands split inside
  * the kernel) -- fp32-class accuracy, which is what the reference computes in; split = 0: plain TF32;
- * split = 2: as 1, and the activation tile is also rewritten as its truncated value (verification only).
+ * split = 2: as 1, and the activation tile is also rewritten as its truncated value (verification only);
+ * split = 3: the three products accumulate into ONE accumulator, small terms first (A/B of the summation order).
  * bias [Cout] (or NULL) and addend [same layout as out] (or NULL; the second gradient of a tensor with
  * two consumers) are added in the epilogue.  Cin % 32 == 0, Cout % 16 == 0, Cout <= 256.
  * ------------------------------------------------------------------------- */

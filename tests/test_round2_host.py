@@ -152,7 +152,7 @@ def test_swap_modules_validates_every_hyperparameter():
     bad = [nn.Conv3d(32, 32, 3, 1, 1, dilation=2, bias=False), nn.Conv3d(32, 32, 3, 1, 1, groups=2, bias=False),
            nn.Conv3d(32, 32, 5, 1, 2, bias=False), nn.ConvTranspose3d(32, 32, 3, 2, 1, output_padding=0, bias=False),
            nn.ConvTranspose3d(32, 32, 3, 1, 1, bias=False), nn.Conv2d(32, 32, 3, 1, 0, bias=False),
-           nn.Conv2d(24, 32, 3, 1, 1, bias=False), nn.Conv2d(32, 32, 3, 2, 2, 2, bias=False),
+           nn.Conv2d(24, 32, 3, 1, 1, bias=False), nn.Conv2d(32, 32, 3, 2, 2, 2, bias=False), nn.Conv2d(3, 32, 3, 1, 1, bias=False),
            nn.GroupNorm(4, 32, affine=False)]
     for layer in bad:
         with pytest.raises(ValueError):
