@@ -42,9 +42,8 @@ SIGNATURES = {
                                   c_int, c_vp]),
     "b2_grid_plan_sort": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "b2_grid_sample_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_int, c_int, c_int, c_vp]),
-    "b2_grid_sample_bwd_tiled": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
-    "b2_lift_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
-                            c_int, c_int, c_int, c_vp]),
+    "b2_lift_fwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_i64, c_int,
+                            c_vp]),
     "b2_conv3d": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_int, c_vp]),
     "b2_conv3d_fusion_caps": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),

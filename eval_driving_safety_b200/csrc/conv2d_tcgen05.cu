@@ -310,6 +310,229 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     }
 }
 
+// =============================================================================================
+// Stride-1 3x3 fast path ("halo" kernel): the bulk of the extractor.  The kernel above reloads -- and, with the
+// split, re-splits -- the 16 KB A box for every tap.  Here, per (kw, 32-channel chunk) "generation", ONE
+// {32 ch, 8 w, 16 + 2 dil rows} halo box is loaded and split once; the three kh taps read that smem tile at row
+// offsets 0 / dil / 2 dil (= whole 1024 B swizzle atoms, so only the descriptor's start address moves).  The
+// weight tiles (w_hi, w_lo pairs) stream through their own ring.  Per tap the smem traffic of the A side drops
+// from 16 KB (TMA) + 32 KB (split) to a third of 18 KB + 36 KB; the kernel is smem-bandwidth bound, so that is
+// what buys time.
+// =============================================================================================
+constexpr int kC2HaloNA = 2;               // A ring slots
+constexpr int kC2HaloMaxNW = 12;           // weight ring slots
+
+struct C2HaloParams {
+    C2Params c;
+    int a_rows, a_bytes, a_slot, w_slot, nw;
+};
+
+__global__ void __launch_bounds__(kC2Threads, 1)
+conv2d_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                           float* __restrict__ out, const float* __restrict__ bias, const float* __restrict__ addend,
+                           const C2HaloParams hp) {
+    const C2Params& p = hp.c;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[3 * kC2HaloNA + 2 * kC2HaloMaxNW + 4];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t a_base = smem_base, w_base = smem_base + (uint32_t)(kC2HaloNA * hp.a_slot);
+    const uint32_t bar0 = smem_u32(bars);
+    auto fullA = [&](int s) { return bar0 + 8u * s; };
+    auto emptyA = [&](int s) { return bar0 + 8u * (kC2HaloNA + s); };
+    auto readyA = [&](int s) { return bar0 + 8u * (2 * kC2HaloNA + s); };
+    auto fullW = [&](int s) { return bar0 + 8u * (3 * kC2HaloNA + s); };
+    auto emptyW = [&](int s) { return bar0 + 8u * (3 * kC2HaloNA + kC2HaloMaxNW + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * kC2HaloNA + 2 * kC2HaloMaxNW + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * kC2HaloNA + 2 * kC2HaloMaxNW + 2 + a); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kC2HaloNA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); mbar_init(readyA(s), 128); }
+        for (int s = 0; s < hp.nw; ++s) { mbar_init(fullW(s), 1); mbar_init(emptyW(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const int ngen = 3 * p.kchunks;            // (kw, chunk) generations per tile
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t aslot = 0, aphase = 0, wslot = 0, wphase = 0;
+            const uint32_t wtx = (uint32_t)hp.w_slot;
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+                const C2Tile tc = c2_decode(p, t);
+                for (int g = 0; g < ngen; ++g) {
+                    const int kw = g / p.kchunks, kc = g % p.kchunks;
+                    mbar_wait(emptyA(aslot), aphase ^ 1);
+                    mbar_expect_tx(fullA(aslot), (uint32_t)hp.a_bytes);
+                    tma_load_4d(a_base + aslot * (uint32_t)hp.a_slot, &map_a, fullA(aslot), kc * kC2K,
+                                tc.w0 + (kw - 1) * p.dil, tc.h0 - p.dil, tc.n);
+                    if (++aslot == kC2HaloNA) { aslot = 0; aphase ^= 1; }
+                    for (int kh = 0; kh < 3; ++kh) {
+                        const int tap = kh * 3 + kw;
+                        mbar_wait(emptyW(wslot), wphase ^ 1);
+                        mbar_expect_tx(fullW(wslot), wtx);
+                        const uint32_t wa = w_base + wslot * (uint32_t)hp.w_slot;
+                        tma_load_2d(wa, &map_b, fullW(wslot), kc * kC2K, tap * p.Cout + tc.nti * p.nt);
+                        if (p.split)
+                            tma_load_2d(wa + (uint32_t)p.b_bytes, &map_b, fullW(wslot), kc * kC2K,
+                                        (9 + tap) * p.Cout + tc.nti * p.nt);
+                        if (++wslot == (uint32_t)hp.nw) { wslot = 0; wphase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_tf32(128, p.nt), idesc2 = umma_idesc_tf32(128, 2 * p.nt);
+            const int acc_cols = p.stack ? 2 * p.nt : p.nt;
+            uint32_t aslot = 0, aphase = 0, wslot = 0, wphase = 0;
+            long long it = 0;
+            for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+                const int acc = (int)(it & 1);
+                mbar_wait(tempty_bar(acc), (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
+                for (int g = 0; g < ngen; ++g) {
+                    mbar_wait(p.split ? readyA(aslot) : fullA(aslot), aphase);
+                    tc_fence_after();
+                    const uint32_t sa = a_base + aslot * (uint32_t)hp.a_slot;
+#pragma unroll
+                    for (int kh = 0; kh < 3; ++kh) {
+                        mbar_wait(fullW(wslot), wphase);
+                        tc_fence_after();
+                        const uint32_t off = (uint32_t)(kh * p.dil) * 1024u;          // kh * dil rows of 8 pixels
+                        const uint64_t a_hi = umma_desc_sw128(sa + off);
+                        const uint64_t b_hi = umma_desc_sw128(w_base + wslot * (uint32_t)hp.w_slot);
+                        const uint32_t first = (uint32_t)(g | kh);
+                        if (p.split && p.stack) {
+                            const uint64_t a_lo = umma_desc_sw128(sa + (uint32_t)hp.a_bytes + off);
+#pragma unroll
+                            for (int k = 0; k < kC2K / 8; ++k) umma_tf32(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc2, (first | (uint32_t)k) != 0);
+#pragma unroll
+                            for (int k = 0; k < kC2K / 8; ++k) umma_tf32(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, 1u);
+                        } else if (p.split) {
+                            const uint64_t a_lo = umma_desc_sw128(sa + (uint32_t)hp.a_bytes + off),
+                                           b_lo = umma_desc_sw128(w_base + wslot * (uint32_t)hp.w_slot + (uint32_t)p.b_bytes);
+#pragma unroll
+                            for (int k = 0; k < kC2K / 8; ++k) umma_tf32(tmem_d, a_lo + 2 * k, b_hi + 2 * k, idesc, (first | (uint32_t)k) != 0);
+#pragma unroll
+                            for (int k = 0; k < kC2K / 8; ++k) umma_tf32(tmem_d, a_hi + 2 * k, b_lo + 2 * k, idesc, 1u);
+#pragma unroll
+                            for (int k = 0; k < kC2K / 8; ++k) umma_tf32(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, 1u);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < kC2K / 8; ++k) umma_tf32(tmem_d, a_hi + 2 * k, b_hi + 2 * k, idesc, (first | (uint32_t)k) != 0);
+                        }
+                        umma_commit(emptyW(wslot));
+                        if (++wslot == (uint32_t)hp.nw) { wslot = 0; wphase ^= 1; }
+                    }
+                    umma_commit(emptyA(aslot));
+                    if (++aslot == kC2HaloNA) { aslot = 0; aphase ^= 1; }
+                }
+                umma_commit(tfull_bar(acc));
+            }
+        }
+        __syncwarp();
+    } else if (warp < 6) {
+        // ===================== epilogue =====================
+        const int lane_grp = warp & 3;
+        const int m = lane_grp * 32 + lane;
+        const int hl = m / kC2TileW, wl = m % kC2TileW;
+        long long it = 0;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
+            const C2Tile tc = c2_decode(p, t);
+            const int h = tc.h0 + hl, w = tc.w0 + wl;
+            const bool ok = h < p.Ht && w < p.Wt;
+            const long long off = (((long long)tc.n * p.Ho + h) * p.Wo + w) * p.out_cstride + tc.nti * p.nt;
+            float* optr = out + off;
+            const float* aptr = addend ? addend + off : nullptr;
+            const float* bptr = bias ? bias + tc.nti * p.nt : nullptr;
+            const int acc = (int)(it & 1);
+            mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * (p.stack ? 2 * p.nt : p.nt));
+            for (int c0 = 0; c0 < p.nt; c0 += 16) {
+                uint32_t r[16];
+                tmem_ld16(taddr + c0, r);
+                if (p.stack) {
+                    uint32_t r2[16];
+                    tmem_ld16(taddr + p.nt + c0, r2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+                } else {
+                    tmem_ld_wait();
+                }
+                if (ok) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
+                                               __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
+                        if (bptr) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(bptr + c0) + q);
+                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+                        }
+                        if (aptr) {
+                            const float4 a = __ldg(reinterpret_cast<const float4*>(aptr + c0) + q);
+                            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
+                        }
+                        *reinterpret_cast<float4*>(optr + c0 + 4 * q) = v;
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(tempty_bar(acc));
+        }
+    } else if (p.split) {
+        // ===================== operand split: the whole halo tile, once per generation =====================
+        const int tid = threadIdx.x - 192;
+        const int n4 = hp.a_bytes / 16;
+        uint32_t aslot = 0, aphase = 0;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+            for (int g = 0; g < ngen; ++g) {
+                mbar_wait(fullA(aslot), aphase);
+                float4* A = reinterpret_cast<float4*>(smem_gen + (size_t)aslot * hp.a_slot);
+                float4* L = A + n4;
+                for (int idx = tid; idx < n4; idx += 128) {
+                    const float4 v = A[idx];
+                    float4 hi, lo;
+                    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u); lo.x = v.x - hi.x;
+                    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u); lo.y = v.y - hi.y;
+                    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u); lo.z = v.z - hi.z;
+                    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u); lo.w = v.w - hi.w;
+                    if (p.rewrite_hi) A[idx] = hi;
+                    L[idx] = lo;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive(readyA(aslot));
+                if (++aslot == kC2HaloNA) { aslot = 0; aphase ^= 1; }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
 int conv2d_tcgen05_launch(const float* in, const float* wp, const float* bias, const float* addend, float* out,
                           int N, int Cin, int Cout, int Hi, int Wi, int ks, int stride, int dil, int mode, int split,
                           cudaStream_t st) {
@@ -349,12 +572,26 @@ int conv2d_tcgen05_launch(const float* in, const float* wp, const float* bias, c
     while (p.tmem_cols < 2 * (p.stack ? 2 : 1) * p.nt) p.tmem_cols *= 2;
     p.total_tiles = (long long)p.n_tiles * (p.mode == 2 ? 4 : 1) * N * p.tiles_h * p.tiles_w;
 
+    static int halo_env = -1;
+    if (halo_env < 0) { const char* e = getenv("B2_CONV2D_HALO"); halo_env = (e && e[0] == '0') ? 0 : 1; }
+    const bool halo = halo_env && p.mode == 0 && ks == 3;
+    C2HaloParams hp{};
+    if (halo) {
+        hp.a_rows = kC2TileH + 2 * dil;
+        hp.a_bytes = hp.a_rows * kC2TileW * 128;
+        hp.a_slot = (p.split ? 2 : 1) * hp.a_bytes;
+        hp.w_slot = (p.split ? 2 : 1) * p.b_bytes;
+        hp.nw = (208 * 1024 - kC2HaloNA * hp.a_slot) / hp.w_slot;
+        if (hp.nw > kC2HaloMaxNW) hp.nw = kC2HaloMaxNW;
+        if (hp.nw < 2) { set_error("conv2d(tcgen05,halo): weight tiles of %d bytes do not fit", hp.w_slot); return B2_ERR_UNSUPPORTED; }
+    }
+
     CUtensorMap map_a, map_b;
     {
         cuuint64_t gdim[4] = {(cuuint64_t)Cin, (cuuint64_t)Wi, (cuuint64_t)Hi, (cuuint64_t)N};
         cuuint64_t gstr[3] = {(cuuint64_t)Cin * 4, (cuuint64_t)Wi * Cin * 4, (cuuint64_t)Hi * Wi * Cin * 4};
         const cuuint32_t s = (p.mode == 1) ? 2 : 1;
-        cuuint32_t box[4] = {(cuuint32_t)kC2K, (cuuint32_t)kC2TileW * s, (cuuint32_t)kC2TileH * s, 1};
+        cuuint32_t box[4] = {(cuuint32_t)kC2K, (cuuint32_t)kC2TileW * s, (cuuint32_t)(halo ? hp.a_rows : kC2TileH * s), 1};
         cuuint32_t estr[4] = {1, s, s, 1};
         CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -371,11 +608,20 @@ int conv2d_tcgen05_launch(const float* in, const float* wp, const float* bias, c
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv2d(tcgen05): cuTensorMapEncodeTiled(B) failed: %d", (int)r); return B2_ERR_DRIVER; }
     }
+    const int grid = (int)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
+    if (halo) {
+        hp.c = p;
+        const int smem_h = kC2HaloNA * hp.a_slot + hp.nw * hp.w_slot + 1024;
+        static SmemOptIn optin_h;
+        cudaError_t eh = ensure_dynamic_smem(optin_h, conv2d_halo_tcgen05_kernel, 209 * 1024 + 1024);
+        if (eh != cudaSuccess) { set_error("conv2d(tcgen05,halo): cudaFuncSetAttribute: %s", cudaGetErrorString(eh)); return (int)eh; }
+        conv2d_halo_tcgen05_kernel<<<grid, kC2Threads, smem_h, st>>>(map_a, map_b, out, bias, addend, hp);
+        return check_launch("conv2d(tcgen05,halo)");
+    }
     const int smem = p.stages * p.stage_bytes + 1024;
     static SmemOptIn optin;
     cudaError_t e = ensure_dynamic_smem(optin, conv2d_tcgen05_kernel, 209 * 1024 + 1024);
     if (e != cudaSuccess) { set_error("conv2d(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    const int grid = (int)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
     conv2d_tcgen05_kernel<<<grid, kC2Threads, smem, st>>>(map_a, map_b, out, bias, addend, p);
     return check_launch("conv2d(tcgen05)");
 }

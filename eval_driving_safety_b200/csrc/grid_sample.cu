@@ -117,60 +117,65 @@ grid_sample2d_fwd_kernel(const float4* __restrict__ in, const float* __restrict_
 // 32-channel image feature sampled bilinearly at the same (u, v), written side by side into one [.., 96]
 // voxel row).  One kernel instead of two: the grid is read once, every output row is written once as three
 // full 128 B lines.
-// Work mapping.  The generic kernel above walks the voxels in memory order (x fastest); neighbouring x voxels
-// sample (36 / z) feature pixels apart, so they share no corner rows over most of the frustum, every corner read
-// is a separate 256 B row from L2 (ncu, round 1: L1 hit 25 %, 2.4 GB of L2->SM traffic for 0.4 GB of DRAM
-// traffic: L2-bandwidth bound).  Consecutive Z voxels of one (y, x) column, however, drift by only
-// 36 x / z^2 pixels (less than the x spacing everywhere inside the +-40 degree frustum) and 4 of them share a
-// plane pair: a block therefore owns ZB consecutive z of XB consecutive x, and most of its 8 x 16 corner rows
-// are L1 hits.
+// What bounds this op (measured, round 2): NOT the memory system.  In the generic kernels above 16 lanes own a
+// voxel and EVERY lane recomputes the corner indices, validity masks, weights and addresses (~190 of its ~270
+// instructions) for its one float4 per corner: 88 M warp instructions for the PSV sample = ~160 us of issue
+// time at IPC 2, the measured 190 us.  Re-ordering the voxels for L1 reuse (blocks of consecutive Z: the
+// corner rows of a column drift by less than a pixel per step) changed nothing -- 0.304-0.312 ms for every
+// block shape, tools/bench_lift.py.  Here 4 lanes own a voxel and each carries 4 float4 per corner (lane l ->
+// float4 l, l+4, l+8, l+12, so that one load instruction of the 4 lanes still covers 64 contiguous bytes):
+// the index arithmetic is amortised over 4x the data.
 // =============================================================================================
-template <int ZB, int XB>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
 lift_fwd_kernel(const float4* __restrict__ psv, const float4* __restrict__ img, const float* __restrict__ grid,
-                float* __restrict__ out, int N, int D, int H, int W, int Hi, int Wi, int Z, int Y, int X, int align) {
-    constexpr int LPV = 16, LPI = 8, CO = 96;
-    static_assert(ZB * XB == 16, "16 voxels per block");
-    const int lane = threadIdx.x % LPV, j = threadIdx.x / LPV;
-    const int xblocks = (X + XB - 1) / XB, zblocks = (Z + ZB - 1) / ZB;
-    int b = blockIdx.x;
-    const int xb = b % xblocks; b /= xblocks;
-    const int zb = b % zblocks; b /= zblocks;
-    const int y = b % Y, n = b / Y;
-    const int z = zb * ZB + j / XB, x = xb * XB + j % XB;
-    if (z >= Z || x >= X) return;
-    const int64_t v = (((int64_t)n * Z + z) * Y + y) * X + x;
+                float* __restrict__ out, int N, int D, int H, int W, int Hi, int Wi, int64_t nvox_per_n, int align) {
+    constexpr int LPV = 4, R3 = 16, R2 = 8, CO = 96;        // lanes per voxel, float4 per PSV row / image row
+    const int lane = threadIdx.x % LPV;
+    const int64_t v = (int64_t)blockIdx.x * (256 / LPV) + threadIdx.x / LPV;
+    if (v >= (int64_t)N * nvox_per_n) return;
+    const int n = (int)(v / nvox_per_n);
     const float* g = grid + v * 3;
     float gg[3] = {__ldg(g), __ldg(g + 1), __ldg(g + 2)};
     const Corners3 c = corners3(gg, D, H, W, align);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool any_in = c.z0 >= -1 && c.z0 < D && c.y0 >= -1 && c.y0 < H && c.x0 >= -1 && c.x0 < W;
     if (any_in) {
-        const float4* base = psv + (int64_t)n * D * H * W * LPV + lane;
-        float4 val[8];
-        float wgt[8];
+        const float4* base = psv + (int64_t)n * D * H * W * R3 + lane;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int dz = k >> 2, dy = (k >> 1) & 1, dx = k & 1;
-            int zz = c.z0 + dz, yy = c.y0 + dy, xx = c.x0 + dx;
-            const bool ok = zz >= 0 && zz < D && yy >= 0 && yy < H && xx >= 0 && xx < W;
-            const float w = (dx ? c.wx1 : 1.f - c.wx1) * (dy ? c.wy1 : 1.f - c.wy1) * (dz ? c.wz1 : 1.f - c.wz1);
-            wgt[k] = ok ? w : 0.f;
-            zz = min(max(zz, 0), D - 1); yy = min(max(yy, 0), H - 1); xx = min(max(xx, 0), W - 1);
-            val[k] = __ldg(base + (uint32_t)(((zz * H + yy) * W + xx) * LPV));
+        for (int half = 0; half < 2; ++half) {               // two batches of 4 corners: 16 loads in flight per lane
+            float4 val[4][4];
+            float wgt[4];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int k = half * 4 + kk;
+                const int dz = k >> 2, dy = (k >> 1) & 1, dx = k & 1;
+                int zz = c.z0 + dz, yy = c.y0 + dy, xx = c.x0 + dx;
+                const bool ok = zz >= 0 && zz < D && yy >= 0 && yy < H && xx >= 0 && xx < W;
+                const float w = (dx ? c.wx1 : 1.f - c.wx1) * (dy ? c.wy1 : 1.f - c.wy1) * (dz ? c.wz1 : 1.f - c.wz1);
+                wgt[kk] = ok ? w : 0.f;
+                zz = min(max(zz, 0), D - 1); yy = min(max(yy, 0), H - 1); xx = min(max(xx, 0), W - 1);
+                const float4* row = base + (uint32_t)(((zz * H + yy) * W + xx) * R3);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) val[kk][q] = __ldg(row + 4 * q);
+            }
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) fma4(acc[q], wgt[kk], val[kk][q]);
         }
-#pragma unroll
-        for (int k = 0; k < 8; ++k) fma4(acc, wgt[k], val[k]);
     }
-    float* orow = out + v * CO;
-    *reinterpret_cast<float4*>(orow + lane * 4) = acc;
-    if (lane < LPI) {
-        // the image feature at the same (u, v): its own size may differ from the PSV's, so its corners are recomputed
+    float4* orow = reinterpret_cast<float4*>(out + v * CO) + lane;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) orow[4 * q] = acc[q];
+    {
+        // the image feature at the same (u, v); its size may differ from the PSV's, so its corners are recomputed
         float g2[3] = {gg[0], gg[1], -1.f};
         const Corners3 c2 = corners3(g2, 1, Hi, Wi, align);
-        const float4* base2 = img + (int64_t)n * Hi * Wi * LPI + lane;
-        float4 a2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 v2[4];
+        const float4* base2 = img + (int64_t)n * Hi * Wi * R2 + lane;
+        float4 a2[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
+        float4 v2[4][2];
         float w2[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -180,11 +185,14 @@ lift_fwd_kernel(const float4* __restrict__ psv, const float4* __restrict__ img, 
             const float w = (dx ? c2.wx1 : 1.f - c2.wx1) * (dy ? c2.wy1 : 1.f - c2.wy1);
             w2[k] = ok ? w : 0.f;
             yy = min(max(yy, 0), Hi - 1); xx = min(max(xx, 0), Wi - 1);
-            v2[k] = __ldg(base2 + (uint32_t)((yy * Wi + xx) * LPI));
+            const float4* row = base2 + (uint32_t)((yy * Wi + xx) * R2);
+            v2[k][0] = __ldg(row);
+            v2[k][1] = __ldg(row + 4);
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) fma4(a2, w2[k], v2[k]);
-        *reinterpret_cast<float4*>(orow + 64 + lane * 4) = a2;
+        for (int k = 0; k < 4; ++k) { fma4(a2[0], w2[k], v2[k][0]); fma4(a2[1], w2[k], v2[k][1]); }
+        orow[R3] = a2[0];
+        orow[R3 + 4] = a2[1];
     }
 }
 
@@ -249,60 +257,58 @@ grid_plan_sort_kernel(const int32_t* __restrict__ row_ptr, int2* __restrict__ en
 // SPLIT = 32/LPV: a whole warp per cell whose sub-groups take every SPLIT-th CSR entry (an
 // image-feature pixel receives from ~150 voxels along its ray); the sub-group partial sums are
 // combined by a fixed shuffle tree.  Either way the summation order depends only on the plan.
-// BRICK: the cells are walked in bricks of 2 x 2 x (cells per block / 4) (planes x rows x w) instead of memory
-// order.  Every output voxel feeds the 2 x 2 x 2 cube of cells around its sample point, so the cells of a brick
-// gather mostly the SAME gout rows: one L2 read, the rest L1 hits (memory order shares only the w neighbours).
-struct BrickDims { int D, H, W, on, bz, by, bw; };
-
-template <int LPV, int SPLIT>
+// F4 = float4 per lane: with F4 = 1 every lane of a cell repeats the entry load and the 64-bit address
+// arithmetic for a single float4 -- the gather is then instruction-issue bound like the forward (see
+// lift_fwd_kernel); F4 = 4 (64 channels on 4 lanes, lane l -> float4 l, l+4, l+8, l+12) amortises them.
+template <int LPV, int SPLIT, int F4>
 __global__ void __launch_bounds__(256)
 grid_sample_bwd_kernel(const float* __restrict__ gout, const int32_t* __restrict__ row_ptr,
                        const int2* __restrict__ entries, float4* __restrict__ gin, int64_t ncell,
-                       int gout_cstride, int gout_coff, const BrickDims bd) {
+                       int gout_cstride, int gout_coff) {
     constexpr int GS = LPV * SPLIT;                 // lanes per cell
-        const int cl = threadIdx.x % LPV, sub = (threadIdx.x / LPV) % SPLIT;
+    const int cl = threadIdx.x % LPV, sub = (threadIdx.x / LPV) % SPLIT;
     const int64_t cstride = (int64_t)gridDim.x * (blockDim.x / GS);
     // the loop bound is warp-uniform (first cell of the warp) because of the shuffles below
     for (int64_t c0 = (int64_t)blockIdx.x * (blockDim.x / GS) + (threadIdx.x / 32) * (32 / GS); c0 < ncell; c0 += cstride) {
-        int64_t c = c0 + (threadIdx.x & 31) / GS;
-        if (bd.on) {
-            // slot -> cell: slots enumerate bricks (w fastest, then row pairs, plane pairs, samples); the host
-            // guarantees D, H even and W a multiple of the brick width, so the map is a bijection of [0, ncell)
-            const int BW = bd.bw, BZ = bd.bz, BY = bd.by;
-            int64_t t = c;
-            const int in_b = (int)(t % (BZ * BY * BW)); t /= (BZ * BY * BW);
-            const int wb = (int)(t % (bd.W / BW)); t /= (bd.W / BW);
-            const int hb = (int)(t % (bd.H / BY)); t /= (bd.H / BY);
-            const int db = (int)(t % (bd.D / BZ)); t /= (bd.D / BZ);
-            const int w = wb * BW + in_b % BW, h = hb * BY + (in_b / BW) % BY, d = db * BZ + in_b / (BW * BY);
-            c = ((t * bd.D + d) * bd.H + h) * bd.W + w;
-        }
+        const int64_t c = c0 + (threadIdx.x & 31) / GS;
         const bool valid = c < ncell;
         const int b = valid ? __ldg(row_ptr + c) : 0, e = valid ? __ldg(row_ptr + c + 1) : 0;
-        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 acc[F4];
+#pragma unroll
+        for (int q = 0; q < F4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
         int i = b + sub;
-        // two independent chains per trip; measured: a 4-way unroll at 48 registers is SLOWER (0.278 vs
-        // 0.215 ms on the PSV lift) -- occupancy hides this two-level (entry -> row) latency better than ILP
+        // two independent chains per trip (a 4-way unroll was measured slower in round 1: occupancy hides this
+        // two-level entry -> row latency better than more ILP)
         for (; i + SPLIT < e; i += 2 * SPLIT) {
-            int2 e0 = __ldg(entries + i), e1 = __ldg(entries + i + SPLIT);
-            float4 g0 = __ldg(reinterpret_cast<const float4*>(gout + (int64_t)e0.x * gout_cstride + gout_coff) + cl);
-            float4 g1 = __ldg(reinterpret_cast<const float4*>(gout + (int64_t)e1.x * gout_cstride + gout_coff) + cl);
-            fma4(acc, __int_as_float(e0.y), g0);
-            fma4(acc, __int_as_float(e1.y), g1);
+            const int2 e0 = __ldg(entries + i), e1 = __ldg(entries + i + SPLIT);
+            const float4* r0 = reinterpret_cast<const float4*>(gout + (int64_t)e0.x * gout_cstride + gout_coff) + cl;
+            const float4* r1 = reinterpret_cast<const float4*>(gout + (int64_t)e1.x * gout_cstride + gout_coff) + cl;
+            float4 g0[F4], g1[F4];
+#pragma unroll
+            for (int q = 0; q < F4; ++q) { g0[q] = __ldg(r0 + LPV * q); g1[q] = __ldg(r1 + LPV * q); }
+#pragma unroll
+            for (int q = 0; q < F4; ++q) { fma4(acc[q], __int_as_float(e0.y), g0[q]); fma4(acc[q], __int_as_float(e1.y), g1[q]); }
         }
         if (i < e) {
-            int2 e0 = __ldg(entries + i);
-            float4 g0 = __ldg(reinterpret_cast<const float4*>(gout + (int64_t)e0.x * gout_cstride + gout_coff) + cl);
-            fma4(acc, __int_as_float(e0.y), g0);
+            const int2 e0 = __ldg(entries + i);
+            const float4* r0 = reinterpret_cast<const float4*>(gout + (int64_t)e0.x * gout_cstride + gout_coff) + cl;
+#pragma unroll
+            for (int q = 0; q < F4; ++q) fma4(acc[q], __int_as_float(e0.y), __ldg(r0 + LPV * q));
         }
 #pragma unroll
         for (int off = GS / 2; off >= LPV; off >>= 1) {
-            acc.x += __shfl_down_sync(0xffffffffu, acc.x, off, GS);
-            acc.y += __shfl_down_sync(0xffffffffu, acc.y, off, GS);
-            acc.z += __shfl_down_sync(0xffffffffu, acc.z, off, GS);
-            acc.w += __shfl_down_sync(0xffffffffu, acc.w, off, GS);
+#pragma unroll
+            for (int q = 0; q < F4; ++q) {
+                acc[q].x += __shfl_down_sync(0xffffffffu, acc[q].x, off, GS);
+                acc[q].y += __shfl_down_sync(0xffffffffu, acc[q].y, off, GS);
+                acc[q].z += __shfl_down_sync(0xffffffffu, acc[q].z, off, GS);
+                acc[q].w += __shfl_down_sync(0xffffffffu, acc[q].w, off, GS);
+            }
         }
-        if (valid && sub == 0) gin[c * LPV + cl] = acc;
+        if (valid && sub == 0) {
+#pragma unroll
+            for (int q = 0; q < F4; ++q) gin[c * (LPV * F4) + cl + LPV * q] = acc[q];
+        }
     }
 }
 
@@ -398,72 +404,56 @@ extern "C" int b2_grid_plan_sort(const int32_t* row_ptr, void* entries, int64_t 
     return check_launch("grid_plan_sort");
 }
 
-static int grid_sample_bwd_impl(const float* gout, const int32_t* row_ptr, const void* entries,
-                                float* gin, int64_t ncell, int C, int gout_cstride, int gout_coff,
-                                int long_rows, void* stream, BrickDims bd) {
+extern "C" int b2_grid_sample_bwd(const float* gout, const int32_t* row_ptr, const void* entries,
+                                  float* gin, int64_t ncell, int C, int gout_cstride, int gout_coff,
+                                  int long_rows, void* stream) {
     B2_REQUIRE(gout && row_ptr && entries && gin, "grid_sample_bwd: null pointer");
     B2_REQUIRE(C % 4 == 0 && gout_cstride % 4 == 0 && gout_coff % 4 == 0 && aligned16(gout) && aligned16(gin),
                "grid_sample_bwd: channel counts/offsets must be multiples of 4 and pointers 16B aligned");
     if (ncell == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    if (bd.on) {
-        // brick walk: needs even D, H and W a multiple of the brick width (cells per block / 4); else memory order
-        const int gs = long_rows ? 32 : C / 4, cpb = 256 / gs;
-        bd.bz = (bd.D > 1 && cpb >= 8) ? 2 : 1;
-        bd.by = cpb / bd.bz >= 2 ? 2 : 1;
-        bd.bw = cpb / (bd.bz * bd.by);
-        if (bd.bw < 1 || bd.bz * bd.by * bd.bw != cpb || bd.D % bd.bz || bd.H % bd.by || bd.W % bd.bw) bd.on = 0;
+    static int wide = -1;
+    if (wide < 0) { const char* e = getenv("B2_GS_BWD_WIDE"); wide = (e && e[0] == '0') ? 0 : 1; }
+    // the DSGN widths take the wide-lane variants (several float4 per lane); any other width one float4 per lane
+    if (wide && C == 64 && !long_rows) {
+        int grid_x = stream_grid(ncell, 256 / 4, kNumSMs * 16);
+        grid_sample_bwd_kernel<4, 1, 4><<<grid_x, 256, 0, st>>>(gout, row_ptr, (const int2*)entries, (float4*)gin, ncell,
+                                                               gout_cstride, gout_coff);
+        return check_launch("grid_sample_bwd");
+    }
+    if (wide && C == 32 && long_rows) {
+        int grid_x = stream_grid(ncell, 256 / 32, kNumSMs * 32);
+        grid_sample_bwd_kernel<4, 8, 2><<<grid_x, 256, 0, st>>>(gout, row_ptr, (const int2*)entries, (float4*)gin, ncell,
+                                                               gout_cstride, gout_coff);
+        return check_launch("grid_sample_bwd");
     }
     B2_LPV_SWITCH(C, {
         if (long_rows) {
             int grid_x = stream_grid(ncell, 256 / 32, kNumSMs * 32);
-            grid_sample_bwd_kernel<LPV, 32 / LPV><<<grid_x, 256, 0, st>>>(gout, row_ptr, (const int2*)entries,
-                                                                         (float4*)gin, ncell, gout_cstride, gout_coff, bd);
+            grid_sample_bwd_kernel<LPV, 32 / LPV, 1><<<grid_x, 256, 0, st>>>(gout, row_ptr, (const int2*)entries,
+                                                                            (float4*)gin, ncell, gout_cstride, gout_coff);
         } else {
             int grid_x = stream_grid(ncell, 256 / LPV, kNumSMs * 16);
-            grid_sample_bwd_kernel<LPV, 1><<<grid_x, 256, 0, st>>>(gout, row_ptr, (const int2*)entries, (float4*)gin,
-                                                                  ncell, gout_cstride, gout_coff, bd);
+            grid_sample_bwd_kernel<LPV, 1, 1><<<grid_x, 256, 0, st>>>(gout, row_ptr, (const int2*)entries, (float4*)gin,
+                                                                     ncell, gout_cstride, gout_coff);
         }
     });
     return check_launch("grid_sample_bwd");
 }
 
-extern "C" int b2_grid_sample_bwd(const float* gout, const int32_t* row_ptr, const void* entries,
-                                  float* gin, int64_t ncell, int C, int gout_cstride, int gout_coff,
-                                  int long_rows, void* stream) {
-    return grid_sample_bwd_impl(gout, row_ptr, entries, gin, ncell, C, gout_cstride, gout_coff, long_rows, stream,
-                                BrickDims{1, 1, 1, 0, 1, 1, 1});
-}
-
-extern "C" int b2_grid_sample_bwd_tiled(const float* gout, const int32_t* row_ptr, const void* entries,
-                                        float* gin, int N, int D, int H, int W, int C, int gout_cstride,
-                                        int gout_coff, int long_rows, void* stream) {
-    B2_REQUIRE(N >= 0 && D > 0 && H > 0 && W > 0, "grid_sample_bwd_tiled: bad dims");
-    return grid_sample_bwd_impl(gout, row_ptr, entries, gin, (int64_t)N * D * H * W, C, gout_cstride, gout_coff,
-                                long_rows, stream, BrickDims{D, H, W, 1, 1, 1, 1});
-}
-
 extern "C" int b2_lift_fwd(const float* psv, const float* img, const float* grid, float* out, int N, int C3, int C2,
-                           int D, int H, int W, int Hi, int Wi, int Z, int Y, int X, int align_corners, int z_run,
-                           void* stream) {
+                           int D, int H, int W, int Hi, int Wi, int64_t nvox_per_n, int align_corners, void* stream) {
     B2_REQUIRE(psv && img && grid && out, "lift_fwd: null pointer");
     B2_REQUIRE(C3 == 64 && C2 == 32, "lift_fwd: the fused kernel serves the DSGN widths (64 + 32 channels); got %d + %d "
                "(use b2_grid_sample3d_fwd / b2_grid_sample2d_fwd)", C3, C2);
     B2_REQUIRE(aligned16(psv) && aligned16(img) && aligned16(out), "lift_fwd: pointers must be 16-byte aligned");
-    B2_REQUIRE(N >= 0 && D > 0 && H > 0 && W > 0 && Hi > 0 && Wi > 0 && Z > 0 && Y > 0 && X > 0, "lift_fwd: bad dims");
+    B2_REQUIRE(N >= 0 && D > 0 && H > 0 && W > 0 && Hi > 0 && Wi > 0 && nvox_per_n >= 0, "lift_fwd: bad dims");
     B2_REQUIRE((int64_t)D * H * W * 16 < ((int64_t)1 << 31), "lift_fwd: input sample has more than 2^31 float4");
-    if (N == 0) return 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int zb = (z_run == 16 || z_run == 8 || z_run == 4 || z_run == 1) ? z_run : 16;
-    const int xb = 16 / zb;
-    const int64_t nblk = (int64_t)N * Y * ((Z + zb - 1) / zb) * ((X + xb - 1) / xb);
+    const int64_t nvox = (int64_t)N * nvox_per_n;
+    if (nvox == 0) return 0;
+    const int64_t nblk = (nvox + 63) / 64;
     B2_REQUIRE(nblk < ((int64_t)1 << 31), "lift_fwd: too many voxels");
-#define B2_LIFT(ZB, XB) lift_fwd_kernel<ZB, XB><<<(unsigned)nblk, 256, 0, st>>>((const float4*)psv, (const float4*)img, \
-        grid, out, N, D, H, W, Hi, Wi, Z, Y, X, align_corners)
-    if (zb == 16) B2_LIFT(16, 1);
-    else if (zb == 8) B2_LIFT(8, 2);
-    else if (zb == 4) B2_LIFT(4, 4);
-    else B2_LIFT(1, 16);
-#undef B2_LIFT
+    lift_fwd_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>((const float4*)psv, (const float4*)img, grid, out, N,
+                                                                       D, H, W, Hi, Wi, nvox_per_n, align_corners);
     return check_launch("lift_fwd");
 }

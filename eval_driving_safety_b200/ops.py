@@ -283,8 +283,6 @@ def grid_sample(inp, grid, align_corners=False, plan=None):
 
 
 LIFT_FUSED = os.environ.get("B2_LIFT_FUSED", "1") != "0"
-LIFT_BWD_TILED = os.environ.get("B2_LIFT_BWD_TILED", "1") != "0"
-LIFT_ZRUN = int(os.environ.get("B2_LIFT_ZRUN", "16"))       # z-run length of the fused lifting kernel's blocks (16, 8, 4, 1)
 
 
 class LiftFn(Function):
@@ -303,12 +301,12 @@ class LiftFn(Function):
         grid2 = grid3[..., :2].contiguous().view(n, z * y, x, 2)
         out = empty_cl3(n, c3 + c2, z, y, x, psv.device)
         if c3 == 64 and c2 == 32 and LIFT_FUSED:
-            # one launch for both samplings, z-run blocks (L1 reuse of the corner rows)
+            # one launch for both samplings, 4 lanes per voxel
             d, h, w = psv.shape[2:]
             work = 4 * (psv.numel() + img.numel() + grid3.numel() + out.numel())
             with _op("lift_fwd", 1, work):
                 check(lib.b2_lift_fwd(_p(psv), _p(img), _p(grid3), _p(out), n, c3, c2, d, h, w, img.shape[2], img.shape[3],
-                                      z, y, x, int(align_corners), LIFT_ZRUN, _stream()), "lift_fwd")
+                                      z * y * x, int(align_corners), _stream()), "lift_fwd")
         else:
             _gs_fwd(lib, psv, grid3, out, c3 + c2, 0, align_corners)
             _gs_fwd(lib, img, grid2, out, c3 + c2, c3, align_corners)
@@ -327,13 +325,11 @@ class LiftFn(Function):
         g3, g2 = empty_cl3(*s3, g.device), empty_cl2(*s2, g.device)
         nv = g.numel() // ctot
         with _op("grid_sample3d_bwd", 1, 4 * (nv * s3[1] + g3.numel()) + 8 * p3.nnz + 4 * p3.ncell):
-            check(lib.b2_grid_sample_bwd_tiled(_p(g), _p(p3.row_ptr), _p(p3.entries), _p(g3), s3[0], s3[2] if LIFT_BWD_TILED else 1,
-                                               s3[3] if LIFT_BWD_TILED else 1, s3[4] if LIFT_BWD_TILED else s3[2] * s3[3] * s3[4],
-                                               s3[1], ctot, 0, p3.long_rows, _stream()), "grid_sample_bwd(3d)")
+            check(lib.b2_grid_sample_bwd(_p(g), _p(p3.row_ptr), _p(p3.entries), _p(g3), p3.ncell, s3[1], ctot, 0,
+                                         p3.long_rows, _stream()), "grid_sample_bwd(3d)")
         with _op("grid_sample2d_bwd", 1, 4 * (nv * s2[1] + g2.numel()) + 8 * p2.nnz + 4 * p2.ncell):
-            check(lib.b2_grid_sample_bwd_tiled(_p(g), _p(p2.row_ptr), _p(p2.entries), _p(g2), s2[0], 1,
-                                               s2[2] if LIFT_BWD_TILED else 1, s2[3] if LIFT_BWD_TILED else s2[2] * s2[3],
-                                               s2[1], ctot, s3[1], p2.long_rows, _stream()), "grid_sample_bwd(2d)")
+            check(lib.b2_grid_sample_bwd(_p(g), _p(p2.row_ptr), _p(p2.entries), _p(g2), p2.ncell, s2[1], ctot, s3[1],
+                                         p2.long_rows, _stream()), "grid_sample_bwd(2d)")
         return g3, g2, None, None, None, None
 
 

@@ -159,20 +159,13 @@ int b2_grid_sample_bwd(const float* gout, const int32_t* row_ptr, const void* en
                        int64_t ncell, int C, int gout_cstride, int gout_coff, int long_rows, void* stream);
 /* long_rows != 0: a whole warp walks each CSR row (rows of >~ 32 entries, e.g. the 2-D lifting). */
 
-/* Same gather, with the input cells walked in 2 x 2 x w bricks instead of memory order (cells of a brick gather
- * mostly the same gout rows: L1 instead of L2 traffic).  Needs the cell grid's dims; falls back to memory order
- * when they do not tile.  The result is bit-identical to b2_grid_sample_bwd (the per-cell order is the plan's). */
-int b2_grid_sample_bwd_tiled(const float* gout, const int32_t* row_ptr, const void* entries, float* gin,
-                             int N, int D, int H, int W, int C, int gout_cstride, int gout_coff, int long_rows,
-                             void* stream);
-
 /* Fused lifting forward of DSGN (frustum -> voxel): out[v, 0:64] = trilinear sample of psv [N,D,H,W,64] at
- * grid[v] = (x,y,z), out[v, 64:96] = bilinear sample of img [N,Hi,Wi,32] at grid[v].xy; out [N,Z,Y,X,96].
- * Same values as b2_grid_sample3d_fwd + b2_grid_sample2d_fwd into the two channel slices, one launch, the grid
- * read once; blocks own z_run (16, 8, 4 or 1) consecutive voxels along Z of 16 / z_run consecutive X so that
- * their corner rows are L1 hits (see the kernel).  C3 = 64, C2 = 32 only. */
+ * grid[v] = (x,y,z), out[v, 64:96] = bilinear sample of img [N,Hi,Wi,32] at grid[v].xy; out [N*nvox_per_n, 96].
+ * Same values, bit for bit, as b2_grid_sample3d_fwd + b2_grid_sample2d_fwd into the two channel slices; one
+ * launch, the grid read once, 4 lanes per voxel (the generic kernels are instruction-issue bound on the corner
+ * arithmetic every one of their 16 lanes repeats).  C3 = 64, C2 = 32 only. */
 int b2_lift_fwd(const float* psv, const float* img, const float* grid, float* out, int N, int C3, int C2,
-                int D, int H, int W, int Hi, int Wi, int Z, int Y, int X, int align_corners, int z_run, void* stream);
+                int D, int H, int W, int Hi, int Wi, int64_t nvox_per_n, int align_corners, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * (3) 3-D convolutions of the hourglass stacks -- replaces cuDNN Conv3d /

@@ -44,7 +44,7 @@ def _ref_grads(s, xL, xR, labels=None):
 
 
 # ---------------------------------------------------------------- module seams (ADVICE)
-def test_swap_modules_on_the_oracle_model_reproduces_the_product_model(tiny):
+def test_swap_modules_on_the_oracle_model_reproduces_the_product_model(tiny, monkeypatch):
     """``swap_modules(upstream model)`` puts every Conv3d / ConvTranspose3d / Conv2d / GroupNorm
     on the sm_100a kernels; the oracle's StereoNetRef (stock cost volume / grid_sample around them) then has to
     give the oracle's outputs and input gradient, and agree with ``dsgn.StereoNet``."""
@@ -52,6 +52,10 @@ def test_swap_modules_on_the_oracle_model_reproduces_the_product_model(tiny):
     from eval_driving_safety_b200 import dsgn, modules, ops
     s = tiny
     ops.set_conv_impl(1)
+    # the oracle builds its calibration-only tensors on the CPU: move them along for this CUDA run of its forward
+    for name in ("plane_shifts", "lifting_grid", "full_depths"):
+        orig = getattr(R, name)
+        monkeypatch.setattr(R, name, (lambda f: lambda *a, **k: f(*a, **k).cuda())(orig))
     swapped = modules.swap_modules(copy.deepcopy(s["ref"])).cuda()
     assert sum(isinstance(m, modules.Conv3dSm100) for m in swapped.modules()) == 15
     assert not any(type(m) in (torch.nn.Conv3d, torch.nn.ConvTranspose3d, torch.nn.Conv2d, torch.nn.GroupNorm)

@@ -10,22 +10,32 @@ dev = torch.device("cuda", 0)
 
 
 def timeit(fn, iters=20):
-    for _ in range(3):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        fn()
-    e1.record(); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    """ms per call with the launches replayed from a CUDA graph (the host's ~30 us per call would otherwise hide
+    every kernel shorter than that)."""
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(iters):
+                fn()
+        g.replay(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            g.replay()
+        e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / (3 * iters)
 
 
 # (n, cin, cout, h, w, k, stride, dil)
 LAYERS = [(2, 32, 32, 192, 624, 3, 1, 1), (2, 32, 64, 192, 624, 3, 2, 1), (2, 64, 64, 96, 312, 3, 1, 1),
           (2, 128, 128, 96, 312, 3, 1, 1), (2, 128, 128, 96, 312, 3, 1, 2), (2, 320, 128, 96, 312, 3, 1, 1),
           (1, 320, 128, 192, 304, 3, 1, 1), (1, 128, 64, 192, 304, 3, 1, 1), (2, 128, 32, 96, 312, 1, 1, 1)]
-print("layer: ms fwd (GFLOP/s-equivalent)  own 3xTF32 | own TF32 | cuDNN TF32")
+print("halo kernel:", os.environ.get("B2_CONV2D_HALO", "1"))
+print("layer: ms fwd (TFLOP/s-equivalent, graph replay)  own 3xTF32 | own TF32 | cuDNN TF32")
 for (n, ci, co, h, w, k, s, d) in LAYERS:
     x = torch.randn(n, ci, h, w, device=dev).contiguous(memory_format=torch.channels_last)
     wt = (torch.randn(co, ci, k, k, device=dev) / (ci * k * k) ** 0.5)

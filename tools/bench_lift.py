@@ -1,5 +1,5 @@
-"""Lifting kernels at KITTI size: fused forward for each z-run length vs the two separate kernels; brick-ordered vs
-memory-ordered backward.  CUDA events, L2 flushed between launches."""
+"""Lifting kernels at KITTI size: fused 4-lane forward vs the two generic kernels; wide-lane gather backward (B2_GS_BWD_WIDE=0
+in the environment selects the one-float4-per-lane variant).  CUDA events, L2 flushed between launches."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -30,28 +30,21 @@ def timeit(fn, iters=10):
 
 
 ref = None
-for fused, zr in ((False, 16), (True, 16), (True, 8), (True, 4), (True, 1)):
-    ops.LIFT_FUSED, ops.LIFT_ZRUN = fused, zr
+for fused in (False, True):
+    ops.LIFT_FUSED = fused
     out = ops.lift(psv, img, grid3, plan3, plan2, True)
     if ref is None:
         ref = out.clone()
     t = timeit(lambda: ops.lift(psv, img, grid3, plan3, plan2, True))
-    print("lift fwd fused=%s z_run=%2d: %.4f ms  (bit-identical to unfused: %s)" % (fused, zr, t, torch.equal(out, ref)), flush=True)
-ops.LIFT_FUSED, ops.LIFT_ZRUN = True, 16
+    print("lift fwd fused=%s: %.4f ms  (bit-identical to unfused: %s)" % (fused, t, torch.equal(out, ref)), flush=True)
+ops.LIFT_FUSED = True
 a, c = psv.detach().requires_grad_(True), img.detach().requires_grad_(True)
-refg = None
-for tiled in (False, True):
-    ops.LIFT_BWD_TILED = tiled
-    o = ops.lift(a, c, grid3, plan3, plan2, True)
-    gs = torch.autograd.grad(o, [a, c], gout, retain_graph=True)
-    if refg is None:
-        refg = [t.clone() for t in gs]
-    with ops.profile() as prof:
-        for _ in range(5):
-            flush.fill_(1.0)
-            torch.autograd.grad(o, [a, c], gout, retain_graph=True)
-    s = prof.summary()
-    print("lift bwd tiled=%s: 3-D %.4f ms, 2-D %.4f ms (bit-identical: %s)" % (
-        tiled, s["grid_sample3d_bwd"]["ms"] / 5, s["grid_sample2d_bwd"]["ms"] / 5,
-        all(torch.equal(x, y) for x, y in zip(gs, refg))), flush=True)
-ops.LIFT_BWD_TILED = True
+o = ops.lift(a, c, grid3, plan3, plan2, True)
+torch.autograd.grad(o, [a, c], gout, retain_graph=True)
+with ops.profile() as prof:
+    for _ in range(5):
+        flush.fill_(1.0)
+        torch.autograd.grad(o, [a, c], gout, retain_graph=True)
+s = prof.summary()
+print("lift bwd (B2_GS_BWD_WIDE=%s): 3-D %.4f ms, 2-D %.4f ms" % (os.environ.get("B2_GS_BWD_WIDE", "1"),
+      s["grid_sample3d_bwd"]["ms"] / 5, s["grid_sample2d_bwd"]["ms"] / 5), flush=True)
