@@ -286,6 +286,163 @@ def run_b200(args):
 
 
 # ---------------------------------------------------------------------------------------------
+# BASELINE configs[3] / configs[4]: the other two attack loops, measured the same way (profiles/ only: the
+# driver's BENCH / SCALE records are the default config)
+# ---------------------------------------------------------------------------------------------
+def _timed(fn, steps, warmup, dev, world):
+    from eval_driving_safety_b200 import parallel
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return t.item()
+
+
+def run_patch(args):
+    """configs[3]: universal adversarial patch (ratio 0.2 -> 77x77, alpha 1e3, eps 8/255, fake ground truth), every
+    rank attacks its own image of the step, the clipped patch step is all-reduced over NCCL INSIDE the captured
+    iteration.  step = one patch iteration per rank; a new image (H2D from pinned memory in the e2e arm) every 2."""
+    import random
+    from eval_driving_safety_b200 import attack, dsgn, engine, ops, parallel, synthetic
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    rank, world = parallel.init(device=dev)
+    cfg = dsgn.default_cfg()
+    model = dsgn.build_model(cfg, seed=1, device=dev)
+    calib = synthetic.make_calib(1)
+    bbox, box3d = synthetic.make_targets(6, 1)
+    attack.inject_fake_gt(bbox, box3d)
+    labels = synthetic.labels_from_box3d(cfg, box3d, device=dev)
+    dim, radius = attack.patch_dim_radius(H, 0.2)
+    patch = torch.zeros(1, 3, dim, dim, device=dev)
+    imgs = [synthetic.make_pair(rank * 4 + j, H, W) for j in range(4)]
+    host = [{k: v.pin_memory() for k, v in p.items()} for p in imgs]
+    devp = [{k: v.to(dev) for k, v in p.items()} for p in imgs]
+    rng = random.Random(1)                                                # SURVEY 8d: seeded centres
+    centres = [attack.generate_round_mask(radius, rng, H, W) for _ in range(64)]
+    hook = parallel.allreduce_patch_delta if world > 1 else None
+    eng = engine.PatchIterationGraph(model, cfg, labels, calib, patch, radius, (devp[0]["imgL"], devp[0]["imgR"], devp[0]["disp_L"]),
+                                     alpha=1e3, eps=8 / 255, allreduce=hook)
+    state = {"k": 0}
+
+    def step(src):
+        k = state["k"]
+        if k % 2 == 0:                                                    # iters = 2 per image (patch_attack.py:53)
+            p = src[(k // 2) % len(src)]
+            cl, cr = centres[(k // 2) % len(centres)]
+            eng.load(p["imgL"], p["imgR"], p["disp_L"], cl, cr)
+        state["k"] = k + 1
+        return eng.iterate()
+
+    ms = _timed(lambda: step(devp), args.steps, args.warmup, dev, world)
+    h_loss = torch.zeros((), pin_memory=True)
+
+    def e2e():
+        h_loss.copy_(step(host), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    parallel.barrier()
+    for _ in range(2):
+        e2e()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    e2e_ms = t.item()
+    if rank != 0:
+        return
+    units = world * args.steps
+    emit({"metric": "patch_attack_pair_iterations_per_second", "value": units / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "tf32 (fp32 storage, fp32 accumulate); 2-D convs 3xTF32", "data": "synthetic",
+          "config": {"workload": "BASELINE configs[3]: DSGN universal adversarial patch (77x77 circular patch, alpha 1e3, eps 8/255, "
+                                 "fake ground truth), one image per GPU per iteration, 2 iterations per image, clipped patch step "
+                                 "all-reduced (NCCL, 71 KB) inside the captured iteration",
+                     "execution": "CUDA graph of one patch iteration incl. the all_reduce; patch centres in device memory",
+                     "parallelism": "dp%d, synchronous mini-batch of %d images per patch step" % (world, world)},
+          "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                  "h2d_bytes_per_step": (2 * 3 * H * W + H * W) * 4 // 2, "d2h_bytes_per_step": 4},
+          "gpu_launches": (eng.launches_per_step or 0) * units, "patch_absmax": patch.abs().max().item()})
+
+
+def run_srcnn(args):
+    """configs[4]: Stereo R-CNN PGD (RoIAlign fwd/bwd path) on 600x1987 pairs in mean-subtracted 0-255 space,
+    R = 256 RoIs per view over FPN levels 2-5, alpha 1.0, eps 0.03*255; step = one PGD iteration of one pair per rank."""
+    from eval_driving_safety_b200 import attack, ops, parallel, stereo_rcnn as S
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    rank, world = parallel.init(device=dev)
+    model = S.SyntheticStereoRCNN(width=256, seed=1).to(dev)
+    il, ir = S.synthetic_pair(rank, 600, 1987)
+    rl, rr = S.synthetic_rois(256, 600, 1987, seed=rank)
+    tg = {k: v.to(dev) for k, v in S.synthetic_targets(256, seed=rank).items()}
+    hl, hr = il.pin_memory(), ir.pin_memory()
+    rl, rr = rl.to(dev), rr.to(dev)
+    st = {"xl": il.to(dev), "xr": ir.to(dev), "cl": il.to(dev), "cr": ir.to(dev)}
+    eps255 = 255 * 0.03
+    n0 = ops.LAUNCH_COUNT
+
+    def step():
+        xl, xr = st["xl"].requires_grad_(True), st["xr"].requires_grad_(True)
+        loss = model(xl, xr, rl, rr, tg)
+        gl, gr = torch.autograd.grad(loss, [xl, xr])
+        st["xl"] = attack.stereo_rcnn_pgd_step(xl.detach(), gl.contiguous(), st["cl"], 1.0, eps255)
+        st["xr"] = attack.stereo_rcnn_pgd_step(xr.detach(), gr.contiguous(), st["cr"], 1.0, eps255)
+        return loss.detach()
+    ms = _timed(step, args.steps, args.warmup, dev, world)
+    launches = (ops.LAUNCH_COUNT - n0) // (args.steps + args.warmup)
+    h_loss = torch.zeros((), pin_memory=True)
+
+    def e2e():
+        st["xl"], st["xr"] = hl.to(dev, non_blocking=True), hr.to(dev, non_blocking=True)
+        h_loss.copy_(step(), non_blocking=True)
+        hl.copy_(st["xl"], non_blocking=True); hr.copy_(st["xr"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+    for _ in range(2):
+        e2e()
+    parallel.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e()
+    torch.cuda.synchronize()
+    t = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    e2e_ms = t.item()
+    if rank != 0:
+        return
+    units = world * args.steps
+    emit({"metric": "stereo_rcnn_pgd_pair_iterations_per_second", "value": units / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
+          "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+          "scaling": "weak", "vs_baseline": None, "dtype": "f32 (stock FPN stand-in; own RoIAlign fwd / deterministic bwd, own update kernel)",
+          "data": "synthetic",
+          "config": {"workload": "BASELINE configs[4]: Stereo R-CNN PGD (RoIAlign fwd/bwd path), 600x1987 pairs, 256 RoIs per view, "
+                                 "alpha 1.0, eps 0.03*255; Stereo-R-CNN-shaped stand-in network (the real detector is un-vendored)",
+                     "parallelism": "dp%d (pairs sharded, no data-path collective)" % world, "execution": "eager"},
+          "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
+                  "h2d_bytes_per_step": 2 * 3 * 600 * 1987 * 4, "d2h_bytes_per_step": 2 * 3 * 600 * 1987 * 4 + 4},
+          "gpu_launches": launches * units})
+
+
+# ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle (the reference's own model lives in the un-vendored DSGN package and cannot run;
 # oracle/ restates the loop with stock torch ops) at FULL SIZE -- the same 384x1248 pair, voxel grid and
 # network as the GPU arm.  A "step" of this arm = one PGD iteration of ONE full-size pair (the bounded
@@ -379,9 +536,15 @@ def main():
     ap.add_argument("--eager", action="store_true", help="no CUDA graph (debug)")
     ap.add_argument("--backbone-fp32", action="store_true", help="cuDNN 2-D convs in fp32 instead of TF32")
     ap.add_argument("--lanes", type=int, default=2, help="pair-iterations captured side by side in one graph")
+    ap.add_argument("--config", default="pgd", choices=["pgd", "patch", "srcnn"],
+                    help="pgd = BASELINE configs[1]/[2] (the headline, default); patch = configs[3]; srcnn = configs[4]")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config == "patch":
+        run_patch(args)
+    elif args.config == "srcnn":
+        run_srcnn(args)
     else:
         run_b200(args)
     if torch.distributed.is_available() and torch.distributed.is_initialized():

@@ -1158,6 +1158,269 @@ conv3d_dc_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid
     }
 }
 
+// =============================================================================================
+// Transposed conv, CTA-PAIR variant (cta_group::2).  ncu on the single-CTA kernel above (128 -> 64 at
+// 24x48x156): tensor pipe 39.8 %, L2->SM 63 %, and per work unit two thirds of the bytes arriving in smem are
+// weight tiles that every unit re-reads -- the kernel is bound by per-SM smem ingress.  Here
+// two CTAs of one TPC take two w-adjacent input blocks of the same (plane, parity) and issue ONE
+// tcgen05.mma.cta_group::2 of M = 256 per step: each CTA brings its own A box (its 128 pixels) and HALF of
+// every weight operand's rows, the tensor cores read the other half from the peer's smem.  Weight bytes
+// arriving per SM halve (per K chunk and plane tap: 17 + 24 and 17 + 12 KB instead of 17 + 48 and 17 + 24),
+// the accumulator layout in each CTA's TMEM is unchanged (its 128 rows x the 4 class column ranges), so the
+// epilogue (incl. the fused statistics / addend) is the single-CTA one.
+//   weight operand split (rows of B = N of the MMA): CTA r holds rows [r N/2, (r+1) N/2):
+//     sw = 0: N = 4 nt  [cls 0..3] -> CTA r loads the tiles of classes 2r, 2r+1;  N = 2 nt [cls 2,3; sh = 1] -> tile 4+r
+//     sw = 1: three MMAs of N = nt -> CTA r loads rows [r nt/2, (r+1) nt/2) of each of the 3 tiles
+//   barriers: "full" lives in the leader (rank 0) and counts the leader's expect_tx arrival plus one remote
+//   arrival of the peer's producer; both CTAs' TMA loads signal it (cta_group::2 loads).  "empty" / "tmem full"
+//   exist in both CTAs and are signalled by multicast tcgen05.commit; "tmem empty" lives in the leader and
+//   collects the 2 x 128 epilogue threads of the pair.
+// =============================================================================================
+constexpr int kDc2MaxStages = 6;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+conv3d_dc2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                          float* __restrict__ out, const DcParams p, const EpiFusion ef) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kDc2MaxStages + 4];
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ float coef_sh[2 * kEpiMaxC];
+    float* __restrict__ stat_partial = ef.stat_partial;
+    if (ef.stat_mode == 3)
+        for (int i = threadIdx.x; i < p.Cout; i += blockDim.x) {
+            coef_sh[i] = ef.gn_coef[i];
+            coef_sh[kEpiMaxC + i] = ef.gn_coef[p.Cout + i];
+        }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = smem_u32(bars);
+    float* const stage_all = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)) + p.stages * p.stage_bytes);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kDc2MaxStages + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kDc2MaxStages + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kDc2MaxStages + 2 + a); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();                       // both CTAs' barriers initialised and TMEM allocated
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const int wpairs = (p.tiles_w + 1) / 2;
+    const long long total_pairs = (long long)p.n_tiles * p.N * p.Pt * 2 * p.tiles_h * wpairs;
+    const long long pair0 = blockIdx.x >> 1, pstride = gridDim.x >> 1;
+    // pair-unit index -> this CTA's unit (w tile 2 * wpair + rank; may lie beyond the volume: loads are zero-filled)
+    auto decode = [&](long long t) {
+        DcUnit u;
+        u.w0 = ((int)(t % wpairs) * 2 + (int)rank) * kTileW; t /= wpairs;
+        u.h0 = (int)(t % p.tiles_h) * kTileH; t /= p.tiles_h;
+        u.pd = (int)(t & 1); t >>= 1;
+        u.d = (int)(t % p.Pt); t /= p.Pt;
+        u.n = (int)(t % p.N); t /= p.N;
+        u.nti = (int)t;
+        return u;
+    };
+    const uint32_t half_b = (uint32_t)p.b_bytes / 2;          // bytes of half a weight tile (nt / 2 rows)
+
+    if (warp == 0) {
+        // ===================== TMA producer (one thread per CTA) =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            for (long long t = pair0; t < total_pairs; t += pstride) {
+                const DcUnit u = decode(t);
+                const int nptap = 1 + u.pd;
+                for (int kc = 0; kc < p.kchunks; ++kc) {
+                    for (int jt = 0; jt < nptap; ++jt) {
+                        int kd, sd;
+                        deconv_axis(u.pd, jt, kd, sd);
+                        for (int sw = 0; sw < 2; ++sw) {
+                            mbar_wait(empty_bar(stage), phase ^ 1);
+                            const uint32_t fb = mapa_cluster(full_bar(stage), 0);          // the leader's barrier
+                            // bytes per CTA: A box + 3 tiles (sw = 0) or 3 half tiles (sw = 1)
+                            const uint32_t mine = (uint32_t)kDcABytes + (sw == 0 ? 3u * (uint32_t)p.b_bytes : 3u * half_b);
+                            if (leader) mbar_expect_tx(full_bar(stage), 2u * mine);
+                            const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                            tma_load_5d_pair(sa, &map_a, fb, kc * kKChunk, u.w0 + sw, u.h0, u.d + sd, u.n);
+                            const uint32_t sb = sa + kDcABytes;
+                            auto tap_of = [&](int kh, int kw) { return p.swap ? (kh * 3 + kd) * 3 + kw : (kd * 3 + kh) * 3 + kw; };
+                            auto half_tile = [&](uint32_t dst, int tap, int half) {      // rows [half nt/2, +nt/2) of a tile
+                                tma_load_2d_pair(dst, &map_b, fb, kc * kKChunk, tap * p.Cout + u.nti * p.nt + half * (p.nt / 2));
+                            };
+                            if (sw == 0) {
+                                // N = 4 nt operand: classes 2r, 2r+1 (class c: kh = c>>1 ? 2 : 1, kw = c&1 ? 2 : 1)
+                                for (int j = 0; j < 2; ++j) {
+                                    const int c = 2 * (int)rank + j;
+                                    const int tap = tap_of((c >> 1) ? 2 : 1, (c & 1) ? 2 : 1);
+                                    half_tile(sb + (uint32_t)(2 * j) * half_b, tap, 0);
+                                    half_tile(sb + (uint32_t)(2 * j + 1) * half_b, tap, 1);
+                                }
+                                // N = 2 nt operand (sh = 1, kh = 0): classes 2, 3 -> tile of class 2 + r
+                                const int tap = tap_of(0, rank ? 2 : 1);
+                                half_tile(sb + 4u * half_b, tap, 0);
+                                half_tile(sb + 5u * half_b, tap, 1);
+                            } else {
+                                // three N = nt operands (kw = 0; kh = 1, 2, 0): this CTA's half of the rows of each
+                                for (int b = 0; b < 3; ++b) {
+                                    const int kh = b == 0 ? 1 : (b == 1 ? 2 : 0);
+                                    half_tile(sb + (uint32_t)b * half_b, tap_of(kh, 0), (int)rank);
+                                }
+                            }
+                            if (!leader) mbar_arrive_cluster(fb);
+                            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (lane == 0 && leader) {
+            const uint32_t idesc1 = umma_idesc_tf32(256, p.nt), idesc2 = umma_idesc_tf32(256, 2 * p.nt),
+                           idesc4 = umma_idesc_tf32(256, 4 * p.nt);
+            int stage = 0; uint32_t phase = 0;
+            long long it = 0;
+            for (long long t = pair0; t < total_pairs; t += pstride, ++it) {
+                const int acc = (int)(it & 1);
+                mbar_wait(tempty_bar(acc), (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * 4 * p.nt);
+                const DcUnit u = decode(t);
+                const int nst = p.kchunks * (1 + u.pd);
+                for (int s = 0; s < nst; ++s) {
+                    // ---- sw = 0 stage
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    {
+                        const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                        const uint64_t a0 = umma_desc_sw128(sa), a1 = umma_desc_sw128(sa + 1024);
+                        const uint64_t b0 = umma_desc_sw128(sa + kDcABytes), b4 = umma_desc_sw128(sa + kDcABytes + 4u * half_b);
+#pragma unroll
+                        for (int k = 0; k < kKChunk / 8; ++k)
+                            umma_tf32_pair(tmem_d, a0 + 2 * k, b0 + 2 * k, idesc4, (s | k) != 0);
+#pragma unroll
+                        for (int k = 0; k < kKChunk / 8; ++k)
+                            umma_tf32_pair(tmem_d + 2 * p.nt, a1 + 2 * k, b4 + 2 * k, idesc2, 1u);
+                    }
+                    umma_commit_pair(empty_bar(stage));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    // ---- sw = 1 stage
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    {
+                        const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                        const uint64_t a0 = umma_desc_sw128(sa), a1 = umma_desc_sw128(sa + 1024);
+                        const uint64_t b0 = umma_desc_sw128(sa + kDcABytes), b1 = umma_desc_sw128(sa + kDcABytes + half_b),
+                                       b2 = umma_desc_sw128(sa + kDcABytes + 2u * half_b);
+#pragma unroll
+                        for (int k = 0; k < kKChunk / 8; ++k)
+                            umma_tf32_pair(tmem_d + p.nt, a0 + 2 * k, b0 + 2 * k, idesc1, 1u);
+#pragma unroll
+                        for (int k = 0; k < kKChunk / 8; ++k)
+                            umma_tf32_pair(tmem_d + 3 * p.nt, a0 + 2 * k, b1 + 2 * k, idesc1, 1u);
+#pragma unroll
+                        for (int k = 0; k < kKChunk / 8; ++k)
+                            umma_tf32_pair(tmem_d + 3 * p.nt, a1 + 2 * k, b2 + 2 * k, idesc1, 1u);
+                    }
+                    umma_commit_pair(empty_bar(stage));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(tfull_bar(acc));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===================== epilogue (both CTAs: their own 128 rows) =====================
+        const int lane_grp = warp & 3;
+        const int m = lane_grp * 32 + lane;
+        const int hl = m / kTileW, wl = m % kTileW;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        const bool stats = stat_partial != nullptr;
+        float4* const stage = reinterpret_cast<float4*>(stage_all + lane_grp * (kEpiStageBytes / 4));
+        StatTotals tot;
+        tot.clear();
+        long long it = 0;
+        for (long long t = pair0; t < total_pairs; t += pstride, ++it) {
+            const int acc = (int)(it & 1);
+            const DcUnit u = decode(t);
+            const int h = u.h0 + hl, w = u.w0 + wl;
+            const bool ok = h < p.Rt && w < p.Wt;
+            const int op = 2 * u.d + u.pd;
+            mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const long long unit_off = (long long)u.n * p.Do * p.Ho * p.Wo * p.Cout + u.nti * p.nt;
+            auto off_of = [&](int rw, int c) -> long long {
+                const int m2 = lane_grp * 32 + rw;
+                const int h2 = u.h0 + (m2 >> 3), w2 = u.w0 + (m2 & 7);
+                if (h2 >= p.Rt || w2 >= p.Wt) return -1;
+                const int orow = 2 * h2 + (c >> 1), ow = 2 * w2 + (c & 1);
+                const int od = p.swap ? orow : op, oh = p.swap ? op : orow;
+                return unit_off + (((long long)od * p.Ho + oh) * p.Wo + ow) * p.Cout;
+            };
+            int c0 = 0;
+            for (; c0 + 32 <= p.nt; c0 += 32) {
+                float ssum[32], ssq[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t taddr = lane_addr + (uint32_t)((acc * 4 + c) * p.nt);
+                    uint32_t rr[32];
+                    tmem_ld32(taddr + c0, rr);
+                    tmem_ld_wait();
+                    epi_chunk32(ef, out, rr, stage, lane, ok,
+                                [&](int rw) { const long long o = off_of(rw, c); return o < 0 ? o : o + c0; },
+                                ssum, ssq, u.nti * p.nt + c0, coef_sh);
+                }
+                if (stats) {
+                    warp_transpose_sum32(ssum, lane);
+                    warp_transpose_sum32(ssq, lane);
+                    tot.add(u.nti * 2 + (c0 >> 5), ssum[0], ssq[0]);
+                }
+            }
+            if (c0 < p.nt) {
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t taddr = lane_addr + (uint32_t)((acc * 4 + c) * p.nt);
+                    uint32_t rr[16];
+                    tmem_ld16(taddr + c0, rr);
+                    tmem_ld_wait();
+                    epi_tail16(ef, out, rr, ok, off_of(lane, c) + c0);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));     // the leader's MMA thread waits for all 256
+        }
+        if (stats) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                stage_all[(lane_grp * 8 + i) * 32 + lane] = tot.s[i];
+                stage_all[(lane_grp * 8 + 4 + i) * 32 + lane] = tot.q[i];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (stat_partial != nullptr && warp == 2) stat_store_row(stage_all, stat_partial, p.Cout, p.nt, p.n_tiles, lane);
+    cluster_sync_all();                       // no CTA may leave (or free TMEM) while its peer can still signal / read it
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
 static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* wp, float* out, int N, int Cin,
                             int Cout, int Di, int Hi, int Wi, cudaStream_t st, const EpiFusion& ef, int* stat_rows,
                             bool query, int* addend_ok) {
@@ -1179,13 +1442,21 @@ static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* 
     p.tiles_h = (p.Rt + kTileH - 1) / kTileH;
     p.kchunks = Cin / kKChunk;
     p.b_bytes = p.nt * 128;
-    p.stage_bytes = kDcABytes + 6 * p.b_bytes;
+    // CTA-pair variant (cta_group::2): each CTA stages its A box and HALF of the weight rows (3 tiles' worth)
+    static int pair_env = -1;
+    if (pair_env < 0) { const char* e = getenv("B2_CONV_DC_PAIR"); pair_env = (e && e[0] == '0') ? 0 : 1; }
+    const bool pair = pair_env && p.nt % 16 == 0;
+    p.stage_bytes = kDcABytes + (pair ? 3 : 6) * p.b_bytes;
     p.stages = (212 * 1024) / p.stage_bytes;
     if (p.stages > kDcMaxStages) p.stages = kDcMaxStages;
     p.tmem_cols = 32;
     while (p.tmem_cols < 8 * p.nt) p.tmem_cols *= 2;
     p.total_units = (long long)p.n_tiles * N * p.Pt * 2 * p.tiles_h * p.tiles_w;
-    const int grid = (int)(p.total_units < kNumSMs ? p.total_units : kNumSMs);
+    int grid = (int)(p.total_units < kNumSMs ? p.total_units : kNumSMs);
+    if (pair) {
+        const long long pairs = (long long)p.n_tiles * N * p.Pt * 2 * p.tiles_h * ((p.tiles_w + 1) / 2);
+        grid = (int)(2 * (pairs < kNumSMs / 2 ? pairs : kNumSMs / 2));
+    }
     const bool stats_ok = N == 1 && p.nt % 32 == 0 && p.nt <= 64 && p.n_tiles <= 2;
     if (stat_rows) *stat_rows = stats_ok ? grid : 0;
     if (addend_ok) *addend_ok = 1;
@@ -1212,7 +1483,7 @@ static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* 
     {
         cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * Cout};
         cuuint64_t gstr[1] = {(cuuint64_t)Cin * 4};
-        cuuint32_t box[2] = {(cuuint32_t)kKChunk, (cuuint32_t)p.nt};
+        cuuint32_t box[2] = {(cuuint32_t)kKChunk, (cuuint32_t)(pair ? p.nt / 2 : p.nt)};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wp, gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1224,6 +1495,13 @@ static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* 
         static SmemOptIn optin;
         cudaError_t e = ensure_dynamic_smem(optin, conv3d_dc_tcgen05_kernel, smem);
         if (e != cudaSuccess) { set_error("conv3d(tcgen05,deconv): cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return (int)e; }
+    }
+    if (pair) {
+        static SmemOptIn optin2;
+        cudaError_t e2 = ensure_dynamic_smem(optin2, conv3d_dc2_tcgen05_kernel, smem);
+        if (e2 != cudaSuccess) { set_error("conv3d(tcgen05,deconv,pair): cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e2)); return (int)e2; }
+        conv3d_dc2_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p, ef);
+        return check_launch("conv3d(tcgen05,deconv,pair)");
     }
     conv3d_dc_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p, ef);
     return check_launch("conv3d(tcgen05,deconv)");

@@ -122,14 +122,16 @@ grid_sample2d_fwd_kernel(const float4* __restrict__ in, const float* __restrict_
 // instructions) for its one float4 per corner: 88 M warp instructions for the PSV sample = ~160 us of issue
 // time at IPC 2, the measured 190 us.  Re-ordering the voxels for L1 reuse (blocks of consecutive Z: the
 // corner rows of a column drift by less than a pixel per step) changed nothing -- 0.304-0.312 ms for every
-// block shape, tools/bench_lift.py.  Here 4 lanes own a voxel and each carries 4 float4 per corner (lane l ->
-// float4 l, l+4, l+8, l+12, so that one load instruction of the 4 lanes still covers 64 contiguous bytes):
-// the index arithmetic is amortised over 4x the data.
+// block shape, tools/bench_lift.py.  Here 8 lanes own a voxel and each carries 2 float4 per PSV corner (lane l ->
+// float4 l and l+8: one load instruction of the 8 lanes covers one whole 128 B line): the index arithmetic is
+// amortised over twice the data without raising the number of cache lines an instruction touches (a 4-lane /
+// 4-float4 variant, 64 B per voxel per instruction, doubled the L1 tag work per byte and needed 128 registers:
+// ncu l1tex 66 %, 21 % occupancy, 0.239 ms).
 // =============================================================================================
-__global__ void __launch_bounds__(256, 2)
+__global__ void __launch_bounds__(256, 3)
 lift_fwd_kernel(const float4* __restrict__ psv, const float4* __restrict__ img, const float* __restrict__ grid,
                 float* __restrict__ out, int N, int D, int H, int W, int Hi, int Wi, int64_t nvox_per_n, int align) {
-    constexpr int LPV = 4, R3 = 16, R2 = 8, CO = 96;        // lanes per voxel, float4 per PSV row / image row
+    constexpr int LPV = 8, R3 = 16, R2 = 8, CO = 96;        // lanes per voxel, float4 per PSV row / image row
     const int lane = threadIdx.x % LPV;
     const int64_t v = (int64_t)blockIdx.x * (256 / LPV) + threadIdx.x / LPV;
     if (v >= (int64_t)N * nvox_per_n) return;
@@ -137,15 +139,13 @@ lift_fwd_kernel(const float4* __restrict__ psv, const float4* __restrict__ img, 
     const float* g = grid + v * 3;
     float gg[3] = {__ldg(g), __ldg(g + 1), __ldg(g + 2)};
     const Corners3 c = corners3(gg, D, H, W, align);
-    float4 acc[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
     const bool any_in = c.z0 >= -1 && c.z0 < D && c.y0 >= -1 && c.y0 < H && c.x0 >= -1 && c.x0 < W;
     if (any_in) {
         const float4* base = psv + (int64_t)n * D * H * W * R3 + lane;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {               // two batches of 4 corners: 16 loads in flight per lane
-            float4 val[4][4];
+        for (int half = 0; half < 2; ++half) {               // two batches of 4 corners: 8 loads in flight per lane
+            float4 val[4][2];
             float wgt[4];
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
@@ -157,25 +157,23 @@ lift_fwd_kernel(const float4* __restrict__ psv, const float4* __restrict__ img, 
                 wgt[kk] = ok ? w : 0.f;
                 zz = min(max(zz, 0), D - 1); yy = min(max(yy, 0), H - 1); xx = min(max(xx, 0), W - 1);
                 const float4* row = base + (uint32_t)(((zz * H + yy) * W + xx) * R3);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) val[kk][q] = __ldg(row + 4 * q);
+                val[kk][0] = __ldg(row);
+                val[kk][1] = __ldg(row + LPV);
             }
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-#pragma unroll
-                for (int q = 0; q < 4; ++q) fma4(acc[q], wgt[kk], val[kk][q]);
+            for (int kk = 0; kk < 4; ++kk) { fma4(acc[0], wgt[kk], val[kk][0]); fma4(acc[1], wgt[kk], val[kk][1]); }
         }
     }
     float4* orow = reinterpret_cast<float4*>(out + v * CO) + lane;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) orow[4 * q] = acc[q];
+    orow[0] = acc[0];
+    orow[LPV] = acc[1];
     {
         // the image feature at the same (u, v); its size may differ from the PSV's, so its corners are recomputed
         float g2[3] = {gg[0], gg[1], -1.f};
         const Corners3 c2 = corners3(g2, 1, Hi, Wi, align);
         const float4* base2 = img + (int64_t)n * Hi * Wi * R2 + lane;
-        float4 a2[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
-        float4 v2[4][2];
+        float4 a2 = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 v2[4];
         float w2[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -185,14 +183,11 @@ lift_fwd_kernel(const float4* __restrict__ psv, const float4* __restrict__ img, 
             const float w = (dx ? c2.wx1 : 1.f - c2.wx1) * (dy ? c2.wy1 : 1.f - c2.wy1);
             w2[k] = ok ? w : 0.f;
             yy = min(max(yy, 0), Hi - 1); xx = min(max(xx, 0), Wi - 1);
-            const float4* row = base2 + (uint32_t)((yy * Wi + xx) * R2);
-            v2[k][0] = __ldg(row);
-            v2[k][1] = __ldg(row + 4);
+            v2[k] = __ldg(base2 + (uint32_t)((yy * Wi + xx) * R2));
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) { fma4(a2[0], w2[k], v2[k][0]); fma4(a2[1], w2[k], v2[k][1]); }
-        orow[R3] = a2[0];
-        orow[R3 + 4] = a2[1];
+        for (int k = 0; k < 4; ++k) fma4(a2, w2[k], v2[k]);
+        orow[R3] = a2;
     }
 }
 
@@ -414,13 +409,9 @@ extern "C" int b2_grid_sample_bwd(const float* gout, const int32_t* row_ptr, con
     cudaStream_t st = (cudaStream_t)stream;
     static int wide = -1;
     if (wide < 0) { const char* e = getenv("B2_GS_BWD_WIDE"); wide = (e && e[0] == '0') ? 0 : 1; }
-    // the DSGN widths take the wide-lane variants (several float4 per lane); any other width one float4 per lane
-    if (wide && C == 64 && !long_rows) {
-        int grid_x = stream_grid(ncell, 256 / 4, kNumSMs * 16);
-        grid_sample_bwd_kernel<4, 1, 4><<<grid_x, 256, 0, st>>>(gout, row_ptr, (const int2*)entries, (float4*)gin, ncell,
-                                                               gout_cstride, gout_coff);
-        return check_launch("grid_sample_bwd");
-    }
+    // Wide lanes (several float4 per lane, the entry load and address arithmetic amortised) pay on the long rows of the
+    // image-feature lift (0.051 -> 0.046 ms) but not on the ~6-entry rows of the PSV lift (0.188 -> 0.198 ms: the 4x
+    // fewer threads per cell hide the entry -> row latency worse), tools/bench_lift.py -- so only the former uses them.
     if (wide && C == 32 && long_rows) {
         int grid_x = stream_grid(ncell, 256 / 32, kNumSMs * 32);
         grid_sample_bwd_kernel<4, 8, 2><<<grid_x, 256, 0, st>>>(gout, row_ptr, (const int2*)entries, (float4*)gin, ncell,
@@ -451,7 +442,7 @@ extern "C" int b2_lift_fwd(const float* psv, const float* img, const float* grid
     B2_REQUIRE((int64_t)D * H * W * 16 < ((int64_t)1 << 31), "lift_fwd: input sample has more than 2^31 float4");
     const int64_t nvox = (int64_t)N * nvox_per_n;
     if (nvox == 0) return 0;
-    const int64_t nblk = (nvox + 63) / 64;
+    const int64_t nblk = (nvox + 31) / 32;
     B2_REQUIRE(nblk < ((int64_t)1 << 31), "lift_fwd: too many voxels");
     lift_fwd_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>((const float4*)psv, (const float4*)img, grid, out, N,
                                                                        D, H, W, Hi, Wi, nvox_per_n, align_corners);

@@ -36,15 +36,38 @@ __device__ __forceinline__ bool axis_interp(float p, int size, int& lo, int& hi,
     return true;
 }
 
+// FPN level of a RoI, attack/Stereo-RCNN/stereo_rcnn.py:113-119: round(log(sqrt(h w) / 224) + 4) clamped to
+// [2, 5] with h = y2 - y1 + 1, w = x2 - x1 + 1 -- NATURAL log and round-half-to-even, as torch.log / torch.round.
+__device__ __forceinline__ int roi_fpn_level(const float* roi) {
+    const float h = __fadd_rn(__fsub_rn(roi[4], roi[2]), 1.f), w = __fadd_rn(__fsub_rn(roi[3], roi[1]), 1.f);
+    float l = rintf(__fadd_rn(logf(__fdiv_rn(sqrtf(__fmul_rn(h, w)), 224.0f)), 4.f));
+    l = fminf(fmaxf(l, 2.f), 5.f);
+    return (int)l;
+}
+
+// The four pyramid levels of one view (stereo_rcnn.py:110-141): level l = 2..5 lives at index l - 2.
+struct PyrLevels {
+    const float* feat[4];
+    float* gfeat[4];
+    int H[4], W[4];
+    float scale[4];
+    long long pix_off[5];      // backward: prefix sums of H*W over the levels
+};
+
+template <bool PYR>
 __global__ void __launch_bounds__(256)
 roi_align_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ rois,
-                     float* __restrict__ out, int R, int C, int H, int W, int P, float scale) {
+                     float* __restrict__ out, int R, int C, int H, int W, int P, float scale, const PyrLevels lv) {
     const int64_t total = (int64_t)R * C * P * P;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (int64_t)gridDim.x * blockDim.x) {
         int pw = (int)(i % P), ph = (int)((i / P) % P);
         int c = (int)((i / ((int64_t)P * P)) % C), r = (int)(i / ((int64_t)P * P * C));
         const float* roi = rois + r * 5;
+        if (PYR) {                                   // the RoI's own level: one launch instead of one per level
+            const int l = roi_fpn_level(roi) - 2;
+            feat = lv.feat[l]; H = lv.H[l]; W = lv.W[l]; scale = lv.scale[l];
+        }
         RoiGeom g = roi_geom(roi, scale, P);
         int b = (int)roi[0];
         const float* f = feat + ((int64_t)b * C + c) * H * W;
@@ -85,11 +108,20 @@ __device__ __forceinline__ void roi_flush(const RoiEntry* e, int n, const float*
     }
 }
 
+template <bool PYR>
 __global__ void __launch_bounds__(128)
 roi_align_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ rois,
-                     float* __restrict__ gfeat, int R, int B, int C, int H, int W, int P, float scale) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (int64_t)B * H * W) return;
+                     float* __restrict__ gfeat, int R, int B, int C, int H, int W, int P, float scale, const PyrLevels lv) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int level = -1;
+    if (PYR) {                                       // pixel of which level?  (batch of 1)
+        if (i >= lv.pix_off[4]) return;
+        level = i >= lv.pix_off[3] ? 3 : (i >= lv.pix_off[2] ? 2 : (i >= lv.pix_off[1] ? 1 : 0));
+        i -= lv.pix_off[level];
+        gfeat = lv.gfeat[level]; H = lv.H[level]; W = lv.W[level]; scale = lv.scale[level];
+    } else if (i >= (int64_t)B * H * W) {
+        return;
+    }
     const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((int64_t)W * H));
     float* gp = gfeat + (int64_t)b * C * H * W + (int64_t)y * W + x;
     const int64_t cstride = (int64_t)H * W;
@@ -100,6 +132,7 @@ roi_align_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ r
     for (int r = 0; r < R; ++r) {
         const float* roi = rois + r * 5;
         if ((int)__ldg(roi) != b) continue;
+        if (PYR && roi_fpn_level(roi) - 2 != level) continue;
         const float sw = __ldg(roi + 1) * scale, sh = __ldg(roi + 2) * scale;
         const float ew = __ldg(roi + 3) * scale, eh = __ldg(roi + 4) * scale;
         const float rw = fmaxf(ew - sw, 1.f), rh = fmaxf(eh - sh, 1.f);
@@ -148,8 +181,8 @@ extern "C" int b2_roi_align_fwd(const float* feat, const float* rois, float* out
     B2_REQUIRE(P >= 1 && C >= 1 && H >= 1 && W >= 1, "roi_align_fwd: bad dims");
     int64_t total = (int64_t)R * C * P * P;
     if (total == 0) return 0;
-    roi_align_fwd_kernel<<<stream_grid(total, 256, kNumSMs * 32), 256, 0, (cudaStream_t)stream>>>(
-        feat, rois, out, R, C, H, W, P, scale);
+    roi_align_fwd_kernel<false><<<stream_grid(total, 256, kNumSMs * 32), 256, 0, (cudaStream_t)stream>>>(
+        feat, rois, out, R, C, H, W, P, scale, PyrLevels{});
     return check_launch("roi_align_fwd");
 }
 
@@ -159,7 +192,50 @@ extern "C" int b2_roi_align_bwd(const float* gout, const float* rois, float* gfe
     B2_REQUIRE(P >= 1 && C >= 1 && H >= 1 && W >= 1, "roi_align_bwd: bad dims");
     B2_REQUIRE((int64_t)R * C * P * P < ((int64_t)1 << 31), "roi_align_bwd: gout has more than 2^31 elements");
     const int64_t npix = (int64_t)H * W;     // batch of 1 (the attack scripts run batch size 1)
-    roi_align_bwd_kernel<<<(unsigned)((npix + 127) / 128), 128, 0, (cudaStream_t)stream>>>(gout, rois, gfeat, R, 1, C, H, W,
-                                                                                          P, scale);
+    roi_align_bwd_kernel<false><<<(unsigned)((npix + 127) / 128), 128, 0, (cudaStream_t)stream>>>(gout, rois, gfeat, R, 1, C, H, W,
+                                                                                                 P, scale, PyrLevels{});
     return check_launch("roi_align_bwd");
+}
+
+static int fill_levels(PyrLevels& lv, const float* const* feats, float* const* gfeats, const int* Hs, const int* Ws,
+                       float im_h, const char* who) {
+    lv.pix_off[0] = 0;
+    for (int l = 0; l < 4; ++l) {
+        if (Hs[l] < 1 || Ws[l] < 1 || (feats && !feats[l]) || (gfeats && !gfeats[l])) {
+            set_error("%s: bad pyramid level %d", who, l + 2);
+            return B2_ERR_BAD_ARG;
+        }
+        lv.feat[l] = feats ? feats[l] : nullptr;
+        lv.gfeat[l] = gfeats ? gfeats[l] : nullptr;
+        lv.H[l] = Hs[l]; lv.W[l] = Ws[l];
+        lv.scale[l] = (float)((double)Hs[l] / (double)im_h);   // stereo_rcnn.py:131: feat_maps[i].size(2) / im_info[0][0]
+        lv.pix_off[l + 1] = lv.pix_off[l] + (long long)Hs[l] * Ws[l];
+    }
+    return 0;
+}
+
+extern "C" int b2_roi_align_pyramid_fwd(const float* const* feats, const int* Hs, const int* Ws, const float* rois,
+                                        float* out, int R, int C, int P, float im_h, void* stream) {
+    B2_REQUIRE(feats && Hs && Ws && out && (rois || R == 0), "roi_align_pyramid_fwd: null pointer");
+    B2_REQUIRE(P >= 1 && C >= 1 && im_h > 0.f, "roi_align_pyramid_fwd: bad dims");
+    PyrLevels lv{};
+    if (int e = fill_levels(lv, feats, nullptr, Hs, Ws, im_h, "roi_align_pyramid_fwd")) return e;
+    int64_t total = (int64_t)R * C * P * P;
+    if (total == 0) return 0;
+    roi_align_fwd_kernel<true><<<stream_grid(total, 256, kNumSMs * 32), 256, 0, (cudaStream_t)stream>>>(
+        nullptr, rois, out, R, C, 0, 0, P, 0.f, lv);
+    return check_launch("roi_align_pyramid_fwd");
+}
+
+extern "C" int b2_roi_align_pyramid_bwd(const float* gout, const float* rois, float* const* gfeats, const int* Hs,
+                                        const int* Ws, int R, int C, int P, float im_h, void* stream) {
+    B2_REQUIRE(gfeats && Hs && Ws && (R == 0 || (gout && rois)), "roi_align_pyramid_bwd: null pointer");
+    B2_REQUIRE(P >= 1 && C >= 1 && im_h > 0.f, "roi_align_pyramid_bwd: bad dims");
+    B2_REQUIRE((int64_t)R * C * P * P < ((int64_t)1 << 31), "roi_align_pyramid_bwd: gout has more than 2^31 elements");
+    PyrLevels lv{};
+    if (int e = fill_levels(lv, nullptr, gfeats, Hs, Ws, im_h, "roi_align_pyramid_bwd")) return e;
+    const int64_t npix = lv.pix_off[4];
+    roi_align_bwd_kernel<true><<<(unsigned)((npix + 127) / 128), 128, 0, (cudaStream_t)stream>>>(gout, rois, nullptr, R, 1, C,
+                                                                                                0, 0, P, 0.f, lv);
+    return check_launch("roi_align_pyramid_bwd");
 }

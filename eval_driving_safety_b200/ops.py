@@ -556,6 +556,8 @@ def conv3d_fork(x, weight, stride=1, transposed=False, impl=None):
 # ---------------------------------------------------------------------------
 # True: error-compensated 3xTF32 (fp32-class accuracy -- the reference computes in fp32); False: plain TF32
 CONV2D_SPLIT = int(os.environ.get("B2_CONV2D_SPLIT", "1"))
+# A/B switch: operand split of the DATA-GRADIENT launches only (None = same as the forward)
+CONV2D_SPLIT_BWD = None if os.environ.get("B2_CONV2D_SPLIT_BWD") is None else int(os.environ["B2_CONV2D_SPLIT_BWD"])
 
 
 def set_conv2d_split(flag):
@@ -661,7 +663,8 @@ class Conv2dFn(Function):
             out = _conv2d_call(x, _packed2d(weight, "fwd", split), b, None, n, ci, co, hi, wi, kh, stride, dilation, 0,
                                split)
         ctx.weight = weight
-        ctx.cfg = (n, ci, co, hi, wi, kh, stride, dilation, first, split, bool(fork))
+        ctx.cfg = (n, ci, co, hi, wi, kh, stride, dilation, first, split if CONV2D_SPLIT_BWD is None else CONV2D_SPLIT_BWD,
+                   bool(fork))
         ctx.set_materialize_grads(False)
         if fork:
             return out, x.view_as(x)
@@ -976,3 +979,48 @@ class RoIAlignFn(Function):
 
 def roi_align(feat, rois, pooled, scale):
     return RoIAlignFn.apply(feat, rois, pooled, scale)
+
+
+class PyramidRoIAlignFn(Function):
+    """``_StereoRCNN.PyramidRoI_Feat`` (attack/Stereo-RCNN/stereo_rcnn.py:110-141) in one launch per direction: FPN level
+    per RoI evaluated in the kernel, output rows in the original RoI order, no host synchronisation."""
+
+    @staticmethod
+    def forward(ctx, rois, pooled, im_h, *feats):
+        _need_cuda(rois, *feats)
+        lib = _lib.load()
+        if len(feats) != 4 or any(f.shape[0] != 1 or f.shape[1] != feats[0].shape[1] for f in feats):
+            raise RuntimeError("pyramid_roi_align: four [1,C,H,W] maps (levels 2..5) expected")
+        feats = [f.contiguous() for f in feats]
+        rois = rois.contiguous()
+        r, c = rois.shape[0], feats[0].shape[1]
+        hs = (ctypes.c_int * 4)(*[f.shape[2] for f in feats])
+        ws = (ctypes.c_int * 4)(*[f.shape[3] for f in feats])
+        out = torch.empty((r, c, pooled, pooled), device=rois.device, dtype=torch.float32)
+        ptrs = ctypes.cast(_lib.ptr_array(feats), ctypes.POINTER(ctypes.c_void_p))
+        with _op("roi_align_fwd", 1, 4 * (sum(f.numel() for f in feats) + out.numel())):
+            check(lib.b2_roi_align_pyramid_fwd(ptrs, hs, ws, _p(rois), _p(out), r, c, pooled, float(im_h), _stream()),
+                  "roi_align_pyramid_fwd")
+        ctx.save_for_backward(rois)
+        ctx.cfg = (r, c, pooled, float(im_h), [tuple(f.shape) for f in feats])
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        lib = _lib.load()
+        (rois,) = ctx.saved_tensors
+        r, c, pooled, im_h, shapes = ctx.cfg
+        g = gout.contiguous()
+        gfeats = [torch.empty(s, device=g.device, dtype=torch.float32) for s in shapes]
+        hs = (ctypes.c_int * 4)(*[s[2] for s in shapes])
+        ws = (ctypes.c_int * 4)(*[s[3] for s in shapes])
+        ptrs = ctypes.cast(_lib.ptr_array(gfeats), ctypes.POINTER(ctypes.c_void_p))
+        with _op("roi_align_bwd", 1, 4 * (g.numel() + sum(t.numel() for t in gfeats))):
+            check(lib.b2_roi_align_pyramid_bwd(_p(g), _p(rois), ptrs, hs, ws, r, c, pooled, im_h, _stream()),
+                  "roi_align_pyramid_bwd")
+        return (None, None, None) + tuple(gfeats)
+
+
+def pyramid_roi_align(feat_maps, rois, im_h, pooled):
+    return PyramidRoIAlignFn.apply(rois, pooled, im_h, *feat_maps)

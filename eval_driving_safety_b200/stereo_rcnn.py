@@ -16,9 +16,16 @@ def roi_levels(rois):
 
 
 def pyramid_roi_feat(feat_maps, rois, im_h, pooled):
-    """``_StereoRCNN.PyramidRoI_Feat``: per level l in 2..5, RoIAlign(feat_l,
-    rois[level==l], scale = feat_l.H / im_h); concatenate; restore RoI order.
+    """``_StereoRCNN.PyramidRoI_Feat`` (stereo_rcnn.py:110-141) in ONE launch: the level of every RoI is evaluated
+    inside the kernel and its pooled row lands in the original RoI order, so the per-level ``nonzero`` index lists
+    (a host synchronisation each), the concatenation and the re-sort of the reference disappear.
     ``pooled`` = 7 (cfg.POOLING_SIZE) or 14 for the keypoint branch (:44-45)."""
+    return ops.pyramid_roi_align(feat_maps, rois, im_h, pooled)
+
+
+def pyramid_roi_feat_per_level(feat_maps, rois, im_h, pooled):
+    """The reference's own structure (one RoIAlign per level, concatenate, restore the order); kept as the
+    cross-check of the one-launch dispatch."""
     lvl = roi_levels(rois)
     feats, idxs = [], []
     for i, l in enumerate(range(2, 6)):

@@ -162,8 +162,8 @@ int b2_grid_sample_bwd(const float* gout, const int32_t* row_ptr, const void* en
 /* Fused lifting forward of DSGN (frustum -> voxel): out[v, 0:64] = trilinear sample of psv [N,D,H,W,64] at
  * grid[v] = (x,y,z), out[v, 64:96] = bilinear sample of img [N,Hi,Wi,32] at grid[v].xy; out [N*nvox_per_n, 96].
  * Same values, bit for bit, as b2_grid_sample3d_fwd + b2_grid_sample2d_fwd into the two channel slices; one
- * launch, the grid read once, 4 lanes per voxel (the generic kernels are instruction-issue bound on the corner
- * arithmetic every one of their 16 lanes repeats).  C3 = 64, C2 = 32 only. */
+ * launch, the grid read once, 8 lanes per voxel (the generic kernels repeat the corner arithmetic in every one of
+ * their 16 lanes).  C3 = 64, C2 = 32 only. */
 int b2_lift_fwd(const float* psv, const float* img, const float* grid, float* out, int N, int C3, int C2,
                 int D, int H, int W, int Hi, int Wi, int64_t nvox_per_n, int align_corners, void* stream);
 
@@ -313,6 +313,18 @@ int b2_roi_align_fwd(const float* feat, const float* rois, float* out, int R, in
                      int P, float scale, void* stream);
 int b2_roi_align_bwd(const float* gout, const float* rois, float* gfeat, int R, int C, int H, int W,
                      int P, float scale, void* stream);
+
+/* The whole FPN dispatch of _StereoRCNN.PyramidRoI_Feat (attack/Stereo-RCNN/stereo_rcnn.py:110-141) in ONE launch
+ * per direction: every RoI's level = clamp(round(log(sqrt(h w) / 224) + 4), 2, 5) (natural log, :113-119) is
+ * evaluated in the kernel, the RoI is pooled from feats[level - 2] with scale = Hs[level - 2] / im_h (:131), and its
+ * row of out [R,C,P,P] is written in the ORIGINAL RoI order -- no per-level index lists, concatenation or re-sort
+ * (:121-141), and no host synchronisation.  feats / gfeats: HOST arrays of 4 device pointers (levels 2..5, each
+ * [1,C,Hs[l],Ws[l]]); Hs, Ws: HOST int[4].  Backward: gather form over the pixels of all four maps, deterministic;
+ * every gfeats[l] is fully written. */
+int b2_roi_align_pyramid_fwd(const float* const* feats, const int* Hs, const int* Ws, const float* rois, float* out,
+                             int R, int C, int P, float im_h, void* stream);
+int b2_roi_align_pyramid_bwd(const float* gout, const float* rois, float* const* gfeats, const int* Hs, const int* Ws,
+                             int R, int C, int P, float im_h, void* stream);
 
 #ifdef __cplusplus
 }

@@ -19,8 +19,8 @@ print("cpu loss", loss_r.item(), "|g| max %.3e median %.3e" % (gL_r.abs().max().
 lab = {k: v.cuda() for k, v in labels.items()}
 adv_r = A.pgd_step_linf(pair["imgL"], gL_r, A.denormalize(pair["imgL"]), 8 / 255, 8 / 255)
 clean = pair["imgL"].cuda() * torch.tensor(A.IMAGENET_STD).view(1, 3, 1, 1).cuda() + torch.tensor(A.IMAGENET_MEAN).view(1, 3, 1, 1).cuda()
-for impl, tf32, bb, split in ((0, False, 'b2', 1), (0, False, 'b2', 3), (1, False, 'b2', 1), (1, False, 'b2', 3), (1, False, 'cudnn', 1)):
-    ops.set_conv_impl(impl); dsgn.set_backbone_impl(bb); ops.set_conv2d_split(split)
+for impl, tf32, bb, split, split_bwd in ((0, False, 'b2', 1, None), (0, False, 'b2', 1, 0), (0, False, 'b2', 0, 1)):
+    ops.set_conv_impl(impl); dsgn.set_backbone_impl(bb); ops.set_conv2d_split(split); ops.CONV2D_SPLIT_BWD = split_bwd
     torch.backends.cudnn.allow_tf32 = tf32; torch.backends.cuda.matmul.allow_tf32 = tf32
     a, b = pair["imgL"].cuda().requires_grad_(True), pair["imgR"].cuda().requires_grad_(True)
     out = model(a, b, *calib[:3], calibs_Proj_R=calib[3])
@@ -29,6 +29,7 @@ for impl, tf32, bb, split in ((0, False, 'b2', 1), (0, False, 'b2', 3), (1, Fals
     big = gL_r.abs() > 1e-2 * gL_r.abs().max()
     adv = attack.pgd_step(pair["imgL"].cuda(), gL.contiguous(), clean, 8 / 255, 8 / 255)
     same = ((adv.cpu() - adv_r).abs() < 1e-5).float().mean().item()
+    print("split_bwd=%s" % split_bwd, end=" ")
     print("impl=%d cudnn_tf32=%s backbone=%s split=%s same_px %.5f: depth %.2e cls %.2e reg %.2e loss %.2e gradL %.2e gradR %.2e sign@1%%max %.5f sign(all) %.5f" % (
         impl, tf32, bb, split, same, rel_err(out["depth_preds"].cpu(), out_r["depth_preds"]), rel_err(out["bbox_cls"].cpu(), out_r["bbox_cls"]),
         rel_err(out["bbox_reg"].cpu(), out_r["bbox_reg"]),
