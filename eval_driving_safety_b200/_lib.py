@@ -18,6 +18,7 @@ _IP = ctypes.POINTER(ctypes.c_int)
 SIGNATURES = {
     "b2_version": (c_int, []),
     "b2_last_error": (ctypes.c_char_p, []),
+    "b2_set_flag": (c_int, [ctypes.c_char_p, c_int]),
     "b2_pgd_update": (c_int, [_PP, _PP, _PP, _PP, c_int, c_int, c_int, c_i64, c_f32, c_f32, c_int,
                               _FP, _FP, _FP, _FP, c_vp]),
     "b2_pgd_update_l2_workspace_bytes": (c_i64, [c_int]),
@@ -97,6 +98,11 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+def set_flag(name, value):
+    """Kernel-variant switch (include/b2attack.h b2_set_flag); value None = back to the default."""
+    check(load().b2_set_flag(name.encode(), -1 if value is None else int(value)), "set_flag(%s)" % name)
 
 
 def last_error():

@@ -11,6 +11,11 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 void set_error(const char* fmt, ...);
 
+// Kernel-variant switches (A/B measurements, tests of both variants): value from b2_set_flag() if set, else from the
+// environment variable B2_<NAME>, else `dflt`.
+enum Flag { kFlagConvDcPair = 0, kFlagConv2dHalo = 1, kNumFlags };
+int flag_value(Flag f, const char* env_name, int dflt);
+
 inline int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -572,9 +572,7 @@ int conv2d_tcgen05_launch(const float* in, const float* wp, const float* bias, c
     while (p.tmem_cols < 2 * (p.stack ? 2 : 1) * p.nt) p.tmem_cols *= 2;
     p.total_tiles = (long long)p.n_tiles * (p.mode == 2 ? 4 : 1) * N * p.tiles_h * p.tiles_w;
 
-    static int halo_env = -1;
-    if (halo_env < 0) { const char* e = getenv("B2_CONV2D_HALO"); halo_env = (e && e[0] == '0') ? 0 : 1; }
-    const bool halo = halo_env && p.mode == 0 && ks == 3;
+    const bool halo = flag_value(kFlagConv2dHalo, "B2_CONV2D_HALO", 1) && p.mode == 0 && ks == 3;
     C2HaloParams hp{};
     if (halo) {
         hp.a_rows = kC2TileH + 2 * dil;

@@ -1278,7 +1278,7 @@ conv3d_dc2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                                     half_tile(sb + (uint32_t)b * half_b, tap_of(kh, 0), (int)rank);
                                 }
                             }
-                            if (!leader) mbar_arrive_cluster(fb);
+                            if (!leader) mbar_arrive_cluster_relaxed(fb);
                             if (++stage == p.stages) { stage = 0; phase ^= 1; }
                         }
                     }
@@ -1400,7 +1400,7 @@ conv3d_dc2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gri
                 }
             }
             tc_fence_before();
-            mbar_arrive_cluster(mapa_cluster(tempty_bar(acc), 0));     // the leader's MMA thread waits for all 256
+            mbar_arrive_cluster_relaxed(mapa_cluster(tempty_bar(acc), 0));     // the leader's MMA thread waits for all 256
         }
         if (stats) {
 #pragma unroll
@@ -1442,10 +1442,13 @@ static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* 
     p.tiles_h = (p.Rt + kTileH - 1) / kTileH;
     p.kchunks = Cin / kKChunk;
     p.b_bytes = p.nt * 128;
-    // CTA-pair variant (cta_group::2): each CTA stages its A box and HALF of the weight rows (3 tiles' worth)
-    static int pair_env = -1;
-    if (pair_env < 0) { const char* e = getenv("B2_CONV_DC_PAIR"); pair_env = (e && e[0] == '0') ? 0 : 1; }
-    const bool pair = pair_env && p.nt % 16 == 0;
+    // CTA-pair variant (cta_group::2, default): each CTA stages its A box and HALF of the weight rows (3 tiles' worth).
+    // Measured (tools/bench_conv3d_shapes.py, graph replay): 0.1806 vs 0.1975 ms on 128 -> 64 at 24x48x156, 0.0634 vs
+    // 0.0687 ms on 128 -> 128 at 12x24x78.  (The first version, whose cross-CTA mbarrier arrivals had cluster-scope RELEASE
+    // semantics, was 1.5x SLOWER than the single-CTA kernel: every epilogue thread then waits for its global stores to
+    // reach L2 before it may hand the accumulator back -- profiles/r2_conv3d_dc_pair_ncu.txt.)
+    // B2_CONV_DC_PAIR=0 / b2_set_flag("conv_dc_pair", 0) selects the single-CTA kernel.
+    const bool pair = flag_value(kFlagConvDcPair, "B2_CONV_DC_PAIR", 1) && p.nt % 16 == 0;
     p.stage_bytes = kDcABytes + (pair ? 3 : 6) * p.b_bytes;
     p.stages = (212 * 1024) / p.stage_bytes;
     if (p.stages > kDcMaxStages) p.stages = kDcMaxStages;

@@ -1,6 +1,7 @@
 // libb2attack.so: version, error reporting and the conv3d dispatcher.
 #include <stdarg.h>
 #include <string.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b2 {
@@ -20,9 +21,28 @@ int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, i
                           int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st,
                           const EpiFusion& ef, int* stat_rows, bool query, int* addend_ok);
 
+static int g_flags[kNumFlags] = {-1, -1};
+
+int flag_value(Flag f, const char* env_name, int dflt) {
+    if (g_flags[f] >= 0) return g_flags[f];
+    const char* e = getenv(env_name);
+    if (e && (e[0] == '0' || e[0] == '1')) return e[0] - '0';
+    return dflt;
+}
+
 }  // namespace b2
 
-extern "C" int b2_version(void) { return 100; }  // 0.1.0
+extern "C" int b2_version(void) { return 200; }  // 0.2.0
+
+extern "C" int b2_set_flag(const char* name, int value) {
+    B2_REQUIRE(name, "set_flag: null name");
+    int idx = -1;
+    if (!strcmp(name, "conv_dc_pair")) idx = b2::kFlagConvDcPair;
+    else if (!strcmp(name, "conv2d_halo")) idx = b2::kFlagConv2dHalo;
+    B2_REQUIRE(idx >= 0, "set_flag: unknown flag '%s'", name);
+    b2::g_flags[idx] = value < 0 ? -1 : (value ? 1 : 0);
+    return 0;
+}
 
 extern "C" const char* b2_last_error(void) { return b2::g_err; }
 

@@ -133,6 +133,12 @@ __device__ __forceinline__ uint32_t mapa_cluster(uint32_t saddr, uint32_t rank) 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
     asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
 }
+// relaxed form: the arrival orders nothing but itself (the TMEM reads it stands for were already completed by
+// tcgen05.wait::ld + tcgen05.fence::before_thread_sync); a cluster-scope RELEASE would first have to push the epilogue's
+// global stores out to L2
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
 // TMA loads of a CTA pair: the bytes land in THIS CTA's smem, the transaction count goes to the mbarrier at the
 // given shared::cluster address (the leader CTA's barrier)
 __device__ __forceinline__ void tma_load_5d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1,

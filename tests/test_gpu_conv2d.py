@@ -135,6 +135,27 @@ def test_first_layer_fwd_dgrad_vs_torch(ops, dims):
     assert max_err(y.cpu(), ref) < 2e-5 and max_err(gx.cpu(), gx_ref) < 2e-5
 
 
+def test_conv2d_halo_kernel_equals_the_tap_per_stage_kernel(ops, built_lib):
+    """Stride-1 3x3 layers have two kernels (halo reuse, the default; one tap per stage): the same products summed in
+    another order (kw-major instead of tap-major) -> equal to fp32 rounding, dilation 1 and 2, with and without the split."""
+    from eval_driving_safety_b200 import _lib
+    g = torch.Generator().manual_seed(21)
+    for (cin, cout, dil) in ((64, 64, 1), (128, 128, 2), (320, 128, 1)):
+        x = torch.randn(2, cin, 37, 29, generator=g).cuda()
+        wt = (torch.randn(cout, cin, 3, 3, generator=g) / (3 * cin ** 0.5)).cuda()
+        res = []
+        try:
+            for halo in (1, 0):
+                _lib.set_flag("conv2d_halo", halo)
+                for split in (1, 0):
+                    ops.set_conv2d_split(split)
+                    res.append(ops.conv2d(x, wt, None, 1, dil))
+        finally:
+            _lib.set_flag("conv2d_halo", None)
+            ops.set_conv2d_split(1)
+        assert rel_err(res[0], res[2]) < 1e-5 and rel_err(res[1], res[3]) < 1e-5
+
+
 def test_conv2d_rejects_unsupported(ops):
     x = torch.randn(1, 24, 8, 8).cuda()
     with pytest.raises(RuntimeError):
