@@ -395,25 +395,50 @@ def run_srcnn(args):
     tg = {k: v.to(dev) for k, v in S.synthetic_targets(256, seed=rank).items()}
     hl, hr = il.pin_memory(), ir.pin_memory()
     rl, rr = rl.to(dev), rr.to(dev)
-    st = {"xl": il.to(dev), "xr": ir.to(dev), "cl": il.to(dev), "cr": ir.to(dev)}
+    xl, xr, cl, cr = il.to(dev), ir.to(dev), il.to(dev), ir.to(dev)
     eps255 = 255 * 0.03
+    lo = [0 - m for m in attack.STEREO_RCNN_MEANS]
+    hi = [255 - m for m in attack.STEREO_RCNN_MEANS]
+
+    def iteration():
+        """one PGD iteration in place on xl / xr (attack/Stereo-RCNN/pgd_attack.py:151-217)"""
+        a, b = xl.detach().requires_grad_(True), xr.detach().requires_grad_(True)
+        loss = model(a, b, rl, rr, tg)
+        gl, gr = torch.autograd.grad(loss, [a, b])
+        attack.pgd_step(xl, gl.contiguous(), cl, 1.0, eps255, mean=None, std=None, lo=lo, hi=hi, out=xl)
+        attack.pgd_step(xr, gr.contiguous(), cr, 1.0, eps255, mean=None, std=None, lo=lo, hi=hi, out=xr)
+        return loss.detach()
+
+    # the one-launch RoIAlign dispatch has no host synchronisation, so the whole iteration is graph-capturable
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            iteration()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
     n0 = ops.LAUNCH_COUNT
+    graph = torch.cuda.CUDAGraph()
+    if args.eager:
+        loss_buf = None
+    else:
+        with torch.cuda.graph(graph):
+            loss_buf = iteration()
+    launches = ops.LAUNCH_COUNT - n0 if not args.eager else 8
+    xl.copy_(cl); xr.copy_(cr)
 
     def step():
-        xl, xr = st["xl"].requires_grad_(True), st["xr"].requires_grad_(True)
-        loss = model(xl, xr, rl, rr, tg)
-        gl, gr = torch.autograd.grad(loss, [xl, xr])
-        st["xl"] = attack.stereo_rcnn_pgd_step(xl.detach(), gl.contiguous(), st["cl"], 1.0, eps255)
-        st["xr"] = attack.stereo_rcnn_pgd_step(xr.detach(), gr.contiguous(), st["cr"], 1.0, eps255)
-        return loss.detach()
+        if args.eager:
+            return iteration()
+        graph.replay()
+        return loss_buf
     ms = _timed(step, args.steps, args.warmup, dev, world)
-    launches = (ops.LAUNCH_COUNT - n0) // (args.steps + args.warmup)
     h_loss = torch.zeros((), pin_memory=True)
 
     def e2e():
-        st["xl"], st["xr"] = hl.to(dev, non_blocking=True), hr.to(dev, non_blocking=True)
+        xl.copy_(hl, non_blocking=True); xr.copy_(hr, non_blocking=True)
         h_loss.copy_(step(), non_blocking=True)
-        hl.copy_(st["xl"], non_blocking=True); hr.copy_(st["xr"], non_blocking=True)
+        hl.copy_(xl, non_blocking=True); hr.copy_(xr, non_blocking=True)
         torch.cuda.current_stream().synchronize()
     for _ in range(2):
         e2e()
@@ -436,7 +461,8 @@ def run_srcnn(args):
           "data": "synthetic",
           "config": {"workload": "BASELINE configs[4]: Stereo R-CNN PGD (RoIAlign fwd/bwd path), 600x1987 pairs, 256 RoIs per view, "
                                  "alpha 1.0, eps 0.03*255; Stereo-R-CNN-shaped stand-in network (the real detector is un-vendored)",
-                     "parallelism": "dp%d (pairs sharded, no data-path collective)" % world, "execution": "eager"},
+                     "parallelism": "dp%d (pairs sharded, no data-path collective)" % world,
+                     "execution": "eager" if args.eager else "CUDA graph of one PGD iteration, replayed"},
           "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                   "h2d_bytes_per_step": 2 * 3 * 600 * 1987 * 4, "d2h_bytes_per_step": 2 * 3 * 600 * 1987 * 4 + 4},
           "gpu_launches": launches * units})
