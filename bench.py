@@ -231,7 +231,16 @@ def run_b200(args):
     units = PAIRS_PER_GPU * world * args.steps
     peaks = measured_peaks()
     conv = kern.get("conv3d_tcgen05", dict(calls=0, ms=0.0, work=0, per_s=0.0))
-    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0     # kind::tf32 issues at half the bf16 rate
+    # TF32 roofline: MEASURED cuBLAS TF32 rate of this GPU class (tools/measure_tf32_peak.py -> profiles/r2_tf32_peak.json,
+    # 8192^3, sustained = back to back for 4 s, like the driver's bf16 figure); if that file is absent, half the driver's
+    # measured bf16 rate (kind::tf32 issues at half the bf16 rate -- nominal, cuBLAS reaches less: 605 vs 691 TFLOP/s)
+    tf32_peak, tf32_src = peaks["bf16_tflops_sustained"] / 2.0, "%s bf16_tflops_sustained / 2" % peaks["source"]
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_tf32_peak.json")) as f:
+            tf32_peak = float(json.load(f)["tf32_tflops_sustained"])
+        tf32_src = "profiles/r2_tf32_peak.json tf32_tflops_sustained (cuBLAS TF32 8192^3 back to back, measured on this pool's B200)"
+    except Exception:
+        pass
     kernels = {}
     for name, k in sorted(kern.items()):
         if name.startswith("conv3d_tcgen05") or name.startswith("conv3d_simt") or name.startswith("conv2d_tcgen05"):
@@ -246,12 +255,16 @@ def run_b200(args):
         "config": {"workload": WORKLOAD,
                    "pairs_per_gpu": PAIRS_PER_GPU, "image": [H, W], "psv": [64, 48, 96, 312],
                    "voxels": [96, 192, 20, 304], "parallelism": "dp%d (pairs sharded, no data-path collective)" % world,
-                   "backbone_2d": {"b2": "own tcgen05 kernels, %s" % ("3xTF32 error-compensated split in-kernel (fp32-class)"
-                                                                    if ops.CONV2D_SPLIT else "plain TF32"),
+                   "backbone_2d": {"b2": "own tcgen05 kernels, %s" % (
+                       ("forward: 3xTF32 error-compensated split in-kernel (fp32-class); data gradient: %s"
+                        % ("3xTF32" if ops.CONV2D_SPLIT_BWD else "plain TF32, like the 3-D convs")) if ops.CONV2D_SPLIT else "plain TF32"),
                                    "cudnn": "cuDNN %s (A/B mode)" % ("fp32" if args.backbone_fp32 else "TF32"),
                                    "cudnn_tf32x3": "cuDNN TF32 x3 stacked on the host (A/B mode)"}[dsgn.BACKBONE_IMPL],
                    "execution": "eager" if args.eager else
                    "CUDA graph of %d concurrent pair-iteration(s) on parallel streams, replayed" % lanes,
+                   "parity_of_this_mode": "tests/test_gpu_fullsize.py on this exact engine: per-iteration gradient-sign agreement mean "
+                                          "99.944 % / min 99.901 %, updated pixels identical to the CPU oracle mean 98.34 % / min 98.17 % "
+                                          "(10 iterations x 2 full-size pairs); cost volume bit-exact",
                    "l2_policy": "per-iteration working set (~10 GB of activations per pair) is far larger than the 126 MB L2"},
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "warmup": e2e_warm},
@@ -265,7 +278,8 @@ def run_b200(args):
                      "traffic": 709.2e6,
                      "traffic_source": "profiles/r1_conv3d_final_ncu.txt (conv3d_s1n_tcgen05_kernel, 64->64 48x96x312: "
                                        "389.3 MB read + 319.8 MB written vs 736 MB algorithmic)",
-                     "peak_source": "%s bf16_tflops_sustained/2 (TF32 rate; kernel timed inside a long step)" % peaks["source"],
+                     "peak_source": tf32_src + "; kernel timed inside a long step",
+                     "frac_of_half_bf16_sustained": conv["per_s"] / 1e12 / (peaks["bf16_tflops_sustained"] / 2.0),
                      "frac_of_bf16_peak": conv["per_s"] / 1e12 / peaks["bf16_tflops_sustained"],
                      "launches": conv["calls"], "avg_launch_ms": conv["ms"] / max(conv["calls"], 1),
                      "note": "conv flops only: about a third of the launches also add up GroupNorm statistics / backward "

@@ -1510,6 +1510,152 @@ static int conv3d_dc_launch(EncodeTiledFn encode, const float* in, const float* 
     return check_launch("conv3d(tcgen05,deconv)");
 }
 
+// =============================================================================================
+// Generic (one tap per stage) kernel on a CTA PAIR, for the stride-2 convs (and the stride-2-conv-shaped data
+// gradients of the transposed convs): two CTAs of one TPC take two w-adjacent output tiles of the same
+// (sample, plane, row block); per (tap, K chunk) stage each stages its own A box (16 KB) and HALF of the weight
+// tile's rows, the leader issues tcgen05.mma.cta_group::2 of M = 256, N = Cout.  Bytes arriving per SM per stage:
+// 16 + Cout*64 B instead of 16 + Cout*128 B (24 vs 32 KB at Cout = 128).  Barrier scheme as in
+// conv3d_dc2_tcgen05_kernel (leader-side "full" and "accumulator free", multicast commits, relaxed cross-CTA arrivals).
+// =============================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+conv3d_g2_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                         float* __restrict__ out, const TcParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ __align__(8) uint64_t bars[2 * kMaxStages + 4];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bar0 = smem_u32(bars);
+    auto full_bar = [&](int s) { return bar0 + 8u * s; };
+    auto empty_bar = [&](int s) { return bar0 + 8u * (kMaxStages + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * kMaxStages + 2 + a); };
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(full_bar(s), 2); mbar_init(empty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(&tmem_base_slot)), "r"((uint32_t)p.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+    const int wpairs = (p.tiles_w + 1) / 2;
+    const long long total_pairs = (long long)p.N * p.Dt * p.tiles_h * wpairs;
+    const long long pair0 = blockIdx.x >> 1, pstride = gridDim.x >> 1;
+    auto decode = [&](long long t) {
+        TileCoord c;
+        c.w0 = ((int)(t % wpairs) * 2 + (int)rank) * kTileW; t /= wpairs;
+        c.h0 = (int)(t % p.tiles_h) * kTileH; t /= p.tiles_h;
+        c.d = (int)(t % p.Dt); t /= p.Dt;
+        c.n = (int)t;
+        c.cls = 0;
+        return c;
+    };
+    const uint32_t half_b = (uint32_t)(p.Cout / 2) * 128u;
+    const int s = p.mode == 1 ? 2 : 1;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int stage = 0; uint32_t phase = 0;
+            const uint32_t mine = (uint32_t)kABytes + half_b;
+            for (long long t = pair0; t < total_pairs; t += pstride) {
+                const TileCoord tc = decode(t);
+                for (int tap_i = 0; tap_i < 27; ++tap_i) {
+                    const int kd = tap_i / 9, kh = (tap_i / 3) % 3, kw = tap_i % 3;
+                    const int aw = s * tc.w0 + kw - 1, ah = s * tc.h0 + kh - 1, ad = s * tc.d + kd - 1;
+                    const int tap = p.swap ? (kh * 3 + kd) * 3 + kw : (kd * 3 + kh) * 3 + kw;
+                    for (int kc = 0; kc < p.kchunks; ++kc) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t fb = mapa_cluster(full_bar(stage), 0);
+                        if (leader) mbar_expect_tx(full_bar(stage), 2u * mine);
+                        const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                        tma_load_5d_pair(sa, &map_a, fb, kc * kKChunk, aw, ah, ad, tc.n);
+                        tma_load_2d_pair(sa + kABytes, &map_b, fb, kc * kKChunk, tap * p.Cout + (int)rank * (p.Cout / 2));
+                        if (!leader) mbar_arrive_cluster_relaxed(fb);
+                        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            const uint32_t idesc = umma_idesc_tf32(256, p.Cout);
+            int stage = 0; uint32_t phase = 0;
+            long long it = 0;
+            for (long long t = pair0; t < total_pairs; t += pstride, ++it) {
+                const int acc = (int)(it & 1);
+                mbar_wait(tempty_bar(acc), (uint32_t)(((it >> 1) & 1) ^ 1));
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)(acc * p.Cout);
+                const int nsteps = 27 * p.kchunks;
+                for (int st = 0; st < nsteps; ++st) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_base + (uint32_t)stage * p.stage_bytes;
+                    const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kKChunk / 8; ++k)
+                        umma_tf32_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (st | k) != 0);
+                    umma_commit_pair(empty_bar(stage));
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit_pair(tfull_bar(acc));
+            }
+        }
+        __syncwarp();
+    } else {
+        const int lane_grp = warp & 3;
+        const int m = lane_grp * 32 + lane;
+        const int hl = m / kTileW, wl = m % kTileW;
+        long long it = 0;
+        for (long long t = pair0; t < total_pairs; t += pstride, ++it) {
+            const int acc = (int)(it & 1);
+            const TileCoord tc = decode(t);
+            const int h = tc.h0 + hl, w = tc.w0 + wl;
+            const bool ok = h < p.Ht && w < p.Wt;
+            const int od = p.swap ? h : tc.d, oh = p.swap ? tc.d : h;
+            float* optr = out + ((((long long)tc.n * p.Do + od) * p.Ho + oh) * p.Wo + w) * p.Cout;
+            mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * p.Cout);
+            for (int c0 = 0; c0 < p.Cout; c0 += 32) {
+                uint32_t r[32];
+                tmem_ld32(taddr + c0, r);
+                tmem_ld_wait();
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<float4*>(optr + c0 + 4 * j) =
+                            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                                        __uint_as_float(r[4 * j + 3]));
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster_relaxed(mapa_cluster(tempty_bar(acc), 0));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    }
+}
+
 int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, int Cin, int Cout, int Di,
                           int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st,
                           const EpiFusion& ef, int* stat_rows, bool query, int* addend_ok) {
@@ -1560,7 +1706,9 @@ int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, i
     p.tiles_w = (p.Wt + kTileW - 1) / kTileW;
     p.tiles_h = (p.Ht + kTileH - 1) / kTileH;
     p.kchunks = Cin / kKChunk;
-    p.stage_bytes = kABytes + Cout * 128;
+    // stride-1 / stride-2 CONV launches that land here run on a CTA pair (see conv3d_g2_tcgen05_kernel)
+    const bool gpair = p.mode != 2 && Cout % 64 == 0 && flag_value(kFlagConvG2Pair, "B2_CONV_G2_PAIR", 1);
+    p.stage_bytes = kABytes + (gpair ? Cout * 64 : Cout * 128);
     p.stages = (200 * 1024) / p.stage_bytes;
     if (p.stages > kMaxStages) p.stages = kMaxStages;
     p.tmem_cols = 32;
@@ -1588,7 +1736,7 @@ int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, i
     {
         cuuint64_t gdim[2] = {(cuuint64_t)Cin, (cuuint64_t)27 * Cout};
         cuuint64_t gstr[1] = {(cuuint64_t)Cin * 4};
-        cuuint32_t box[2] = {(cuuint32_t)kKChunk, (cuuint32_t)Cout};
+        cuuint32_t box[2] = {(cuuint32_t)kKChunk, (cuuint32_t)(gpair ? Cout / 2 : Cout)};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)wp, gdim, gstr, box, estr,
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1603,6 +1751,15 @@ int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, i
         if (e != cudaSuccess) { set_error("conv3d(tcgen05): cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e)); return (int)e; }
     }
     int grid = (int)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
+    if (gpair) {
+        const long long pairs = (long long)N * p.Dt * p.tiles_h * ((p.tiles_w + 1) / 2);
+        grid = (int)(2 * (pairs < kNumSMs / 2 ? pairs : kNumSMs / 2));
+        static SmemOptIn optin2;
+        cudaError_t e2 = ensure_dynamic_smem(optin2, conv3d_g2_tcgen05_kernel, smem);
+        if (e2 != cudaSuccess) { set_error("conv3d(tcgen05,pair): cudaFuncSetAttribute(%d): %s", smem, cudaGetErrorString(e2)); return (int)e2; }
+        conv3d_g2_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p);
+        return check_launch("conv3d(tcgen05,pair)");
+    }
     conv3d_tcgen05_kernel<<<grid, kTcThreads, smem, st>>>(map_a, map_b, out, p);
     return check_launch("conv3d(tcgen05)");
 }

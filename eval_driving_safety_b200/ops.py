@@ -35,8 +35,11 @@ TF32_ROUND_WEIGHTS = os.environ.get("B2_TF32_ROUND_WEIGHTS", "0") != "0"
 
 
 def set_conv_impl(impl):
-    global CONV_IMPL
+    """0 = the benchmarked path (tcgen05 TF32 3-D convs; 2-D convs: 3xTF32 forward, plain-TF32 data gradient);
+    1 = verification mode: fp32 SIMT 3-D convs and the 3xTF32 split in the 2-D data gradients too."""
+    global CONV_IMPL, CONV2D_SPLIT_BWD
     CONV_IMPL = int(impl)
+    CONV2D_SPLIT_BWD = 1 if CONV_IMPL == 1 else int(os.environ.get("B2_CONV2D_SPLIT_BWD", "0"))
 
 
 def _stream():
@@ -556,8 +559,14 @@ def conv3d_fork(x, weight, stride=1, transposed=False, impl=None):
 # ---------------------------------------------------------------------------
 # True: error-compensated 3xTF32 (fp32-class accuracy -- the reference computes in fp32); False: plain TF32
 CONV2D_SPLIT = int(os.environ.get("B2_CONV2D_SPLIT", "1"))
-# A/B switch: operand split of the DATA-GRADIENT launches only (None = same as the forward)
-CONV2D_SPLIT_BWD = None if os.environ.get("B2_CONV2D_SPLIT_BWD") is None else int(os.environ["B2_CONV2D_SPLIT_BWD"])
+# Operand split of the DATA-GRADIENT launches.  Default 0 = plain TF32: the backward pass is LINEAR in the gradient it
+# propagates (the linearisation point -- activations, GroupNorm statistics, ReLU masks -- comes from the forward, which
+# keeps the split), so a 2^-11 operand error perturbs a gradient entry by ~1e-3 relative per layer and cannot flip its
+# sign unless the entry is already ~0; the 3-D convs work the same way in both directions.  Measured on the timed path
+# (tests/test_gpu_fullsize.py, 10 iterations x 2 pairs): sign agreement mean 99.944 % / min 99.901 %, identical pixels
+# mean 98.338 % / min 98.167 % -- the same to four digits as with the split in both directions (98.337 / 98.182), at
+# 43.1 instead of 40.2 pair-iterations/s.  B2_CONV2D_SPLIT_BWD=1 splits the data gradients too.
+CONV2D_SPLIT_BWD = int(os.environ.get("B2_CONV2D_SPLIT_BWD", "0"))
 
 
 def set_conv2d_split(flag):
@@ -663,7 +672,7 @@ class Conv2dFn(Function):
             out = _conv2d_call(x, _packed2d(weight, "fwd", split), b, None, n, ci, co, hi, wi, kh, stride, dilation, 0,
                                split)
         ctx.weight = weight
-        ctx.cfg = (n, ci, co, hi, wi, kh, stride, dilation, first, split if CONV2D_SPLIT_BWD is None else CONV2D_SPLIT_BWD,
+        ctx.cfg = (n, ci, co, hi, wi, kh, stride, dilation, first, (split if CONV2D_SPLIT_BWD else 0),
                    bool(fork))
         ctx.set_materialize_grads(False)
         if fork:

@@ -19,7 +19,7 @@ print("cpu loss", loss_r.item(), "|g| max %.3e median %.3e" % (gL_r.abs().max().
 lab = {k: v.cuda() for k, v in labels.items()}
 adv_r = A.pgd_step_linf(pair["imgL"], gL_r, A.denormalize(pair["imgL"]), 8 / 255, 8 / 255)
 clean = pair["imgL"].cuda() * torch.tensor(A.IMAGENET_STD).view(1, 3, 1, 1).cuda() + torch.tensor(A.IMAGENET_MEAN).view(1, 3, 1, 1).cuda()
-for impl, tf32, bb, split, split_bwd in ((0, False, 'b2', 1, None), (0, False, 'b2', 1, 0), (0, False, 'b2', 0, 1)):
+for impl, tf32, bb, split, split_bwd in ((0, False, 'b2', 1, 0), (0, False, 'b2', 1, 1), (0, False, 'b2', 0, 0)):
     ops.set_conv_impl(impl); dsgn.set_backbone_impl(bb); ops.set_conv2d_split(split); ops.CONV2D_SPLIT_BWD = split_bwd
     torch.backends.cudnn.allow_tf32 = tf32; torch.backends.cuda.matmul.allow_tf32 = tf32
     a, b = pair["imgL"].cuda().requires_grad_(True), pair["imgR"].cuda().requires_grad_(True)

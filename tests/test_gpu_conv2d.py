@@ -49,12 +49,20 @@ def test_conv2d_fwd_dgrad_vs_torch(ops, case, split):
     gy = torch.randn(ref.shape, generator=g)
     (gx_ref,) = torch.autograd.grad(ref, x, gy)
     ops.set_conv2d_split(split)
+    saved_bwd = ops.CONV2D_SPLIT_BWD
+    ops.CONV2D_SPLIT_BWD = 1                  # this test is about the kernels: split (or not) in BOTH directions
     try:
         xc = x.detach().cuda().requires_grad_(True)
         y = ops.conv2d(xc, wt.cuda(), b.cuda() if has_bias else None, stride, dil)
         gx = torch.autograd.grad(y, xc, gy.cuda())[0] if cout != 16 else None   # the data gradient's K is Cout
+        if split and gx is not None:
+            ops.CONV2D_SPLIT_BWD = 0          # the benchmarked default: forward split, plain-TF32 data gradient
+            y0 = ops.conv2d(xc, wt.cuda(), b.cuda() if has_bias else None, stride, dil)
+            (gx0,) = torch.autograd.grad(y0, xc, gy.cuda())
+            assert torch.equal(y0, y) and rel_err(gx0.cpu(), gx_ref) < TOL_TF32
     finally:
         ops.set_conv2d_split(True)
+        ops.CONV2D_SPLIT_BWD = saved_bwd
     tol = TOL_SPLIT if split else TOL_TF32
     assert y.shape == ref.shape
     print("conv2d %s split=%s: rel. error fwd %.2e dgrad %s" % (case, split, rel_err(y.cpu(), ref),

@@ -3,8 +3,8 @@
 BASELINE config 1 (single-step FGSM, one 384x1248 pair) and config 2 (10-iteration L-inf PGD, eps 0.03,
 alpha eps/4) on full-size synthetic pairs with the random-init DSGN-shaped model: the CPU oracle loop
 (oracle/, stock torch fp32 ops) against exactly what bench.py times -- ``engine.PgdIterationGraph(lanes=2)``
-replaying the CUDA graph of two concurrent pair-iterations, tcgen05 TF32 3-D convs (impl 0), own 3xTF32
-2-D convs, every fused kernel.  north_star: "outputs must match ... within a stated tolerance on cost
+replaying the CUDA graph of two concurrent pair-iterations, tcgen05 TF32 3-D convs (impl 0), own 2-D convs
+(3xTF32 forward, plain-TF32 data gradient: the defaults), every fused kernel.  north_star: "outputs must match ... within a stated tolerance on cost
 volume, input gradient and final perturbation, with an identical perturbation sign pattern outside
 near-zero gradients".
 

@@ -221,11 +221,14 @@ TC_CASES = [c for c in CONV_CASES if c[0] % 32 == 0 and c[1] % 32 == 0] + [
 
 @pytest.fixture(params=[0, 1], ids=["single-cta", "cta-pair"])
 def dc_pair(request, built_lib):
-    """Both variants of the transposed-conv kernel: single-CTA and the tcgen05 cta_group::2 CTA pair (default)."""
+    """Both variants of the transposed-conv and of the stride-2 (one tap per stage) kernel: single-CTA and the tcgen05
+    cta_group::2 CTA pair (default)."""
     from eval_driving_safety_b200 import _lib
     _lib.set_flag("conv_dc_pair", request.param)
+    _lib.set_flag("conv_s2_pair", request.param)
     yield request.param
     _lib.set_flag("conv_dc_pair", None)
+    _lib.set_flag("conv_s2_pair", None)
 
 
 @pytest.mark.parametrize("case", TC_CASES)

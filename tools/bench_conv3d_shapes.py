@@ -35,16 +35,19 @@ def timeit(fn, iters=10):
 from eval_driving_safety_b200 import _lib
 for pair in (0, 1):
   _lib.set_flag("conv_dc_pair", pair)
-  print("conv_dc_pair =", pair)
+  _lib.set_flag("conv_s2_pair", pair)
+  print("conv_dc_pair = conv_s2_pair =", pair)
   for name, x, w, stride, mode in (
           ("deconv 128->64  @24x48x156", cl(1, 128, 24, 48, 156), (torch.randn(27, 64, 128, generator=g) * 0.02).to(dev), 2, 1),
           ("deconv 128->128 @12x24x78 ", cl(1, 128, 12, 24, 78), (torch.randn(27, 128, 128, generator=g) * 0.02).to(dev), 2, 1),
           ("deconv 128->64  @96x10x152 (3DGV)", cl(1, 128, 96, 10, 152), (torch.randn(27, 64, 128, generator=g) * 0.02).to(dev), 2, 1),
-          ("conv s2 64->128 @48x96x312", cl(1, 64, 48, 96, 312), (torch.randn(27, 128, 64, generator=g) * 0.02).to(dev), 2, 0)):
+          ("conv s2 64->128 @48x96x312", cl(1, 64, 48, 96, 312), (torch.randn(27, 128, 64, generator=g) * 0.02).to(dev), 2, 0),
+        ("conv s2 128->128 @24x48x156", cl(1, 128, 24, 48, 156), (torch.randn(27, 128, 128, generator=g) * 0.02).to(dev), 2, 0),
+        ("conv s2 64->128 @192x20x304 (3DGV)", cl(1, 64, 192, 20, 304), (torch.randn(27, 128, 64, generator=g) * 0.02).to(dev), 2, 0)):
       n, cin, d, h, wd = x.shape
       cout = w.shape[1]
       vox = n * d * h * wd if mode == 1 else n * (d // 2) * (h // 2) * (wd // 2)
       fl = 2 * cin * cout * 27 * vox
       t = timeit(lambda: ops._conv_call(x, w, stride, mode, 0))
       print("  %s: %.4f ms  %.0f TFLOP/s" % (name, t, fl / t / 1e9), flush=True)
-_lib.set_flag("conv_dc_pair", None)
+_lib.set_flag("conv_dc_pair", None); _lib.set_flag("conv_s2_pair", None)
