@@ -1,10 +1,7 @@
 #!/bin/bash
 tag=${1:-b}
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_volume.py tests/test_gpu_properties.py -q -m gpu --maxfail=10 > gpurun_out/${tag}_pytest_conv.log 2>&1
-rc=$?; echo "conv tests rc=$rc"; tail -6 gpurun_out/${tag}_pytest_conv.log
-timeout 300 python tools/bench_conv3d_shapes.py > gpurun_out/${tag}_conv3d_shapes.log 2>&1; cat gpurun_out/${tag}_conv3d_shapes.log
-timeout 900 python -m pytest tests -q -m gpu --maxfail=10 --deselect tests/test_gpu_fullsize.py --deselect tests/test_gpu_volume.py --deselect tests/test_gpu_properties.py > gpurun_out/${tag}_pytest.log 2>&1
-echo "other gpu tests rc=$?"; tail -8 gpurun_out/${tag}_pytest.log
-timeout 900 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
-echo "bench rc=$?"; head -c 200 gpurun_out/${tag}_bench.json
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${tag}_launches.csv python tools/one_iter.py 3 > gpurun_out/${tag}_one_iter.log 2>&1
+echo "launch list rc=$?"; tail -2 gpurun_out/${tag}_one_iter.log; wc -l gpurun_out/${tag}_launches.csv
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"lift_fwd|grid_sample_bwd|conv2d_halo|conv3d_dc2|conv3d_g2|cost_volume_bwd_row|pgd_update" -s 9 -c 9 -o gpurun_out/${tag}_prof -f python tools/prof_r2.py > gpurun_out/${tag}_ncu.log 2>&1
+echo "ncu rc=$?"; tail -2 gpurun_out/${tag}_ncu.log
