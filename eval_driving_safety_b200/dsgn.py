@@ -513,6 +513,51 @@ def attack_loss(cfg, outputs, disp_true, labels):
     return loss
 
 
+def decode_detections(cfg, outputs, proj, score_thresh=0.5, topk=20, cls_id=2):
+    """Stand-in for the upstream post-processor the reference calls before ``kitti_output``
+    (attack/DSGN/predict_and_save_pgd.py:220-283; un-vendored): the inverse of the stand-in target assignment
+    ``synthetic.labels_from_box3d`` -- BEV cells whose best anchor's sigmoid score passes ``score_thresh`` (at most
+    ``topk``, highest first) become boxes (h, w, l, centre, ry) from that anchor's 7 regression channels; the 2-D box is
+    the projection of the 8 corners with ``proj`` [3,4].  Returns a list of dicts in the format
+    ``kitti_io.write_detections`` takes (cls 2 = 'Car', the class of the reference's fake ground truth).
+    One host synchronisation: meant for the hand-off after an attack, not for the iteration."""
+    import math
+    cls = torch.sigmoid(outputs['bbox_cls'][0].float())                 # [A, Z, X]
+    reg = outputs['bbox_reg'][0].float()
+    a, zz, xx = cls.shape
+    score, anchor = cls.max(0)
+    flat = score.flatten()
+    k = min(int(topk), flat.numel())
+    top, idx = torch.topk(flat, k)
+    keep = top >= score_thresh
+    top, idx, anchor = top[keep].cpu(), idx[keep].cpu(), anchor.flatten()[idx[keep]].cpu()
+    reg = reg.cpu()
+    P = torch.as_tensor(proj, dtype=torch.float64).reshape(3, 4)
+    dets = []
+    for s, i, an in zip(top.tolist(), idx.tolist(), anchor.tolist()):
+        iz, ix = divmod(i, xx)
+        zc = cfg.z_range[0] + (iz + 0.5) * cfg.voxel
+        xc = cfg.x_range[0] + (ix + 0.5) * cfg.voxel
+        r = reg[an * cfg.reg_dim:(an + 1) * cfg.reg_dim, iz, ix].tolist()
+        x, y, z = xc + r[0], r[1], zc + r[2]
+        h, w, l = (math.exp(min(max(v, -4.0), 4.0)) for v in r[3:6])
+        ry = an * math.pi / 2 + r[6]
+        # 8 corners (KITTI camera frame: x right, y down, z forward; the box stands on y + h/2)
+        cs, sn = math.cos(ry), math.sin(ry)
+        corners = []
+        for dx in (-l / 2, l / 2):
+            for dz in (-w / 2, w / 2):
+                for dy in (-h / 2, h / 2):
+                    corners.append((x + cs * dx + sn * dz, y + dy, z - sn * dx + cs * dz))
+        pts = torch.tensor(corners, dtype=torch.float64)
+        uvw = torch.cat([pts, torch.ones(8, 1, dtype=torch.float64)], 1) @ P.t()
+        zc_ = uvw[:, 2].clamp_min(1e-3)
+        u, v = uvw[:, 0] / zc_, uvw[:, 1] / zc_
+        dets.append(dict(cls=cls_id, bbox=[u.min().item(), v.min().item(), u.max().item(), v.max().item()],
+                         hwl=(h, w, l), center3d=(x, y, z), ry=ry, score=s))
+    return dets
+
+
 def build_model(cfg=None, seed=1, device='cuda'):
     """Seeded default-PyTorch init (reference default seed 1, pgd_attack.py:41, 86),
     frozen, eval() (:140), on ``device``."""

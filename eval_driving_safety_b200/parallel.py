@@ -9,7 +9,7 @@ import os
 import torch
 import torch.distributed as dist
 
-STAT_FIELDS = ("pair", "loss_0", "loss_K", "linf", "l2", "frac_changed", "depth_err_clean", "depth_err_adv")
+STAT_FIELDS = ("pair", "loss_0", "loss_K", "linf", "l2", "frac_changed", "n_det_clean", "n_det_adv")
 
 
 def init(backend=None, device=None):
@@ -37,14 +37,14 @@ def shard_pairs(num_pairs, rank_=None, world=None):
     return list(range(rank_, num_pairs, world))
 
 
-def pair_stats(pair, losses, adv01, clean01, depth_err_clean=float('nan'), depth_err_adv=float('nan')):
+def pair_stats(pair, losses, adv01, clean01, n_det_clean=float('nan'), n_det_adv=float('nan')):
     """Fixed-size statistics row for one attacked pair (device tensor [len(STAT_FIELDS)])."""
     delta = (adv01 - clean01).flatten()
     row = torch.stack([
         torch.tensor(float(pair), device=delta.device), losses[0].float(), losses[-1].float(),
         delta.abs().max(), delta.norm(), (delta != 0).float().mean(),
-        torch.tensor(float(depth_err_clean), device=delta.device),
-        torch.tensor(float(depth_err_adv), device=delta.device)])
+        torch.tensor(float(n_det_clean), device=delta.device),
+        torch.tensor(float(n_det_adv), device=delta.device)])
     return row
 
 

@@ -50,6 +50,16 @@ def _setup(args):
     return rank, world, dev, cfg, (h, w), model, calib, labels
 
 
+def _write_detections(args, model, cfg, calib, index, xL, xR, tag):
+    """Detections of the (clean / attacked) pair in the reference's KITTI hand-off format
+    (attack/DSGN/predict_and_save_pgd.py:249-283) under ``<detections>/<tag>/%06d.txt``; returns their number."""
+    with torch.no_grad():
+        out = model(xL, xR, calib[0], calib[1], calib[2], calibs_Proj_R=calib[3])
+    dets = dsgn.decode_detections(cfg, out, calib[2][0], score_thresh=args.score_thresh)
+    kitti_io.write_detections(os.path.join(args.detections, tag), index, dets)
+    return len(dets)
+
+
 def run_pgd(args):
     rank, world, dev, cfg, (h, w), model, calib, labels = _setup(args)
     mean = torch.tensor(attack.IMAGENET_MEAN, device=dev).view(1, 3, 1, 1)
@@ -65,12 +75,17 @@ def run_pgd(args):
                                            norm=args.norm, use_graph=not args.eager)
         if args.save_dir:
             save_pair(args.save_dir, 0, i, xL, xR, w, h, writer)
+        n_clean = n_adv = float('nan')
+        if args.detections:
+            n_clean = _write_detections(args, model, cfg, calib, i, xL, xR, "clean")
         losses = []
         for k in range(args.iter):
             losses.append(eng.step(xL, xR, cL, cR, disp, calib=calib).clone())
             if args.save_dir:
                 save_pair(args.save_dir, k + 1, i, xL, xR, w, h, writer)
-        rows.append(parallel.pair_stats(i, losses, xL * std + mean, cL))
+        if args.detections:
+            n_adv = _write_detections(args, model, cfg, calib, i, xL, xR, "adv")
+        rows.append(parallel.pair_stats(i, losses, xL * std + mean, cL, n_clean, n_adv))
     if writer is not None:
         writer.close()
     stats = parallel.gather_stats(rows, args.pairs)
@@ -226,6 +241,8 @@ def main(argv=None):
     a.add_argument("--eps", type=float, default=0.3)                     # :55
     a.add_argument("--norm", default="linf", choices=["linf", "l2"])
     a.add_argument("--stats-out", default=None, help="rank 0 saves the gathered per-pair statistics [pairs, fields] here")
+    a.add_argument("--detections", default=None, help="write clean / attacked detections as KITTI txt files under this directory")
+    a.add_argument("--score-thresh", type=float, default=0.5)
     b = sub.add_parser("patch")
     b.add_argument("--iter", type=int, default=2)                        # patch_attack.py:53
     b.add_argument("--eps", type=float, default=8 / 255)                 # :54

@@ -337,3 +337,17 @@ def test_pyramid_roi_align_one_launch_matches_the_per_level_dispatch_and_the_ora
         assert max_err(a, b) < 1e-5 and rel_err(a.cpu(), r) < 1e-5     # (P = 14 sums ~200 terms per pixel: 1.7e-4 absolute)
     g_two = torch.autograd.grad(S.pyramid_roi_feat(fa, rois.cuda(), float(im_h), pooled), fa, gy.cuda())
     assert all(torch.equal(a, b) for a, b in zip(g_one, g_two))
+
+
+def test_runner_writes_detections_for_the_evaluation_stage(built_lib, tmp_path):
+    """runner pgd --detections: clean and attacked detections of every pair as KITTI txt files (the hand-off the
+    reference's predict scripts produce, predict_and_save_pgd.py:249-283), counts gathered into the statistics."""
+    from eval_driving_safety_b200 import kitti_io, parallel, runner
+    stats = runner.main(["pgd", "--tiny", "--pairs", "2", "--iter", "1", "--alpha", "0.0075", "--eps", "0.03",
+                         "--detections", str(tmp_path), "--score-thresh", "0.0"])
+    for tag in ("clean", "adv"):
+        for i in range(2):
+            dets = kitti_io.read_detections(str(tmp_path / tag / ("%06d.txt" % i)))
+            assert 1 <= len(dets) <= 20 and all(d["type"] == "Car" and 0.0 <= d["score"] <= 1.0 for d in dets)
+    col = parallel.STAT_FIELDS.index("n_det_clean")
+    assert (stats[:, col] >= 1).all() and (stats[:, col + 1] >= 1).all()

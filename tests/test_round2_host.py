@@ -220,3 +220,33 @@ def test_geometry_against_hand_computed_values():
         z50 = 2.0 + 50.5 * 0.2
         assert abs(g0[0].item() - (2 * (cu / 4) / 311 - 1)) < 1e-5
         assert abs(g0[1].item() - (2 * ((f * 0.9 / z50 + cv) / 4) / 95 - 1)) < 1e-5
+
+
+# ---------------------------------------------------------------- detections hand-off (8f-3)
+def test_decode_detections_inverts_the_target_assignment_and_writes_kitti_files(tmp_path):
+    """labels_from_box3d (fake car of attack/DSGN/patch_attack.py:342-354) -> ideal head outputs -> decode_detections ->
+    kitti_io.write_detections (predict_and_save_pgd.py:249-283 format) -> read back: the car comes out where it was put."""
+    from eval_driving_safety_b200 import attack, dsgn, kitti_io, synthetic
+    cfg = dsgn.default_cfg()
+    bbox, box3d = synthetic.make_targets(4, 2)
+    attack.inject_fake_gt(bbox, box3d)
+    lab = synthetic.labels_from_box3d(cfg, box3d)
+    out = {"bbox_cls": lab["cls"] * 20 - 10 + lab["ctr"] * lab["cls"], "bbox_reg": lab["reg"]}    # most confident at the centre
+    _, _, P, _ = synthetic.make_calib(1)
+    dets = dsgn.decode_detections(cfg, out, P[0], score_thresh=0.5, topk=5)
+    assert 1 <= len(dets) <= 5 and dets[0]["score"] > 0.99
+    h, w, l, x, y, z, th = attack.FAKE_GT_BOX3D
+    d = dets[0]
+    assert max(abs(a - b) for a, b in zip(d["hwl"], (h, w, l))) < 1e-4
+    assert max(abs(a - b) for a, b in zip(d["center3d"], (x, y, z))) < 1e-4
+    assert abs(math.remainder(d["ry"] - th, 2 * math.pi)) < 1e-4
+    # the projected 2-D box contains the projection of the centre and lies around the reference's fake 2-D box
+    u = 721.5377 * x / z + 609.5593
+    assert d["bbox"][0] < u < d["bbox"][2] and abs((d["bbox"][0] + d["bbox"][2]) / 2 - (569.33 + 613.91) / 2) < 8
+    path = kitti_io.write_detections(str(tmp_path), 7, dets)
+    back = kitti_io.read_detections(path)
+    assert os.path.basename(path) == "000007.txt" and len(back) == len(dets) and back[0]["type"] == "Car"
+    assert abs(back[0]["location"][2] - z) < 1e-4 and abs(back[0]["location"][1] - (y + h / 2)) < 1e-4
+    # nothing above the threshold -> empty file, as the reference writes for an image without detections
+    none = dsgn.decode_detections(cfg, {"bbox_cls": torch.full_like(lab["cls"], -10.0), "bbox_reg": lab["reg"]}, P[0])
+    assert none == [] and kitti_io.read_detections(kitti_io.write_detections(str(tmp_path), 8, none)) == []
