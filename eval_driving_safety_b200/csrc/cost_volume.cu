@@ -282,12 +282,24 @@ cost_volume_fwd_row(const float4* __restrict__ left, const float4* __restrict__ 
 }
 
 // partial[seg][n][h][w][2C] (left half then right half of every voxel row)
+//
+// Round 2: software-pipelined with cp.async.  The first version loaded a plane's row into registers, used it, and only
+// then asked for the next plane: one HBM round trip per plane exposed, 120 registers, one block per SM (ncu: DRAM 56 %).
+// Now the WHOLE row (both halves, 2C x W floats = 80 KB at KITTI size) of plane d+1 streams into the second smem buffer
+// with cp.async (L1-bypassing .cg, no registers) while plane d is consumed from the first; the left half accumulates
+// straight from smem, the right half is gathered from it as before.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int C4>
 __global__ void __launch_bounds__(kCvRowThreads)
 cost_volume_bwd_row(const float4* __restrict__ gcost, const float* __restrict__ shifts,
                     float4* __restrict__ partial, int N, int D, int H, int W, int dseg) {
     constexpr int Q = 2 * C4, WL = kCvRowThreads / Q;
-    extern __shared__ float4 s_g[];                     // [2][W][C4] right-half gradient row, double buffered
+    extern __shared__ float4 s_g[];                     // [2][W][Q]: whole gradient rows of two planes
     __shared__ int s_s0[kCvMaxD];
     __shared__ float s_f[kCvMaxD];
     const int h = blockIdx.x, n = blockIdx.y, seg = blockIdx.z;
@@ -299,45 +311,45 @@ cost_volume_bwd_row(const float4* __restrict__ gcost, const float* __restrict__ 
     }
     const int q = threadIdx.x % Q, wl = threadIdx.x / Q;
     const bool is_left = q < C4;
+    const int row4 = W * Q;                              // float4 per row
+    auto prefetch = [&](int d, int buf) {
+        const float4* g = gcost + ((((int64_t)n * D + d) * H + h) * W) * Q;
+        float4* dst = s_g + buf * row4;
+        for (int i = threadIdx.x; i < row4; i += kCvRowThreads) cp_async16(dst + i, g + i);
+        cp_async_commit();
+    };
     float4 acc[kCvMaxW32];
 #pragma unroll
     for (int k = 0; k < kCvMaxW32; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncthreads();
+    if (d_lo < d_hi) prefetch(d_lo, 0);
     for (int d = d_lo; d < d_hi; ++d) {
-        const float4* g = gcost + ((((int64_t)n * D + d) * H + h) * W) * Q + threadIdx.x;
+        const int buf = (d - d_lo) & 1;
+        cp_async_wait_all();
+        __syncthreads();                                // plane d has landed; everybody is done with the other buffer
+        if (d + 1 < d_hi) prefetch(d + 1, buf ^ 1);
         const int s0 = s_s0[d];
         const float f = s_f[d];
-        float4* sg = s_g + ((d - d_lo) & 1) * W * C4;
-        float4 v[kCvMaxW32];
-#pragma unroll
-        for (int k = 0; k < kCvMaxW32; ++k)             // whole row: one coalesced 16 B load per position
-            v[k] = (wl + k * WL < W) ? ldg_stream(g + k * kCvRowThreads) : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4* sg = s_g + buf * row4;
         if (is_left) {
 #pragma unroll
             for (int k = 0; k < kCvMaxW32; ++k) {
-                const float m = (wl + k * WL - s0 >= 0) ? 1.f : 0.f;
-                acc[k].x += m * v[k].x; acc[k].y += m * v[k].y; acc[k].z += m * v[k].z; acc[k].w += m * v[k].w;
+                const int w = wl + k * WL;
+                if (w < W && w - s0 >= 0) {
+                    const float4 v = sg[w * Q + q];
+                    acc[k].x += v.x; acc[k].y += v.y; acc[k].z += v.z; acc[k].w += v.w;
+                }
             }
         } else {
-#pragma unroll
-            for (int k = 0; k < kCvMaxW32; ++k) {
-                const int w = wl + k * WL;
-                if (w < W) sg[w * C4 + (q - C4)] = v[k];
-            }
-        }
-        __syncthreads();                                // row staged (the other buffer is free for d+1)
-        if (!is_left) {
-            const float4* sr = sg + (q - C4);
             const float a = 1.f - f;
 #pragma unroll
             for (int k = 0; k < kCvMaxW32; ++k) {
                 const int wa = wl + k * WL + s0;        // gR[x] += (1-f) G[x+s0] + f G[x+s0+1]
                 if (wa < W) {
-                    const float4 t = sr[wa * C4];
+                    const float4 t = sg[wa * Q + q];
                     acc[k].x += a * t.x; acc[k].y += a * t.y; acc[k].z += a * t.z; acc[k].w += a * t.w;
                 }
                 if (wa + 1 < W) {
-                    const float4 t = sr[(wa + 1) * C4];
+                    const float4 t = sg[(wa + 1) * Q + q];
                     acc[k].x += f * t.x; acc[k].y += f * t.y; acc[k].z += f * t.z; acc[k].w += f * t.w;
                 }
             }
@@ -425,11 +437,11 @@ extern "C" int b2_cost_volume_bwd(const float* gcost, const float* shifts, float
         const int row_bytes = W * C * 4;
         if (workspace && C == 32 && W <= 32 * kCvMaxW32 && H <= 65535 && N <= 65535 && aligned16(workspace)) {
             static SmemOptIn optin;
-            cudaError_t ea = ensure_dynamic_smem(optin, cost_volume_bwd_row<8>, 100 * 1024);
+            cudaError_t ea = ensure_dynamic_smem(optin, cost_volume_bwd_row<8>, 200 * 1024);
             if (ea != cudaSuccess) { set_error("cost_volume_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(ea)); return (int)ea; }
             const int nseg = D >= 2 * kCvBwdSegs ? kCvBwdSegs : 1;
             const int dseg = (D + nseg - 1) / nseg;
-            cost_volume_bwd_row<8><<<dim3(H, N, nseg), kCvRowThreads, 2 * row_bytes, st>>>(
+            cost_volume_bwd_row<8><<<dim3(H, N, nseg), kCvRowThreads, 4 * row_bytes, st>>>(
                 (const float4*)gcost, shifts, (float4*)workspace, N, D, H, W, dseg);
             const int64_t nrows = (int64_t)N * H * W;
             cost_volume_bwd_combine<<<stream_grid(nrows * (C / 2), 256, kNumSMs * 8), 256, 0, st>>>(

@@ -301,10 +301,12 @@ class LiftFn(Function):
         n, c3 = psv.shape[:2]
         c2 = img.shape[1]
         z, y, x = grid3.shape[1:4]
-        grid2 = grid3[..., :2].contiguous().view(n, z * y, x, 2)
+        fused = c3 == 64 and c2 == 32 and LIFT_FUSED
+        # the 2-channel copy of the grid is only needed by the un-fused 2-D sampler and to build a missing plan
+        grid2 = None if (fused and plan2 is not None) else grid3[..., :2].contiguous().view(n, z * y, x, 2)
         out = empty_cl3(n, c3 + c2, z, y, x, psv.device)
-        if c3 == 64 and c2 == 32 and LIFT_FUSED:
-            # one launch for both samplings, 4 lanes per voxel
+        if fused:
+            # one launch for both samplings, 8 lanes per voxel
             d, h, w = psv.shape[2:]
             work = 4 * (psv.numel() + img.numel() + grid3.numel() + out.numel())
             with _op("lift_fwd", 1, work):
