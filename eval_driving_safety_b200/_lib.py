@@ -52,6 +52,9 @@ SIGNATURES = {
                                 c_int, c_int, c_int, c_vp]),
     "b2_conv2d": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                           c_int, c_int, c_vp]),
+    "b2_conv2d_fused": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                c_int, c_int, c_int, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "b2_conv2d_stat_rows": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "b2_conv2d_first_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "b2_conv2d_first_dgrad": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "b2_conv3d_c1_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),

@@ -96,13 +96,136 @@ __device__ __forceinline__ void c2_tap(const C2Params& p, const C2Tile& tc, int 
     tap = tap_i;
 }
 
+// ---------------------------------------------------------------- epilogue: bias, addend, GroupNorm sums, store
+// What rides along while an accumulator tile is drained (all optional):
+//   bias / addend : out = conv + bias + addend (addend = the other consumers' gradient of a forked tensor)
+//   stat_mode 1   : per-channel (sum, sum of squares) of the OUTPUT = the statistics pass of the GroupNorm that follows
+//   stat_mode 2/3 : the launch writes the gradient gy w.r.t. the output of a GroupNorm (+ReLU) whose input was gn_x:
+//                   per-channel (sum gz*x, sum gz), gz = gy (2) or gy * [fma(x, scale, shift) > 0] (3: the ReLU mask
+//                   recomputed with the forward's own scale / shift) = the statistics pass of that norm's backward.
+// Sums are kept per CTA and per sample in shared memory (one row per epilogue warp) and written as row blockIdx.x of
+// the table [N][gridDim.x][2][Cout] when the CTA's tile sequence leaves a (channel tile, sample) -- fixed order, no
+// atomics: bitwise reproducible for a given grid.
+constexpr int kC2StatMaxNt = 128;
+
+struct C2Epi {
+    const float* bias;
+    const float* addend;
+    int stat_mode;
+    float* stat_partial;
+    const float* gn_x;
+    const float* gn_coef;        // sample 0: scale[Cout], shift[Cout]; sample n at + n * gn_coef_stride
+    int gn_coef_stride;
+};
+
+// v[0..15] = s, v[16..31] = q of this lane's pixel for 16 channels; on return v[0] of lane l is the warp total of
+// s[l] (l < 16) or q[l - 16] (l >= 16).  Recursive halving, 31 shuffles, fixed order.
+__device__ __forceinline__ void c2_transpose_sum32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = upper ? v[i] : v[i + off];
+            const float keep = upper ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+    }
+}
+
+// grp = epilogue group (0: warps 2-5; 1: warps 6-9, which drain every other tile when no operand split keeps them
+// busy); each group owns table row blockIdx.x * ngroups + grp and named barrier 1 + grp.
+__device__ __forceinline__ void c2_stat_flush(const C2Params& p, const C2Epi& e, int key, float (*tot)[2][kC2StatMaxNt],
+                                              int lane_grp, int lane, int grp, int ngroups) {
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");   // the group's four warps walk the same tile sequence
+    if (lane_grp == 0) {
+        const int n = key % p.N, nti = key / p.N;
+        float* row = e.stat_partial + (((long long)n * gridDim.x + blockIdx.x) * ngroups + grp) * 2 * p.Cout + nti * p.nt;
+        for (int c = lane; c < p.nt; c += 32) {
+            row[c] = ((tot[0][0][c] + tot[1][0][c]) + tot[2][0][c]) + tot[3][0][c];
+            row[p.Cout + c] = ((tot[0][1][c] + tot[1][1][c]) + tot[2][1][c]) + tot[3][1][c];
+        }
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+    for (int c = lane; c < 2 * kC2StatMaxNt; c += 32) (&tot[lane_grp][0][0])[c] = 0.f;
+    __syncwarp();
+}
+
+// One accumulator tile: TMEM -> registers (+ second half of a stacked accumulator) -> +bias +addend -> sums -> st.global.
+// off = element offset of this lane's output pixel (channel tile included); ok = the pixel exists.
+__device__ __forceinline__ void c2_epilogue_tile(const C2Params& p, const C2Epi& e, const C2Tile& tc, float* __restrict__ out,
+                                                 uint32_t taddr, bool active, bool ok, long long off, int lane,
+                                                 float (*mytot)[kC2StatMaxNt]) {
+    float* optr = out + off;
+    const float* aptr = e.addend ? e.addend + off : nullptr;
+    const float* xptr = e.stat_mode >= 2 ? e.gn_x + off : nullptr;
+    const float* bptr = e.bias ? e.bias + tc.nti * p.nt : nullptr;
+    const float* cptr = e.stat_mode == 3 ? e.gn_coef + (long long)tc.n * e.gn_coef_stride + tc.nti * p.nt : nullptr;
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c0 = 0; c0 < p.nt; c0 += 16) {
+        float4 av[4], xv[4];
+        // operand rows requested before the accumulator is waited for
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            av[q] = (aptr && ok) ? __ldg(reinterpret_cast<const float4*>(aptr + c0) + q) : z4;
+            xv[q] = (xptr && ok) ? __ldg(reinterpret_cast<const float4*>(xptr + c0) + q) : z4;
+        }
+        uint32_t r[16];
+        if (active) {
+            tmem_ld16(taddr + c0, r);
+            if (p.stack) {                                    // + the x_hi*w_lo half of the accumulator
+                uint32_t r2[16];
+                tmem_ld16(taddr + p.nt + c0, r2);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+            } else {
+                tmem_ld_wait();
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) r[j] = 0u;
+        }
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 t = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                                   __uint_as_float(r[4 * q + 3]));
+            if (bptr) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(bptr + c0) + q);
+                t.x += b.x; t.y += b.y; t.z += b.z; t.w += b.w;
+            }
+            if (aptr) { t.x += av[q].x; t.y += av[q].y; t.z += av[q].z; t.w += av[q].w; }
+            v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+            if (ok) *reinterpret_cast<float4*>(optr + c0 + 4 * q) = t;
+        }
+        if (e.stat_mode) {
+            float sq[32];
+            if (e.stat_mode == 1) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { const float u = ok ? v[j] : 0.f; sq[j] = u; sq[16 + j] = u * u; }
+            } else {
+                const float* x = reinterpret_cast<const float*>(xv);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float g = ok ? v[j] : 0.f;
+                    if (cptr && !(fmaf(x[j], __ldg(cptr + c0 + j), __ldg(cptr + p.Cout + c0 + j)) > 0.f)) g = 0.f;
+                    sq[j] = g * x[j]; sq[16 + j] = g;
+                }
+            }
+            c2_transpose_sum32(sq, lane);
+            mytot[lane >> 4][c0 + (lane & 15)] += sq[0];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(kC2Threads, 1)
 conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                      float* __restrict__ out, const float* __restrict__ bias, const float* __restrict__ addend,
-                      const C2Params p) {
+                      float* __restrict__ out, const C2Epi epi, const C2Params p) {
     extern __shared__ uint8_t smem_raw[];
     __shared__ __align__(8) uint64_t bars[3 * kC2MaxStages + 4];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float stat_tot[2][4][2][kC2StatMaxNt];      // [epilogue group][warp][sum | second sum][channel]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -209,70 +332,51 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
             }
         }
         __syncwarp();
-    } else if (warp < 6) {
-        // ===================== epilogue (4 warps, one output pixel row per thread) =====================
+    } else if (warp < 6 || !p.split) {
+        // ===================== epilogue (one output pixel row per thread) =====================
+        // warps 2-5; without the operand split warps 6-9 are a second group: group g drains accumulator g
+        const int grp = warp >= 6 ? 1 : 0, ngroups = p.split ? 1 : 2;
         const int lane_grp = warp & 3;                            // TMEM lanes [32*lane_grp, +32)
         const int m = lane_grp * 32 + lane;
         const int hl = m / kC2TileW, wl = m % kC2TileW;
-        long long it = 0;
-        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
+        const bool stats = epi.stat_mode != 0;
+        float (*tot)[2][kC2StatMaxNt] = stat_tot[grp];
+        if (stats) {
+            for (int c = lane; c < 2 * kC2StatMaxNt; c += 32) (&tot[lane_grp][0][0])[c] = 0.f;
+            __syncwarp();
+        }
+        int cur_key = 0;
+        long long it = 0, ti = 0;
+        for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++ti) {
             const C2Tile tc = c2_decode(p, t);
-            const int h = tc.h0 + hl, w = tc.w0 + wl;
-            const bool ok = h < p.Ht && w < p.Wt;
-            int oh = h, ow = w;
-            if (p.mode == 2) { oh = 2 * h + ((tc.cls >> 1) & 1); ow = 2 * w + (tc.cls & 1); }
-            const long long off = (((long long)tc.n * p.Ho + oh) * p.Wo + ow) * p.out_cstride + tc.nti * p.nt;
-            float* optr = out + off;
-            const float* aptr = addend ? addend + off : nullptr;
+            if (stats)
+                for (const int key = tc.nti * p.N + tc.n; cur_key < key; ++cur_key)
+                    c2_stat_flush(p, epi, cur_key, tot, lane_grp, lane, grp, ngroups);
             const bool active = c2_taps(p, tc.cls) != 0;
             const int acc = (int)(it & 1);
-            if (active) {
-                mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
-                tc_fence_after();
-            }
-            const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * (p.stack ? 2 * p.nt : p.nt));
-            const float* bptr = bias ? bias + tc.nti * p.nt : nullptr;
-            for (int c0 = 0; c0 < p.nt; c0 += 16) {
-                uint32_t r[16];
+            const bool mine = ngroups == 1 || (int)((active ? it : ti) & 1) == grp;
+            if (mine) {
+                const int h = tc.h0 + hl, w = tc.w0 + wl;
+                const bool ok = h < p.Ht && w < p.Wt;
+                int oh = h, ow = w;
+                if (p.mode == 2) { oh = 2 * h + ((tc.cls >> 1) & 1); ow = 2 * w + (tc.cls & 1); }
+                const long long off = (((long long)tc.n * p.Ho + oh) * p.Wo + ow) * p.out_cstride + tc.nti * p.nt;
                 if (active) {
-                    tmem_ld16(taddr + c0, r);
-                    if (p.stack) {                                // + the x_hi*w_lo half of the accumulator
-                        uint32_t r2[16];
-                        tmem_ld16(taddr + p.nt + c0, r2);
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
-                    } else {
-                        tmem_ld_wait();
-                    }
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) r[j] = 0u;
+                    mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
+                    tc_fence_after();
                 }
-                if (ok) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                               __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-                        if (bptr) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(bptr + c0) + q);
-                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                        }
-                        if (aptr) {
-                            const float4 a = __ldg(reinterpret_cast<const float4*>(aptr + c0) + q);
-                            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-                        }
-                        *reinterpret_cast<float4*>(optr + c0 + 4 * q) = v;
-                    }
+                const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * (p.stack ? 2 * p.nt : p.nt));
+                c2_epilogue_tile(p, epi, tc, out, taddr, active, ok, off, lane, tot[lane_grp]);
+                if (active) {
+                    tc_fence_before();
+                    mbar_arrive(tempty_bar(acc));
                 }
             }
-            if (active) {
-                tc_fence_before();
-                mbar_arrive(tempty_bar(acc));
-                ++it;
-            }
+            if (active) ++it;
         }
-    } else if (p.split) {
+        if (stats)
+            for (; cur_key < p.n_tiles * p.N; ++cur_key) c2_stat_flush(p, epi, cur_key, tot, lane_grp, lane, grp, ngroups);
+    } else {
         // ===================== operand split (4 warps): A tile -> (hi in place, lo) =====================
         const int tid = threadIdx.x - 192;
         int stage = 0; uint32_t phase = 0;
@@ -319,38 +423,39 @@ conv2d_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
 // from 16 KB (TMA) + 32 KB (split) to a third of 18 KB + 36 KB; the kernel is smem-bandwidth bound, so that is
 // what buys time.
 // =============================================================================================
-constexpr int kC2HaloNA = 2;               // A ring slots
+constexpr int kC2HaloMaxNA = 4;            // A ring slots: 2 with the split (hi + lo tiles, 40 KB a slot), 4 without --
+                                           // a plain-TF32 generation retires in ~0.5 us, less than one TMA round trip
 constexpr int kC2HaloMaxNW = 12;           // weight ring slots
 
 struct C2HaloParams {
     C2Params c;
-    int a_rows, a_bytes, a_slot, w_slot, nw;
+    int a_rows, a_bytes, a_slot, w_slot, nw, na;
 };
 
 __global__ void __launch_bounds__(kC2Threads, 1)
 conv2d_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                           float* __restrict__ out, const float* __restrict__ bias, const float* __restrict__ addend,
-                           const C2HaloParams hp) {
+                           float* __restrict__ out, const C2Epi epi, const C2HaloParams hp) {
     const C2Params& p = hp.c;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ __align__(8) uint64_t bars[3 * kC2HaloNA + 2 * kC2HaloMaxNW + 4];
+    __shared__ __align__(8) uint64_t bars[3 * kC2HaloMaxNA + 2 * kC2HaloMaxNW + 4];
     __shared__ uint32_t tmem_base_slot;
+    __shared__ float stat_tot[2][4][2][kC2StatMaxNt];      // [epilogue group][warp][sum | second sum][channel]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t* const smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-    const uint32_t a_base = smem_base, w_base = smem_base + (uint32_t)(kC2HaloNA * hp.a_slot);
+    const uint32_t a_base = smem_base, w_base = smem_base + (uint32_t)(hp.na * hp.a_slot);
     const uint32_t bar0 = smem_u32(bars);
     auto fullA = [&](int s) { return bar0 + 8u * s; };
-    auto emptyA = [&](int s) { return bar0 + 8u * (kC2HaloNA + s); };
-    auto readyA = [&](int s) { return bar0 + 8u * (2 * kC2HaloNA + s); };
-    auto fullW = [&](int s) { return bar0 + 8u * (3 * kC2HaloNA + s); };
-    auto emptyW = [&](int s) { return bar0 + 8u * (3 * kC2HaloNA + kC2HaloMaxNW + s); };
-    auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * kC2HaloNA + 2 * kC2HaloMaxNW + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * kC2HaloNA + 2 * kC2HaloMaxNW + 2 + a); };
+    auto emptyA = [&](int s) { return bar0 + 8u * (kC2HaloMaxNA + s); };
+    auto readyA = [&](int s) { return bar0 + 8u * (2 * kC2HaloMaxNA + s); };
+    auto fullW = [&](int s) { return bar0 + 8u * (3 * kC2HaloMaxNA + s); };
+    auto emptyW = [&](int s) { return bar0 + 8u * (3 * kC2HaloMaxNA + kC2HaloMaxNW + s); };
+    auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * kC2HaloMaxNA + 2 * kC2HaloMaxNW + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * kC2HaloMaxNA + 2 * kC2HaloMaxNW + 2 + a); };
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kC2HaloNA; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); mbar_init(readyA(s), 128); }
+        for (int s = 0; s < hp.na; ++s) { mbar_init(fullA(s), 1); mbar_init(emptyA(s), 1); mbar_init(readyA(s), 128); }
         for (int s = 0; s < hp.nw; ++s) { mbar_init(fullW(s), 1); mbar_init(emptyW(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -380,7 +485,7 @@ conv2d_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
                     mbar_expect_tx(fullA(aslot), (uint32_t)hp.a_bytes);
                     tma_load_4d(a_base + aslot * (uint32_t)hp.a_slot, &map_a, fullA(aslot), kc * kC2K,
                                 tc.w0 + (kw - 1) * p.dil, tc.h0 - p.dil, tc.n);
-                    if (++aslot == kC2HaloNA) { aslot = 0; aphase ^= 1; }
+                    if (++aslot == (uint32_t)hp.na) { aslot = 0; aphase ^= 1; }
                     for (int kh = 0; kh < 3; ++kh) {
                         const int tap = kh * 3 + kw;
                         mbar_wait(emptyW(wslot), wphase ^ 1);
@@ -442,63 +547,47 @@ conv2d_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
                         if (++wslot == (uint32_t)hp.nw) { wslot = 0; wphase ^= 1; }
                     }
                     umma_commit(emptyA(aslot));
-                    if (++aslot == kC2HaloNA) { aslot = 0; aphase ^= 1; }
+                    if (++aslot == (uint32_t)hp.na) { aslot = 0; aphase ^= 1; }
                 }
                 umma_commit(tfull_bar(acc));
             }
         }
         __syncwarp();
-    } else if (warp < 6) {
+    } else if (warp < 6 || !p.split) {
         // ===================== epilogue =====================
+        // warps 2-5; without the operand split warps 6-9 are a second group: group g drains accumulator g
+        const int grp = warp >= 6 ? 1 : 0, ngroups = p.split ? 1 : 2;
         const int lane_grp = warp & 3;
         const int m = lane_grp * 32 + lane;
         const int hl = m / kC2TileW, wl = m % kC2TileW;
+        const bool stats = epi.stat_mode != 0;
+        float (*tot)[2][kC2StatMaxNt] = stat_tot[grp];
+        if (stats) {
+            for (int c = lane; c < 2 * kC2StatMaxNt; c += 32) (&tot[lane_grp][0][0])[c] = 0.f;
+            __syncwarp();
+        }
+        int cur_key = 0;
         long long it = 0;
         for (long long t = blockIdx.x; t < p.total_tiles; t += gridDim.x, ++it) {
             const C2Tile tc = c2_decode(p, t);
+            if (stats)
+                for (const int key = tc.nti * p.N + tc.n; cur_key < key; ++cur_key)
+                    c2_stat_flush(p, epi, cur_key, tot, lane_grp, lane, grp, ngroups);
+            const int acc = (int)(it & 1);
+            if (ngroups == 2 && acc != grp) continue;
             const int h = tc.h0 + hl, w = tc.w0 + wl;
             const bool ok = h < p.Ht && w < p.Wt;
             const long long off = (((long long)tc.n * p.Ho + h) * p.Wo + w) * p.out_cstride + tc.nti * p.nt;
-            float* optr = out + off;
-            const float* aptr = addend ? addend + off : nullptr;
-            const float* bptr = bias ? bias + tc.nti * p.nt : nullptr;
-            const int acc = (int)(it & 1);
             mbar_wait(tfull_bar(acc), (uint32_t)((it >> 1) & 1));
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * (p.stack ? 2 * p.nt : p.nt));
-            for (int c0 = 0; c0 < p.nt; c0 += 16) {
-                uint32_t r[16];
-                tmem_ld16(taddr + c0, r);
-                if (p.stack) {
-                    uint32_t r2[16];
-                    tmem_ld16(taddr + p.nt + c0, r2);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
-                } else {
-                    tmem_ld_wait();
-                }
-                if (ok) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float4 v = make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]),
-                                               __uint_as_float(r[4 * q + 2]), __uint_as_float(r[4 * q + 3]));
-                        if (bptr) {
-                            const float4 b = __ldg(reinterpret_cast<const float4*>(bptr + c0) + q);
-                            v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-                        }
-                        if (aptr) {
-                            const float4 a = __ldg(reinterpret_cast<const float4*>(aptr + c0) + q);
-                            v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-                        }
-                        *reinterpret_cast<float4*>(optr + c0 + 4 * q) = v;
-                    }
-                }
-            }
+            c2_epilogue_tile(p, epi, tc, out, taddr, true, ok, off, lane, tot[lane_grp]);
             tc_fence_before();
             mbar_arrive(tempty_bar(acc));
         }
-    } else if (p.split) {
+        if (stats)
+            for (; cur_key < p.n_tiles * p.N; ++cur_key) c2_stat_flush(p, epi, cur_key, tot, lane_grp, lane, grp, ngroups);
+    } else {
         // ===================== operand split: the whole halo tile, once per generation =====================
         const int tid = threadIdx.x - 192;
         const int n4 = hp.a_bytes / 16;
@@ -520,7 +609,7 @@ conv2d_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 mbar_arrive(readyA(aslot));
-                if (++aslot == kC2HaloNA) { aslot = 0; aphase ^= 1; }
+                if (++aslot == (uint32_t)hp.na) { aslot = 0; aphase ^= 1; }
             }
         }
     }
@@ -533,9 +622,11 @@ conv2d_halo_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __gr
     }
 }
 
-int conv2d_tcgen05_launch(const float* in, const float* wp, const float* bias, const float* addend, float* out,
+// stat_rows (if given) receives the rows per sample of the statistics table [N][rows][2][Cout] this launch
+// configuration writes (0: the kernel serving it has no statistics epilogue); query = compute that only.
+int conv2d_tcgen05_launch(const float* in, const float* wp, const C2Epi& epi, float* out,
                           int N, int Cin, int Cout, int Hi, int Wi, int ks, int stride, int dil, int mode, int split,
-                          cudaStream_t st) {
+                          cudaStream_t st, int* stat_rows, bool query) {
     // N tile: <= 256 columns per MMA; with the split an accumulator is 2 nt columns wide and double buffered
     const int nt_max = (split == 1 || split == 2) ? 128 : 256;
     int n_tiles = 0;
@@ -546,8 +637,6 @@ int conv2d_tcgen05_launch(const float* in, const float* wp, const float* bias, c
                   "(multiples of 16); got %d -> %d", Cin, Cout);
         return B2_ERR_UNSUPPORTED;
     }
-    EncodeTiledFn encode = get_encode();
-    if (!encode) { set_error("conv2d(tcgen05): cuTensorMapEncodeTiled not available from the driver"); return B2_ERR_DRIVER; }
     C2Params p{};
     p.n_tiles = n_tiles; p.nt = Cout / n_tiles;
     p.N = N; p.Cin = Cin; p.Cout = Cout; p.Hi = Hi; p.Wi = Wi; p.ks = ks; p.dil = dil; p.split = split ? 1 : 0;
@@ -572,6 +661,17 @@ int conv2d_tcgen05_launch(const float* in, const float* wp, const float* bias, c
     while (p.tmem_cols < 2 * (p.stack ? 2 : 1) * p.nt) p.tmem_cols *= 2;
     p.total_tiles = (long long)p.n_tiles * (p.mode == 2 ? 4 : 1) * N * p.tiles_h * p.tiles_w;
 
+    const int grid = (int)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
+    const bool stats_ok = p.mode != 2 && p.nt <= kC2StatMaxNt;
+    if (stat_rows) *stat_rows = stats_ok ? grid * (p.split ? 1 : 2) : 0;   // one row per CTA and epilogue group
+    if (query) return 0;
+    if (epi.stat_mode && !stats_ok) {
+        set_error("conv2d(tcgen05): no statistics epilogue for this shape (transposed, or channel tile of %d > %d)", p.nt, kC2StatMaxNt);
+        return B2_ERR_UNSUPPORTED;
+    }
+    EncodeTiledFn encode = get_encode();
+    if (!encode) { set_error("conv2d(tcgen05): cuTensorMapEncodeTiled not available from the driver"); return B2_ERR_DRIVER; }
+
     const bool halo = flag_value(kFlagConv2dHalo, "B2_CONV2D_HALO", 1) && p.mode == 0 && ks == 3;
     C2HaloParams hp{};
     if (halo) {
@@ -579,7 +679,8 @@ int conv2d_tcgen05_launch(const float* in, const float* wp, const float* bias, c
         hp.a_bytes = hp.a_rows * kC2TileW * 128;
         hp.a_slot = (p.split ? 2 : 1) * hp.a_bytes;
         hp.w_slot = (p.split ? 2 : 1) * p.b_bytes;
-        hp.nw = (208 * 1024 - kC2HaloNA * hp.a_slot) / hp.w_slot;
+        hp.na = p.split ? 2 : kC2HaloMaxNA;
+        hp.nw = (208 * 1024 - hp.na * hp.a_slot) / hp.w_slot;
         if (hp.nw > kC2HaloMaxNW) hp.nw = kC2HaloMaxNW;
         if (hp.nw < 2) { set_error("conv2d(tcgen05,halo): weight tiles of %d bytes do not fit", hp.w_slot); return B2_ERR_UNSUPPORTED; }
     }
@@ -606,21 +707,20 @@ int conv2d_tcgen05_launch(const float* in, const float* wp, const float* bias, c
                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_error("conv2d(tcgen05): cuTensorMapEncodeTiled(B) failed: %d", (int)r); return B2_ERR_DRIVER; }
     }
-    const int grid = (int)(p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs);
     if (halo) {
         hp.c = p;
-        const int smem_h = kC2HaloNA * hp.a_slot + hp.nw * hp.w_slot + 1024;
+        const int smem_h = hp.na * hp.a_slot + hp.nw * hp.w_slot + 1024;
         static SmemOptIn optin_h;
         cudaError_t eh = ensure_dynamic_smem(optin_h, conv2d_halo_tcgen05_kernel, 209 * 1024 + 1024);
         if (eh != cudaSuccess) { set_error("conv2d(tcgen05,halo): cudaFuncSetAttribute: %s", cudaGetErrorString(eh)); return (int)eh; }
-        conv2d_halo_tcgen05_kernel<<<grid, kC2Threads, smem_h, st>>>(map_a, map_b, out, bias, addend, hp);
+        conv2d_halo_tcgen05_kernel<<<grid, kC2Threads, smem_h, st>>>(map_a, map_b, out, epi, hp);
         return check_launch("conv2d(tcgen05,halo)");
     }
     const int smem = p.stages * p.stage_bytes + 1024;
     static SmemOptIn optin;
     cudaError_t e = ensure_dynamic_smem(optin, conv2d_tcgen05_kernel, 209 * 1024 + 1024);
     if (e != cudaSuccess) { set_error("conv2d(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
-    conv2d_tcgen05_kernel<<<grid, kC2Threads, smem, st>>>(map_a, map_b, out, bias, addend, p);
+    conv2d_tcgen05_kernel<<<grid, kC2Threads, smem, st>>>(map_a, map_b, out, epi, p);
     return check_launch("conv2d(tcgen05)");
 }
 
@@ -720,9 +820,8 @@ conv2d_first_dgrad_kernel(const float* __restrict__ gout, const float* __restric
 
 }  // namespace b2
 
-extern "C" int b2_conv2d(const float* in, const float* wp, const float* bias, const float* addend, float* out,
-                         int N, int Cin, int Cout, int Hi, int Wi, int ksize, int stride, int dilation, int mode,
-                         int split, void* stream) {
+static int conv2d_check(const float* in, const float* wp, const float* bias, const float* addend, float* out, int N,
+                        int Cin, int Cout, int Hi, int Wi, int ksize, int stride, int dilation, int mode) {
     B2_REQUIRE(in && wp && out, "conv2d: null pointer");
     B2_REQUIRE(N >= 0 && Cin > 0 && Cout > 0 && Hi > 0 && Wi > 0, "conv2d: bad dims");
     B2_REQUIRE(ksize == 1 || ksize == 3, "conv2d: kernel size must be 1 or 3 (got %d)", ksize);
@@ -732,9 +831,49 @@ extern "C" int b2_conv2d(const float* in, const float* wp, const float* bias, co
     B2_REQUIRE(dilation == 1 || (dilation == 2 && stride == 1 && mode == 0), "conv2d: dilation %d unsupported here", dilation);
     B2_REQUIRE(b2::aligned16(in) && b2::aligned16(out) && b2::aligned16(wp) && (!bias || b2::aligned16(bias)) &&
                (!addend || b2::aligned16(addend)), "conv2d: pointers must be 16-byte aligned");
+    return 0;
+}
+
+extern "C" int b2_conv2d(const float* in, const float* wp, const float* bias, const float* addend, float* out,
+                         int N, int Cin, int Cout, int Hi, int Wi, int ksize, int stride, int dilation, int mode,
+                         int split, void* stream) {
+    if (int e = conv2d_check(in, wp, bias, addend, out, N, Cin, Cout, Hi, Wi, ksize, stride, dilation, mode)) return e;
     if (N == 0) return 0;
-    return b2::conv2d_tcgen05_launch(in, wp, bias, addend, out, N, Cin, Cout, Hi, Wi, ksize, stride, dilation, mode,
-                                     split, (cudaStream_t)stream);
+    b2::C2Epi epi{};
+    epi.bias = bias; epi.addend = addend;
+    return b2::conv2d_tcgen05_launch(in, wp, epi, out, N, Cin, Cout, Hi, Wi, ksize, stride, dilation, mode, split,
+                                     (cudaStream_t)stream, nullptr, false);
+}
+
+extern "C" int b2_conv2d_fused(const float* in, const float* wp, const float* bias, const float* addend, float* out,
+                               int N, int Cin, int Cout, int Hi, int Wi, int ksize, int stride, int dilation, int mode,
+                               int split, int stat_mode, float* stat_partial, const float* gn_x, const float* gn_coef,
+                               int gn_coef_stride, void* stream) {
+    if (int e = conv2d_check(in, wp, bias, addend, out, N, Cin, Cout, Hi, Wi, ksize, stride, dilation, mode)) return e;
+    B2_REQUIRE(stat_mode >= 0 && stat_mode <= 3, "conv2d_fused: stat_mode must be 0..3");
+    B2_REQUIRE(stat_mode == 0 || stat_partial, "conv2d_fused: stat_mode %d needs the statistics table", stat_mode);
+    B2_REQUIRE(stat_mode < 2 || (gn_x && b2::aligned16(gn_x)), "conv2d_fused: stat_mode %d needs gn_x (16-byte aligned)", stat_mode);
+    B2_REQUIRE(stat_mode != 3 || (gn_coef && gn_coef_stride >= 2 * Cout), "conv2d_fused: stat_mode 3 needs gn_coef with a per-sample stride >= 2*Cout");
+    if (N == 0) return 0;
+    b2::C2Epi epi{};
+    epi.bias = bias; epi.addend = addend; epi.stat_mode = stat_mode; epi.stat_partial = stat_partial;
+    epi.gn_x = gn_x; epi.gn_coef = gn_coef; epi.gn_coef_stride = gn_coef_stride;
+    return b2::conv2d_tcgen05_launch(in, wp, epi, out, N, Cin, Cout, Hi, Wi, ksize, stride, dilation, mode, split,
+                                     (cudaStream_t)stream, nullptr, false);
+}
+
+extern "C" int b2_conv2d_stat_rows(int N, int Cin, int Cout, int Hi, int Wi, int ksize, int stride, int dilation, int mode,
+                                   int split, int* rows) {
+    B2_REQUIRE(rows, "conv2d_stat_rows: null pointer");
+    *rows = 0;
+    if (N <= 0 || Cin <= 0 || Cout <= 0 || Hi <= 0 || Wi <= 0 || (ksize != 1 && ksize != 3) || (mode != 0 && mode != 1) ||
+        (stride != 1 && stride != 2) || (mode == 1 && stride != 2))
+        return 0;
+    b2::C2Epi epi{};
+    int e = b2::conv2d_tcgen05_launch(nullptr, nullptr, epi, nullptr, N, Cin, Cout, Hi, Wi, ksize, stride, dilation, mode,
+                                      split, nullptr, rows, true);
+    if (e) { *rows = 0; }
+    return 0;
 }
 
 extern "C" int b2_conv2d_first_fwd(const float* img, const float* w, float* out, int N, int Cout, int H, int W,

@@ -283,14 +283,14 @@ static int groupnorm_fwd_impl(const float* x, const float* res, const float* gam
     B2_REQUIRE(x && gamma && beta && y && stats && workspace, "groupnorm_fwd: null pointer");
     if (int e = gn_check("groupnorm_fwd", N, C, S, G)) return e;
     B2_REQUIRE(aligned16(x) && aligned16(y) && (!res || aligned16(res)), "groupnorm_fwd: pointers must be 16B aligned");
-    B2_REQUIRE(!ext_partial || (N == 1 && ext_rows >= 1), "groupnorm_fwd: external partial sums need N == 1 and >= 1 row");
+    B2_REQUIRE(!ext_partial || ext_rows >= 1, "groupnorm_fwd: external partial sums need >= 1 row per sample");
     if (N == 0 || S == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     GnLayout l = gn_layout(C);
     float* partial = (float*)workspace;
     float* coef = partial + gn_partial_floats(N, C);
     if (ext_partial) {
-        // statistics pass already done by the producer (conv epilogue): table [ext_rows][2][C]
+        // statistics pass already done by the producer (conv epilogue): table [N][ext_rows][2][C]
         gn_finalize_fwd<<<dim3(G, N), kGnFinThreads, 0, st>>>(ext_partial, gamma, beta, stats, coef, C, S, G, eps, ext_rows);
     } else {
         int nblocks = gn_nblocks(S);
@@ -326,8 +326,8 @@ static int groupnorm_bwd_impl(const float* gy, const float* x, const float* y, c
     B2_REQUIRE(relu >= 0 && relu <= 2, "groupnorm_bwd: relu must be 0, 1 or 2");
     if (int e = gn_check("groupnorm_bwd", N, C, S, G)) return e;
     B2_REQUIRE(aligned16(gy) && aligned16(x) && aligned16(gx), "groupnorm_bwd: pointers must be 16B aligned");
-    B2_REQUIRE(!ext_partial || (N == 1 && ext_rows >= 1 && relu != 1),
-               "groupnorm_bwd: external partial sums need N == 1, >= 1 row and relu in {0, 2}");
+    B2_REQUIRE(!ext_partial || (ext_rows >= 1 && relu != 1),
+               "groupnorm_bwd: external partial sums need >= 1 row per sample and relu in {0, 2}");
     if (N == 0 || S == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     GnLayout l = gn_layout(C);

@@ -125,14 +125,17 @@ class Conv2dTf32x3Fn(torch.autograd.Function):
         return gx, None, None, None, None, None
 
 
-def conv2d_any(conv, x, fork=False):
+def conv2d_any(conv, x, fork=False, stats=False):
     """``conv`` = nn.Conv2d used as parameter holder.  Returns y, or (y, x2) with ``fork`` (x2 = x for its
-    other consumers; with our kernels their gradient is added inside the data-gradient launch)."""
+    other consumers; with our kernels their gradient is added inside the data-gradient launch).
+    ``stats``: (y, partial[, x2]) -- the conv epilogue's GroupNorm partial sums of y (None where not available)."""
     if BACKBONE_IMPL == "b2":
         k, pad, dil = conv.kernel_size[0], conv.padding[0], conv.dilation[0]
         if conv.kernel_size[0] != conv.kernel_size[1] or pad != dil * (k // 2) or conv.groups != 1 \
                 or conv.stride[0] != conv.stride[1]:
             raise RuntimeError("conv2d: unsupported layer %r" % (conv,))
+        if stats:
+            return ops.conv2d_with_stats(x, conv.weight, conv.bias, conv.stride[0], dil, fork=fork)
         if fork:
             return ops.conv2d_fork(x, conv.weight, conv.bias, conv.stride[0], dil)
         return ops.conv2d(x, conv.weight, conv.bias, conv.stride[0], dil)
@@ -141,17 +144,20 @@ def conv2d_any(conv, x, fork=False):
         y = Conv2dTf32x3Fn.apply(x, conv.weight, conv.bias, conv.stride, conv.padding, conv.dilation)
     else:
         y = conv(x)
+    if stats:
+        return (y, None, x) if fork else (y, None)
     return (y, x) if fork else y
 
 
 def run_convbn_2d(seq, x, relu=False, res=None, fork=False):
     """conv2d -> GroupNorm (+res) (+ReLU), all on the sm_100a kernels.  ``seq`` = Sequential(Conv2d, GroupNorm)."""
     conv, norm = seq[0], seq[1]
-    y = conv2d_any(conv, x, fork)
-    if fork:
-        y, x2 = y
-    y = ops.groupnorm_act(y, norm.weight, norm.bias, norm.num_groups, norm.eps, relu=relu, res=res)
-    return (y, x2) if fork else y
+    # the conv epilogue adds up the GroupNorm statistics of its own output (no statistics pass over y), and the
+    # norm's output carries a GnLink: the data-gradient launch of its consumer adds up the backward sums as well
+    out = conv2d_any(conv, x, fork, stats=True)
+    y, part = out[0], out[1]
+    y = ops.groupnorm_act(y, norm.weight, norm.bias, norm.num_groups, norm.eps, relu=relu, res=res, partial=part)
+    return (y, out[2]) if fork else y
 
 
 class BasicBlock(nn.Module):

@@ -396,13 +396,28 @@ class GnLink:
     """Hand-off between a GroupNorm node and the conv that consumes its output.  The norm's forward
     fills in what its backward statistics need (x, stats, activation mode); the conv's DATA-GRADIENT
     launch -- which produces exactly the gradient w.r.t. the norm's output -- adds up the norm's
-    backward sums in its epilogue and leaves them here together with the identity of the gradient
-    tensor it wrote; the norm's backward uses them only if that very tensor, unmodified, arrives."""
-    __slots__ = ("x", "stats", "groups", "mode", "bwd_partial", "gy_key")
+    backward sums in its epilogue and leaves them here together with the gradient tensor it wrote;
+    the norm's backward uses them only if that very tensor, unmodified, arrives.
+    The link holds the tensor itself, not just its address: the autograd engine adds a second
+    consumer's gradient IN PLACE into a buffered gradient it holds the last reference to (without a
+    version bump visible here) -- the extra reference makes it add out of place, so a gradient the sums
+    no longer describe always arrives as another tensor."""
+    __slots__ = ("x", "stats", "groups", "mode", "bwd_partial", "gy", "gy_key")
 
     def __init__(self):
-        self.x = self.stats = self.bwd_partial = self.gy_key = None
+        self.x = self.stats = self.bwd_partial = self.gy = self.gy_key = None
         self.groups = self.mode = 0
+
+    def offer(self, partial, gy):
+        self.bwd_partial, self.gy = partial, gy
+        self.gy_key = (gy.data_ptr(), gy._version, tuple(gy.shape))
+
+    def take(self, gy):
+        """The sums, if ``gy`` is the tensor they were added up from; clears the hand-off either way."""
+        ok = self.bwd_partial is not None and self.gy_key == (gy.data_ptr(), gy._version, tuple(gy.shape))
+        part = self.bwd_partial if ok else None
+        self.bwd_partial = self.gy = self.gy_key = None
+        return part
 
 
 def _conv_caps(n, cin, cout, di, hi, wi, stride, mode):
@@ -459,8 +474,7 @@ def _conv_call(x, wp, stride, mode, impl, stats=False, addend=None, bstat=None):
                                       3 if bstat.mode == 2 else 2, _p(bstat.x), coef, n, cin, cout,
                                       di, hi, wi, stride, mode, _stream()),
                   "conv3d_fused(mode=%d,stride=%d,bstat)" % (mode, stride))
-            bstat.bwd_partial = bpart
-            bstat.gy_key = (out.data_ptr(), out._version, tuple(out.shape))
+            bstat.offer(bpart, out)
         elif rows > 0 or fused_add:
             part = torch.empty((rows, 2, cout), device=x.device, dtype=torch.float32) if rows > 0 else None
             check(lib.b2_conv3d_fused(_p(x), _p(wp), _p(out), _p(addend) if fused_add else None, _p(part),
@@ -621,7 +635,25 @@ def _plain_weight(weight):
     return w
 
 
-def _conv2d_call(x, wp, bias, addend, n, cin, cout, hi, wi, ks, stride, dil, mode, split):
+_CAPS2D = {}
+
+
+def _conv2d_stat_rows(n, cin, cout, hi, wi, ks, stride, dil, mode, split):
+    """Rows per sample of the statistics table the conv2d kernel serving this shape writes (0: none)."""
+    key = (n, cin, cout, hi, wi, ks, stride, dil, mode, int(split))
+    hit = _CAPS2D.get(key)
+    if hit is None:
+        rows = ctypes.c_int(0)
+        check(_lib.load().b2_conv2d_stat_rows(n, cin, cout, hi, wi, ks, stride, dil, mode, int(split), ctypes.byref(rows)),
+              "conv2d_stat_rows")
+        hit = _CAPS2D[key] = rows.value
+    return hit
+
+
+def _conv2d_call(x, wp, bias, addend, n, cin, cout, hi, wi, ks, stride, dil, mode, split, stats=False, bstat=None):
+    """``stats``: also return the GroupNorm partial sums of the output ([n, rows, 2, cout]) added up by the epilogue,
+    or None when the kernel serving this shape has none.  ``bstat``: GnLink of the norm whose output gradient this
+    launch computes; its backward sums are added up in the epilogue when possible (as ``_conv_call``)."""
     lib = _lib.load()
     if mode == 0:
         ho, wo = (hi - 1) // stride + 1, (wi - 1) // stride + 1
@@ -632,10 +664,34 @@ def _conv2d_call(x, wp, bias, addend, n, cin, cout, hi, wi, ks, stride, dil, mod
         addend = cl2(addend)
         assert addend.shape == out.shape, (addend.shape, out.shape)
     pix = n * ho * wo if mode == 0 else n * hi * wi
+    what = "conv2d(k=%d,stride=%d,dil=%d,mode=%d,%d->%d)" % (ks, stride, dil, mode, cin, cout)
+    part, stat_mode, gn_x, gn_coef, coef_stride = None, 0, None, None, 0
+    if bstat is not None and not (FUSE_GN_BWD and bstat.mode in (0, 2) and bstat.x is not None
+                                  and tuple(bstat.x.shape) == tuple(out.shape)):
+        bstat = None
+    if (stats and FUSE_GN_STATS) or bstat is not None:
+        rows = _conv2d_stat_rows(n, cin, cout, hi, wi, ks, stride, dil, mode, split)
+        if rows:
+            part = torch.empty((n, rows, 2, cout), device=x.device, dtype=torch.float32)
+            if bstat is not None:
+                stat_mode = 3 if bstat.mode == 2 else 2
+                gn_x = bstat.x
+                coef_stride = bstat.stats.shape[1]
+                gn_coef = bstat.stats[:, 2 * bstat.groups:]           # scale[C], shift[C] of sample 0
+            else:
+                stat_mode = 1
     with _op("conv2d_tcgen05", 1, 2 * cin * cout * ks * ks * pix):
-        check(lib.b2_conv2d(_p(x), _p(wp), _p(bias), _p(addend), _p(out), n, cin, cout, hi, wi, ks, stride, dil,
-                            mode, int(split), _stream()),
-              "conv2d(k=%d,stride=%d,dil=%d,mode=%d,%d->%d)" % (ks, stride, dil, mode, cin, cout))
+        if stat_mode:
+            check(lib.b2_conv2d_fused(_p(x), _p(wp), _p(bias), _p(addend), _p(out), n, cin, cout, hi, wi, ks, stride,
+                                      dil, mode, int(split), stat_mode, _p(part), _p(gn_x), _p(gn_coef), coef_stride,
+                                      _stream()), what)
+        else:
+            check(lib.b2_conv2d(_p(x), _p(wp), _p(bias), _p(addend), _p(out), n, cin, cout, hi, wi, ks, stride, dil,
+                                mode, int(split), _stream()), what)
+    if bstat is not None and stat_mode >= 2:
+        bstat.offer(part, out)
+    if stats:
+        return out, (part if stat_mode == 1 else None)
     return out
 
 
@@ -643,10 +699,12 @@ class Conv2dFn(Function):
     """nn.Conv2d(k 1|3, stride 1|2, padding = dilation*(k//2), dilation 1|2, groups 1) forward and data
     gradient on the sm_100a kernels; channels-last maps.  The 3-channel first layer (k3, s2) takes the exact
     fp32 SIMT pair and reads / writes the NCHW image tensors of the attack directly.
-    ``fork``: also return a second handle on x for its other consumers (see ``conv3d_fork``)."""
+    ``stats``: also return the epilogue's GroupNorm partial sums of the output (empty tensor: none available).
+    ``fork``: also return a second handle on x for its other consumers (see ``conv3d_fork``).
+    ``gn_link``: GnLink of the norm that produced x (its backward sums ride this conv's data-gradient epilogue)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, stride, dilation, fork):
+    def forward(ctx, x, weight, bias, stride, dilation, fork, stats=False, gn_link=None):
         _need_cuda(x, weight, bias)
         if weight.requires_grad or (bias is not None and bias.requires_grad):
             raise RuntimeError("attack path: weights are frozen; call requires_grad_(False) on the model")
@@ -657,6 +715,7 @@ class Conv2dFn(Function):
             raise RuntimeError("conv2d: unsupported configuration k=%dx%d stride=%d dilation=%d" % (kh, kw, stride, dilation))
         first = ci == 3
         split = CONV2D_SPLIT
+        part = None
         if first:
             if not (kh == 3 and stride == 2 and dilation == 1 and bias is None):
                 raise RuntimeError("conv2d: the 3-channel layer must be k3/s2/p1/bias-free")
@@ -672,22 +731,31 @@ class Conv2dFn(Function):
                 raise RuntimeError("conv2d: stride 2 needs even spatial dims, got %dx%d" % (hi, wi))
             b = bias.detach() if bias is not None else None
             out = _conv2d_call(x, _packed2d(weight, "fwd", split), b, None, n, ci, co, hi, wi, kh, stride, dilation, 0,
-                               split)
+                               split, stats=stats)
+            if stats:
+                out, part = out
         ctx.weight = weight
+        ctx.gn_link = gn_link
         ctx.cfg = (n, ci, co, hi, wi, kh, stride, dilation, first, (split if CONV2D_SPLIT_BWD else 0),
-                   bool(fork))
+                   bool(fork), bool(stats))
         ctx.set_materialize_grads(False)
+        res = []
+        if stats:
+            if part is None:
+                part = out.new_empty(0)                   # "no statistics": autograd outputs must be tensors
+            ctx.mark_non_differentiable(part)
+            res.append(part)
         if fork:
-            return out, x.view_as(x)
-        return out
+            res.append(x.view_as(x))
+        return (out, *res) if res else out
 
     @staticmethod
     @once_differentiable
     def backward(ctx, gout, *extra):
-        n, ci, co, hi, wi, ks, stride, dil, first, split, fork = ctx.cfg
-        g_other = extra[0] if fork else None
+        n, ci, co, hi, wi, ks, stride, dil, first, split, fork, stats = ctx.cfg
+        g_other = extra[int(stats)] if fork else None
         if gout is None:
-            return g_other, None, None, None, None, None
+            return g_other, None, None, None, None, None, None, None
         lib = _lib.load()
         g = cl2(gout)
         if first:
@@ -697,15 +765,16 @@ class Conv2dFn(Function):
                 check(lib.b2_conv2d_first_dgrad(_p(g), _p(w), _p(gin), n, co, hi, wi, _stream()), "conv2d_first_dgrad")
             if g_other is not None:
                 gin = gin + g_other
-            return gin, None, None, None, None, None
+            return gin, None, None, None, None, None, None, None
         ho, wo = g.shape[2:]
+        link = ctx.gn_link
         if stride == 1:
             gin = _conv2d_call(g, _packed2d(ctx.weight, "dgrad_s1", split), None, g_other, n, co, ci, ho, wo, ks, 1, dil,
-                               0, split)
+                               0, split, bstat=link)
         else:
             gin = _conv2d_call(g, _packed2d(ctx.weight, "dgrad_s2", split), None, g_other, n, co, ci, ho, wo, ks, 2, 1,
-                               1, split)
-        return gin, None, None, None, None, None
+                               1, split, bstat=link)
+        return gin, None, None, None, None, None, None, None
 
 
 def _padded_out_channels(weight, bias):
@@ -730,14 +799,28 @@ def conv2d(x, weight, bias=None, stride=1, dilation=1):
         if weight.requires_grad:
             raise RuntimeError("attack path: weights are frozen; call requires_grad_(False) on the model")
         w, b = _padded_out_channels(weight, bias)
-        return Conv2dFn.apply(x, w, b, stride, dilation, False)[:, :co]
-    return Conv2dFn.apply(x, weight, bias, stride, dilation, False)
+        return Conv2dFn.apply(x, w, b, stride, dilation, False, False, getattr(x, "_b2_gn", None))[:, :co]
+    return Conv2dFn.apply(x, weight, bias, stride, dilation, False, False, getattr(x, "_b2_gn", None))
 
 
 def conv2d_fork(x, weight, bias=None, stride=1, dilation=1):
     """(y, x2): x2 is x for its OTHER consumers; their gradient is added inside this conv's data-gradient
     kernel (no separate accumulation pass), exactly as ``conv3d_fork``."""
-    return Conv2dFn.apply(x, weight, bias, stride, dilation, True)
+    return Conv2dFn.apply(x, weight, bias, stride, dilation, True, False, getattr(x, "_b2_gn", None))
+
+
+def conv2d_with_stats(x, weight, bias=None, stride=1, dilation=1, fork=False):
+    """conv2d whose epilogue also adds up the GroupNorm statistics of its output: (y, partial[, x2]); ``partial``
+    [N, rows, 2, Cout] goes to ``groupnorm_act(..., partial=)`` and is None when the kernel serving this shape has
+    no statistics epilogue (the 3-channel first layer, odd widths)."""
+    if weight.shape[1] != 3 and weight.shape[0] % 32:
+        y = conv2d(x, weight, bias, stride, dilation)
+        assert not fork
+        return y, None
+    out = Conv2dFn.apply(x, weight, bias, stride, dilation, bool(fork), True, getattr(x, "_b2_gn", None))
+    y, part = out[0], out[1]
+    part = part if part.numel() else None
+    return (y, part, out[2]) if fork else (y, part)
 
 
 class Conv3dC1Fn(Function):
@@ -815,10 +898,12 @@ class GroupNormActFn(Function):
         ws = _workspace(lib.b2_groupnorm_workspace_bytes(n, c), x.device)
         gamma, beta = gamma.detach().contiguous(), beta.detach().contiguous()
         if partial is not None:
-            assert n == 1 and partial.dim() == 3 and partial.shape[1:] == (2, c), (partial.shape, n, c)
+            # [rows, 2, C] (single sample) or [N, rows, 2, C]
+            assert (partial.dim() == 3 and n == 1) or (partial.dim() == 4 and partial.shape[0] == n), (partial.shape, n)
+            assert tuple(partial.shape[-2:]) == (2, c) and partial.is_contiguous(), (partial.shape, c)
             with _op("groupnorm_fwd", 2, 4 * x.numel() * (2 + (res is not None))):
                 check(lib.b2_groupnorm_fwd_ext(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(stats), n, c, s, groups,
-                                               float(eps), int(relu), _p(partial), partial.shape[0], _p(ws),
+                                               float(eps), int(relu), _p(partial), partial.shape[-3], _p(ws),
                                                _stream()), "groupnorm_fwd_ext")
         else:
             with _op("groupnorm_fwd", 3, 4 * x.numel() * (3 + (res is not None))):
@@ -850,16 +935,16 @@ class GroupNormActFn(Function):
         mode = 0 if not relu else (1 if has_res else 2)
         ext = None
         link = ctx.link
-        if link is not None and link.bwd_partial is not None:
+        if link is not None:
             # the conv that consumed y added up (sum gz*x, sum gz) while writing gy: valid only if that
             # very tensor arrives here untouched (no other consumer's gradient was accumulated into it)
-            if link.gy_key == (gy.data_ptr(), gy._version, tuple(gy.shape)) and mode != 1:
-                ext = link.bwd_partial
-            link.bwd_partial = link.gy_key = None
+            ext = link.take(gy)
+            if mode == 1:
+                ext = None
         if ext is not None:
             with _op("groupnorm_bwd", 2, 4 * x.numel() * (3 + (gres is not None))):
                 check(lib.b2_groupnorm_bwd_ext(_p(gy), _p(x), _p(y), _p(gamma), _p(stats), _p(gx), _p(gres), n, c, s,
-                                               groups, mode, _p(ext), ext.shape[0], _p(ws), _stream()),
+                                               groups, mode, _p(ext), ext.shape[-3], _p(ws), _stream()),
                       "groupnorm_bwd_ext")
         else:
             with _op("groupnorm_bwd", 3, 4 * x.numel() * (5 + 2 * int(mode == 1) + (gres is not None))):
@@ -875,7 +960,7 @@ def groupnorm_act(x, gamma, beta, groups, eps=1e-5, relu=False, res=None, partia
     (``conv3d_with_stats``); the statistics pass over x is skipped.
     A single-sample 3-D output carries a ``GnLink`` so that a conv consuming it can add up this
     norm's backward sums while it writes the gradient (see ``GnLink``)."""
-    link = GnLink() if (x.dim() == 5 and x.shape[0] == 1 and FUSE_GN_BWD) else None
+    link = GnLink() if (FUSE_GN_BWD and ((x.dim() == 5 and x.shape[0] == 1) or x.dim() == 4)) else None
     y = GroupNormActFn.apply(x, res, gamma, beta, groups, eps, relu, partial, link)
     if link is not None:
         y._b2_gn = link

@@ -238,6 +238,23 @@ int b2_conv2d(const float* in, const float* wp, const float* bias, const float* 
               int N, int Cin, int Cout, int Hi, int Wi, int ksize, int stride, int dilation, int mode,
               int split, void* stream);
 
+/* b2_conv2d whose epilogue also adds up GroupNorm sums of the rows it writes (upstream convbn = Conv2d +
+ * GroupNorm, the pattern of every extractor / BEV layer), stat_mode as b2_conv3d_fused:
+ *   1  (sum v, sum v^2) of this conv's output v (after bias / addend) -> b2_groupnorm_fwd_ext skips its statistics pass;
+ *   2  this launch is the data gradient that produces gy w.r.t. the output of a GroupNorm whose input was gn_x
+ *      [same layout as out]: (sum gy*x, sum gy) -> b2_groupnorm_bwd_ext skips its statistics pass;
+ *   3  as 2 for a norm followed by ReLU: gy counts only where fmaf(x, scale_c, shift_c) > 0; gn_coef = the norm's
+ *      forward scale[Cout], shift[Cout] of sample 0 (tail of its stats row), sample n at + n * gn_coef_stride floats.
+ * stat_partial: [N][rows][2][Cout] floats, rows = b2_conv2d_stat_rows(...) (one row per CTA and sample, fixed
+ * summation order); rows == 0: the kernel serving this shape has no statistics epilogue (DECONV, or a channel
+ * tile wider than 128) and stat_mode must be 0. */
+int b2_conv2d_fused(const float* in, const float* wp, const float* bias, const float* addend, float* out,
+                    int N, int Cin, int Cout, int Hi, int Wi, int ksize, int stride, int dilation, int mode,
+                    int split, int stat_mode, float* stat_partial, const float* gn_x, const float* gn_coef,
+                    int gn_coef_stride, void* stream);
+int b2_conv2d_stat_rows(int N, int Cin, int Cout, int Hi, int Wi, int ksize, int stride, int dilation, int mode,
+                        int split, int* rows);
+
 /* First extractor layer, Conv2d(3 -> Cout, k3, stride 2, pad 1), exact fp32: img [N,3,H,W] (NCHW, the
  * attack's image tensor) -> out [N,Ho,Wo,Cout] channels-last, and its data gradient back to the NCHW
  * pixels (the gradient tensor b2_pgd_update consumes).  w [Cout][3][3][3] (the nn.Conv2d layout). */
@@ -269,8 +286,8 @@ int64_t b2_groupnorm_workspace_bytes(int N, int C);
 int b2_groupnorm_fwd(const float* x, const float* res, const float* gamma, const float* beta,
                      float* y, float* stats, int N, int C, int64_t S, int G, float eps,
                      int relu, void* workspace, void* stream);
-/* forward with the per-channel partial sums supplied by the producer (b2_conv3d_fused):
- * ext_partial [ext_rows][2][C] (sum, sum of squares), N == 1. */
+/* forward with the per-channel partial sums supplied by the producer (b2_conv3d_fused, b2_conv2d_fused):
+ * ext_partial [N][ext_rows][2][C] (sum, sum of squares). */
 int b2_groupnorm_fwd_ext(const float* x, const float* res, const float* gamma, const float* beta,
                          float* y, float* stats, int N, int C, int64_t S, int G, float eps,
                          int relu, const float* ext_partial, int ext_rows, void* workspace,
@@ -279,7 +296,7 @@ int b2_groupnorm_bwd(const float* gy, const float* x, const float* y, const floa
                      const float* stats, float* gx, float* gres, int N, int C, int64_t S, int G,
                      int relu, void* workspace, void* stream);
 /* backward with (sum gz*x, sum gz) per channel supplied by the kernel that produced gy
- * (b2_conv3d_fused stat_mode 2 / 3): ext_partial [ext_rows][2][C], N == 1, relu 0 or 2. */
+ * (b2_conv3d_fused / b2_conv2d_fused stat_mode 2 / 3): ext_partial [N][ext_rows][2][C], relu 0 or 2. */
 int b2_groupnorm_bwd_ext(const float* gy, const float* x, const float* y, const float* gamma,
                          const float* stats, float* gx, float* gres, int N, int C, int64_t S, int G,
                          int relu, const float* ext_partial, int ext_rows, void* workspace,

@@ -174,3 +174,113 @@ def test_conv2d_rejects_unsupported(ops):
         ops.conv2d(torch.randn(1, 32, 9, 8).cuda(), torch.randn(32, 32, 3, 3).cuda(), None, 2, 1)   # odd dims, stride 2
     with pytest.raises(RuntimeError):
         ops.conv2d(torch.randn(1, 32, 8, 8), torch.randn(32, 32, 3, 3))                            # CPU tensors
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# GroupNorm sums in the conv2d epilogue (upstream convbn = Conv2d + GroupNorm behind attack/DSGN/pgd_attack.py:308/:336)
+# ---------------------------------------------------------------------------------------------------------------
+def _cl2(shape, g):
+    return torch.randn(shape, generator=g).cuda().contiguous(memory_format=torch.channels_last)
+
+
+# (n, cin, cout, h, w, k, stride, dilation, bias)
+STAT_CASES = [
+    (2, 32, 32, 24, 40, 3, 1, 1, False),       # halo kernel, two samples, fewer tiles than CTAs (zero rows)
+    (2, 32, 64, 200, 328, 3, 1, 1, False),     # halo kernel, more tiles than CTAs: a CTA's sequence crosses the samples
+    (2, 32, 64, 64, 96, 3, 2, 1, False),       # generic kernel, stride 2
+    (3, 64, 128, 37, 29, 1, 1, 1, True),       # generic kernel 1x1, three samples, ragged tiles, bias
+    (1, 128, 128, 20, 24, 3, 1, 2, False),     # dilation 2
+    (2, 320, 128, 18, 26, 3, 1, 1, False),     # widest K
+]
+
+
+@pytest.mark.parametrize("split", [1, 0])
+@pytest.mark.parametrize("case", STAT_CASES)
+def test_conv2d_epilogue_adds_up_the_groupnorm_statistics(ops, case, split):
+    """partial[n, rows, 2, C] summed over rows = per-channel (sum, sum of squares) of the conv output; GroupNorm fed
+    with it equals GroupNorm with its own statistics pass; the table is bitwise reproducible."""
+    n, cin, cout, h, w, k, stride, dil, has_bias = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = _cl2((n, cin, h, w), g)
+    wt = (torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5).cuda()
+    b = torch.randn(cout, generator=g).cuda() if has_bias else None
+    gamma, beta = (torch.rand(cout, generator=g) + 0.5).cuda(), (torch.randn(cout, generator=g) * 0.3).cuda()
+    ops.set_conv2d_split(split)
+    try:
+        y0 = ops.conv2d(x, wt, b, stride, dil)
+        n0 = ops.LAUNCH_COUNT
+        y, part = ops.conv2d_with_stats(x, wt, b, stride, dil)
+        assert ops.LAUNCH_COUNT - n0 == 1
+        assert part is not None and part.shape[0] == n and tuple(part.shape[2:]) == (2, cout)
+        assert torch.equal(y, y0)
+        tot = part.double().sum(1).cpu()
+        yd = y.double().cpu()
+        ref = torch.stack([yd.sum((2, 3)), (yd * yd).sum((2, 3))], 1)
+        assert (tot - ref).abs().max().item() < 2e-5 * ref.abs().max().item()
+        y2, part2 = ops.conv2d_with_stats(x, wt, b, stride, dil)
+        assert torch.equal(part, part2)
+        n1 = ops.LAUNCH_COUNT
+        a = ops.groupnorm_act(y, gamma, beta, 32, 1e-5, relu=True, partial=part)
+        fused_launches = ops.LAUNCH_COUNT - n1
+        r = ops.groupnorm_act(y, gamma, beta, 32, 1e-5, relu=True)
+        assert fused_launches == 2 and ops.LAUNCH_COUNT - n1 == 5
+        assert (a - r).abs().max().item() < 2e-5
+    finally:
+        ops.set_conv2d_split(1)
+
+
+@pytest.mark.parametrize("relu,with_res,second_consumer,case", [
+    (True, False, False, (2, 64, 64, 40, 56, 3, 1)),      # norm+ReLU -> 3x3 conv: mask recomputed in the halo kernel's epilogue
+    (False, True, False, (2, 64, 64, 40, 56, 3, 1)),      # norm + shortcut, no activation (BasicBlock tail)
+    (True, False, True, (2, 32, 32, 200, 328, 3, 1)),     # the norm's output is forked (BasicBlock input); many tiles per CTA
+    (True, False, False, (3, 128, 32, 19, 27, 1, 1)),     # 1x1 consumer (generic kernel), ragged, three samples
+    (True, False, False, (1, 128, 128, 24, 40, 3, 2)),    # dilation-2 consumer
+    (True, True, False, (2, 64, 64, 24, 40, 3, 1)),       # ReLU + residual needs the saved output: not fused, still right
+    # a second consumer WITHOUT the fork: autograd adds the two gradients itself (in place into the conv's gradient
+    # buffer if it holds the last reference to it) -- the sums of the conv's epilogue must then be dropped
+    (True, False, "plain_after", (2, 64, 64, 24, 40, 3, 1)),
+    (True, False, "plain_before", (2, 64, 64, 24, 40, 3, 1)),
+])
+def test_groupnorm2d_backward_sums_from_the_consuming_convs_dgrad(ops, relu, with_res, second_consumer, case):
+    """conv_a -> GroupNorm -> conv_b on 2-D maps: conv_b's data-gradient launch adds up the norm's backward sums in its
+    epilogue and conv_a's epilogue the forward statistics; the input gradient equals the unfused path."""
+    n, c, c2, h, w, k, dil = case
+    g = torch.Generator().manual_seed(sum(case))
+    x = _cl2((n, c, h, w), g).requires_grad_(True)
+    wa = (torch.randn(c, c, 3, 3, generator=g) * (9 * c) ** -0.5).cuda()
+    wb = (torch.randn(c2, c, k, k, generator=g) * (k * k * c) ** -0.5).cuda()
+    gamma, beta = (torch.rand(c, generator=g) + 0.5).cuda(), (torch.randn(c, generator=g) * 0.3).cuda()
+    res = _cl2((n, c, h, w), g) if with_res else None
+    gy, g2 = _cl2((n, c2, h, w), g), _cl2((n, c, h, w), g)
+
+    def run(fuse):
+        old = ops.FUSE_GN_BWD, ops.FUSE_GN_STATS
+        ops.FUSE_GN_BWD = ops.FUSE_GN_STATS = fuse
+        try:
+            n0 = ops.LAUNCH_COUNT
+            ya, part = ops.conv2d_with_stats(x, wa)
+            assert (part is not None) == fuse
+            hmap = ops.groupnorm_act(ya, gamma, beta, 32, 1e-5, relu=relu, res=res, partial=part)
+            if second_consumer == "plain_before":
+                other = (hmap * g2).sum()
+                loss = (ops.conv2d(hmap, wb, None, 1, dil) * gy).sum() + other
+            elif second_consumer == "plain_after":
+                loss = (ops.conv2d(hmap, wb, None, 1, dil) * gy).sum() + (hmap * g2).sum()
+            elif second_consumer:
+                yb, h2 = ops.conv2d_fork(hmap, wb, None, 1, dil)
+                loss = (yb * gy).sum() + (h2 * g2).sum()
+            else:
+                loss = (ops.conv2d(hmap, wb, None, 1, dil) * gy).sum()
+            (gx,) = torch.autograd.grad(loss, x)
+            return gx, ops.LAUNCH_COUNT - n0
+        finally:
+            ops.FUSE_GN_BWD, ops.FUSE_GN_STATS = old
+
+    ref, n_ref = run(False)
+    got, n_got = run(True)
+    fusable = not (relu and with_res) and second_consumer not in ("plain_after", "plain_before")
+    assert n_got == n_ref - 1 - (1 if fusable else 0)      # both statistics launches of the norm are gone
+    # fp32 partial sums in another order (the norm's backward cancels sum gz*x against mean * sum gz)
+    assert (got - ref).abs().max().item() < 5e-5 * ref.abs().max().item() + 1e-7
+    got2, _ = run(True)
+    assert torch.equal(got, got2)                          # reproducible

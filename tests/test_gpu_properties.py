@@ -139,6 +139,7 @@ def test_conv3d_fork_adds_the_other_gradient_in_the_epilogue(ops, cin, cout, str
     (True, False, True, (5, 7, 9), 64),         # the norm's output also feeds a second consumer through the fork
     (True, False, False, (6, 10, 12), 128),     # two N tiles
     (True, True, False, (6, 10, 12), 64),       # ReLU + residual needs the saved output: not fused, still right
+    (True, False, "plain", (6, 10, 12), 64),    # second consumer WITHOUT the fork: autograd's own (in-place) accumulation
 ])
 def test_groupnorm_backward_sums_from_the_consuming_convs_dgrad(ops, relu, with_res, second_consumer, sp, c):
     """conv_a -> GroupNorm -> conv_b: conv_b's data-gradient launch adds up the norm's backward sums
@@ -159,7 +160,9 @@ def test_groupnorm_backward_sums_from_the_consuming_convs_dgrad(ops, relu, with_
             n0 = ops.LAUNCH_COUNT
             ya = ops.conv3d(x, wa)
             h = ops.groupnorm_act(ya, gamma, beta, 32, 1e-5, relu=relu, res=res)
-            if second_consumer:
+            if second_consumer == "plain":
+                loss = (ops.conv3d(h, wb) * gy).sum() + (h * g2).sum()
+            elif second_consumer:
                 yb, _, h2 = ops.conv3d_fork(h, wb)
                 loss = (yb * gy).sum() + (h2 * g2).sum()
             else:
@@ -171,7 +174,7 @@ def test_groupnorm_backward_sums_from_the_consuming_convs_dgrad(ops, relu, with_
 
     ref, n_ref = run(False)
     got, n_got = run(True)
-    fusable = not (relu and with_res)
+    fusable = not (relu and with_res) and second_consumer != "plain"
     assert n_got == n_ref - (1 if fusable else 0)          # the norm's backward statistics launch is gone
     assert (got - ref).abs().max().item() < 2e-5 * ref.abs().max().item() + 1e-7
     got2, _ = run(True)
