@@ -333,11 +333,14 @@ def run_b200(args):
 # driver's BENCH / SCALE records are the default config)
 # ---------------------------------------------------------------------------------------------
 def _timed(fn, steps, warmup, dev, world):
+    """(ms of the timed steps: CUDA events, max over ranks; this rank's clocks sampled during them)"""
     from eval_driving_safety_b200 import parallel
     for _ in range(warmup):
         fn()
     torch.cuda.synchronize()
     parallel.barrier()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     e0.record()
@@ -346,10 +349,15 @@ def _timed(fn, steps, warmup, dev, world):
     e1.record()
     torch.cuda.synchronize()
     parallel.barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    clocks = sampler.stop()
+    own = e0.elapsed_time(e1)
+    t = torch.tensor([own], device=dev, dtype=torch.float64)
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    return t.item()
+        lo = torch.tensor([own], device=dev, dtype=torch.float64)
+        torch.distributed.all_reduce(lo, op=torch.distributed.ReduceOp.MIN)
+        clocks["ms_fastest_rank"] = lo.item() / steps
+    return t.item(), clocks
 
 
 def run_patch(args):
@@ -389,7 +397,7 @@ def run_patch(args):
         state["k"] = k + 1
         return eng.iterate()
 
-    ms = _timed(lambda: step(devp), args.steps, args.warmup, dev, world)
+    ms, clocks = _timed(lambda: step(devp), args.steps, args.warmup, dev, world)
     h_loss = torch.zeros((), pin_memory=True)
 
     def e2e():
@@ -421,7 +429,7 @@ def run_patch(args):
                      "parallelism": "dp%d, synchronous mini-batch of %d images per patch step" % (world, world)},
           "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                   "h2d_bytes_per_step": (2 * 3 * H * W + H * W) * 4 // 2, "d2h_bytes_per_step": 4},
-          "gpu_launches": (eng.launches_per_step or 0) * units, "patch_absmax": patch.abs().max().item()})
+          "gpu_launches": (eng.launches_per_step or 0) * units, "clocks": clocks, "patch_absmax": patch.abs().max().item()})
 
 
 def run_srcnn(args):
@@ -475,7 +483,7 @@ def run_srcnn(args):
             return iteration()
         graph.replay()
         return loss_buf
-    ms = _timed(step, args.steps, args.warmup, dev, world)
+    ms, clocks = _timed(step, args.steps, args.warmup, dev, world)
     h_loss = torch.zeros((), pin_memory=True)
 
     def e2e():
@@ -508,7 +516,7 @@ def run_srcnn(args):
                      "execution": "eager" if args.eager else "CUDA graph of one PGD iteration, replayed"},
           "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                   "h2d_bytes_per_step": 2 * 3 * 600 * 1987 * 4, "d2h_bytes_per_step": 2 * 3 * 600 * 1987 * 4 + 4},
-          "gpu_launches": launches * units})
+          "gpu_launches": launches * units, "clocks": clocks})
 
 
 # ---------------------------------------------------------------------------------------------

@@ -26,7 +26,7 @@ static int g_flags[kNumFlags] = {-1, -1, -1};
 int flag_value(Flag f, const char* env_name, int dflt) {
     if (g_flags[f] >= 0) return g_flags[f];
     const char* e = getenv(env_name);
-    if (e && (e[0] == '0' || e[0] == '1')) return e[0] - '0';
+    if (e && e[0] >= '0' && e[0] <= '9') return atoi(e);
     return dflt;
 }
 
@@ -41,7 +41,7 @@ extern "C" int b2_set_flag(const char* name, int value) {
     else if (!strcmp(name, "conv2d_halo")) idx = b2::kFlagConv2dHalo;
     else if (!strcmp(name, "conv_s2_pair")) idx = b2::kFlagConvG2Pair;
     B2_REQUIRE(idx >= 0, "set_flag: unknown flag '%s'", name);
-    b2::g_flags[idx] = value < 0 ? -1 : (value ? 1 : 0);
+    b2::g_flags[idx] = value < 0 ? -1 : value;
     return 0;
 }
 
