@@ -142,6 +142,139 @@ depth_head_gather_kernel(const float* __restrict__ G, float* __restrict__ gcost,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// x4 specialisation (the KITTI configuration: 48x96x312 -> 192x384x1248).  With an integer ratio of 4 the depth
+// lerp is periodic: fine planes 4k+2 .. 4k+5 blend coarse planes (k, k+1) with l1 = 1/8, 3/8, 5/8, 7/8, planes 0, 1
+// are coarse plane 0 and the last two blend plane D-1 with itself -- the per-plane source-index arithmetic, its
+// branches and the per-plane online-softmax rescale (the kernels above are instruction-bound on exactly those) become
+// four unrolled FMAs + one exp per plane.  A lerp never exceeds its end points, so the running maximum is taken over
+// the COARSE column (one conditional rescale per coarse plane); plane depths come from a shared-memory table.
+// Same operation order per plane as the generic kernel (ATen's l0*c0 + l1*c1, ascending planes).
+// ---------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(256)
+depth_head_pixel_x4_kernel(const float* __restrict__ cost, const float* __restrict__ gdepth,
+                           float* __restrict__ depth, float* __restrict__ G, DhGeom g,
+                           float2* __restrict__ sm_out, const float2* __restrict__ sm_in,
+                           const float* __restrict__ depth_in) {
+    extern __shared__ float zt[];                               // [J] plane depths
+    for (int j = threadIdx.x; j < g.J; j += blockDim.x) zt[j] = __fadd_rn(g.z0, __fmul_rn((float)j + 0.5f, g.dz));
+    __syncthreads();
+    const int64_t total = (int64_t)g.N * g.H * g.W;
+    const int D = g.D;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % g.W), y = (int)((i / g.W) % g.H), n = (int)(i / ((int64_t)g.W * g.H));
+        const Lerp ly = lerp_src(y, g.sh, g.Hc), lx = lerp_src(x, g.sw, g.Wc);
+        const float* cn = cost + (int64_t)n * D * g.Hc * g.Wc;
+        float m, s, dep;
+        const bool saved = MODE == 1 && sm_in != nullptr;
+        if (saved) {
+            const float2 ms = __ldg(sm_in + i); m = ms.x; s = ms.y; dep = __ldg(depth_in + i);
+        } else {
+            float c0 = dh_col(cn, 0, ly, lx, g.Hc, g.Wc), t;
+            m = c0; s = 2.f; t = zt[0] + zt[1];                  // planes 0, 1: v = c0, exp(0) = 1
+            for (int k = 0; k + 1 < D; ++k) {
+                const float c1 = dh_col(cn, k + 1, ly, lx, g.Hc, g.Wc);
+                if (c1 > m) { const float r = __expf(m - c1); s *= r; t *= r; m = c1; }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float l1 = 0.125f + 0.25f * q, l0 = 1.f - l1;
+                    const float e = __expf(l0 * c0 + l1 * c1 - m);
+                    s += e; t += e * zt[4 * k + 2 + q];
+                }
+                c0 = c1;
+            }
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {                       // last two planes: both sources are plane D-1
+                const float l1 = 0.125f + 0.25f * q, l0 = 1.f - l1;
+                const float e = __expf(l0 * c0 + l1 * c0 - m);
+                s += e; t += e * zt[4 * D - 2 + q];
+            }
+            dep = t / s;
+        }
+        if (MODE == 0) {
+            depth[i] = dep;
+            if (sm_out) sm_out[i] = make_float2(m, s);
+            continue;
+        }
+        // g_up[j] = g * p_j * (z_j - depth), accumulated onto its two source planes in ascending plane order
+        const float go = __ldg(gdepth + i) / s;
+        float* Gp = G + (int64_t)n * D * g.H * g.W + (int64_t)y * g.W + x;
+        const int64_t plane = (int64_t)g.H * g.W;
+        float c0 = dh_col(cn, 0, ly, lx, g.Hc, g.Wc);
+        float a0 = 0.f;
+        {
+            const float e = go * __expf(c0 - m);
+            a0 += e * (zt[0] - dep);
+            a0 += e * (zt[1] - dep);
+        }
+        for (int k = 0; k + 1 < D; ++k) {
+            const float c1 = dh_col(cn, k + 1, ly, lx, g.Hc, g.Wc);
+            float a1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float l1 = 0.125f + 0.25f * q, l0 = 1.f - l1;
+                const float gu = go * __expf(l0 * c0 + l1 * c1 - m) * (zt[4 * k + 2 + q] - dep);
+                a0 += l0 * gu; a1 += l1 * gu;
+            }
+            Gp[(int64_t)k * plane] = a0;
+            a0 = a1; c0 = c1;
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float l1 = 0.125f + 0.25f * q, l0 = 1.f - l1;
+            const float gu = go * __expf(l0 * c0 + l1 * c0 - m) * (zt[4 * D - 2 + q] - dep);
+            a0 += l0 * gu; a0 += l1 * gu;
+        }
+        Gp[(int64_t)(D - 1) * plane] = a0;
+    }
+}
+
+// x4 gather: the output rows whose bilinear stencil touches coarse row h are exactly 4h-2 .. 4h+5 (clipped): an 8 x 8
+// window with the weights hoisted, instead of a 14 x 14 scan that recomputes source indices per pixel.
+__global__ void __launch_bounds__(256)
+depth_head_gather_x4_kernel(const float* __restrict__ G, float* __restrict__ gcost, DhGeom g) {
+    const int64_t total = (int64_t)g.N * g.D * g.Hc * g.Wc;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const int w = (int)(i % g.Wc), h = (int)((i / g.Wc) % g.Hc);
+        const int64_t nd = i / ((int64_t)g.Wc * g.Hc);
+        const float* Gp = G + nd * g.H * g.W;
+        float wx[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int x = 4 * w - 2 + u;
+            float v = 0.f;
+            if (x >= 0 && x < g.W) {
+                const Lerp lx = lerp_src(x, g.sw, g.Wc);
+                v = (lx.i0 == w ? lx.l0 : 0.f) + (lx.i1 == w ? lx.l1 : 0.f);
+            }
+            wx[u] = v;
+        }
+        float acc = 0.f;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            const int y = 4 * h - 2 + r;
+            if (y < 0 || y >= g.H) continue;
+            const Lerp ly = lerp_src(y, g.sh, g.Hc);
+            const float wy = (ly.i0 == h ? ly.l0 : 0.f) + (ly.i1 == h ? ly.l1 : 0.f);
+            const float* row = Gp + (int64_t)y * g.W;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int x = 4 * w - 2 + u;
+                if (x >= 0 && x < g.W) acc += wy * wx[u] * __ldg(row + x);
+            }
+        }
+        gcost[i] = acc;
+    }
+}
+
+static bool dh_is_x4(int D, int Hc, int Wc, int H, int W, int J) {
+    return flag_value(kFlagDepthHeadX4, "B2_DEPTH_HEAD_X4", 1) && J == 4 * D && H == 4 * Hc && W == 4 * Wc && D >= 2;
+}
+
 static DhGeom dh_geom(int N, int D, int Hc, int Wc, int H, int W, int J, float z0, float dz) {
     DhGeom g{N, D, Hc, Wc, H, W, J, z0, dz, (float)D / (float)J, (float)Hc / (float)H, (float)Wc / (float)W};
     return g;
@@ -158,8 +291,12 @@ extern "C" int b2_depth_head_fwd(const float* cost, float* depth, float* sm_stat
     B2_REQUIRE(H % Hc == 0 && W % Wc == 0 && J % D == 0, "depth_head_fwd: integer upsampling ratios only (%dx%dx%d -> %dx%dx%d)", D, Hc, Wc, J, H, W);
     int64_t total = (int64_t)N * H * W;
     if (total == 0) return 0;
-    depth_head_pixel_kernel<0><<<stream_grid(total, 256, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(
-        cost, nullptr, depth, nullptr, dh_geom(N, D, Hc, Wc, H, W, J, z0, dz), (float2*)sm_stats, nullptr, nullptr);
+    if (dh_is_x4(D, Hc, Wc, H, W, J))
+        depth_head_pixel_x4_kernel<0><<<stream_grid(total, 256, kNumSMs * 8), 256, J * sizeof(float), (cudaStream_t)stream>>>(
+            cost, nullptr, depth, nullptr, dh_geom(N, D, Hc, Wc, H, W, J, z0, dz), (float2*)sm_stats, nullptr, nullptr);
+    else
+        depth_head_pixel_kernel<0><<<stream_grid(total, 256, kNumSMs * 16), 256, 0, (cudaStream_t)stream>>>(
+            cost, nullptr, depth, nullptr, dh_geom(N, D, Hc, Wc, H, W, J, z0, dz), (float2*)sm_stats, nullptr, nullptr);
     return check_launch("depth_head_fwd");
 }
 
@@ -179,9 +316,15 @@ extern "C" int b2_depth_head_bwd(const float* cost, const float* gdepth, float* 
     if (total == 0) return 0;
     DhGeom g = dh_geom(N, D, Hc, Wc, H, W, J, z0, dz);
     cudaStream_t st = (cudaStream_t)stream;
-    depth_head_pixel_kernel<1><<<stream_grid(total, 256, kNumSMs * 16), 256, 0, st>>>(
-        cost, gdepth, nullptr, (float*)workspace, g, nullptr, (const float2*)sm_stats, depth);
     int64_t cells = (int64_t)N * D * Hc * Wc;
-    depth_head_gather_kernel<<<stream_grid(cells, 256, kNumSMs * 16), 256, 0, st>>>((const float*)workspace, gcost, g);
+    if (dh_is_x4(D, Hc, Wc, H, W, J)) {
+        depth_head_pixel_x4_kernel<1><<<stream_grid(total, 256, kNumSMs * 8), 256, J * sizeof(float), st>>>(
+            cost, gdepth, nullptr, (float*)workspace, g, nullptr, (const float2*)sm_stats, depth);
+        depth_head_gather_x4_kernel<<<stream_grid(cells, 256, kNumSMs * 16), 256, 0, st>>>((const float*)workspace, gcost, g);
+    } else {
+        depth_head_pixel_kernel<1><<<stream_grid(total, 256, kNumSMs * 16), 256, 0, st>>>(
+            cost, gdepth, nullptr, (float*)workspace, g, nullptr, (const float2*)sm_stats, depth);
+        depth_head_gather_kernel<<<stream_grid(cells, 256, kNumSMs * 16), 256, 0, st>>>((const float*)workspace, gcost, g);
+    }
     return check_launch("depth_head_bwd");
 }

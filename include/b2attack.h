@@ -39,7 +39,8 @@ const char* b2_last_error(void);
 /* Kernel-variant switches for A/B measurements and for testing both variants in one process:
  *   "conv_dc_pair"  1 = CTA-pair (tcgen05 cta_group::2) transposed-conv kernel (default), 0 = single-CTA;
  *   "conv_s2_pair"  1 = CTA-pair variant of the one-tap-per-stage kernel that serves the stride-2 convs (default), 0 = single-CTA;
- *   "conv2d_halo"   1 = halo-reuse stride-1 3x3 2-D conv kernel (default), 0 = one tap per stage.
+ *   "conv2d_halo"   1 = halo-reuse stride-1 3x3 2-D conv kernel (default), 0 = one tap per stage;
+ *   "depth_head_x4" 1 = unrolled depth-head kernels when every upsampling ratio is 4 (default), 0 = the generic ones.
  * value < 0 returns the flag to its default (environment variable B2_<NAME>, else the built-in default). */
 int b2_set_flag(const char* name, int value);
 

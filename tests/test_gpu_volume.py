@@ -303,6 +303,29 @@ def test_depth_head_vs_torch(ops, dims):
     assert torch.equal(gc, gc2)
 
 
+def test_depth_head_x4_kernels_against_the_generic_ones(ops):
+    """The ratio-4 specialisation (KITTI: 48x96x312 -> 192x384x1248) against the generic kernels on the same input:
+    same lerp and accumulation order; only the softmax shift differs (maximum of the coarse column instead of the
+    fine one), i.e. last-ulp differences."""
+    from eval_driving_safety_b200 import _lib
+    g = torch.Generator().manual_seed(17)
+    res = {}
+    for dims in ((1, 12, 24, 40), (2, 5, 7, 9)):
+        n, d, hc, wc = dims
+        cost = (torch.randn(n, 1, d, hc, wc, generator=g) * 4).cuda().requires_grad_(True)
+        gy = torch.randn(n, 4 * hc, 4 * wc, generator=g).cuda()
+        for flag in (0, 1):
+            _lib.set_flag("depth_head_x4", flag)
+            try:
+                out = ops.depth_head(cost, (4 * d, 4 * hc, 4 * wc), 2.0, 0.2)
+                (gc,) = torch.autograd.grad(out, cost, gy)
+            finally:
+                _lib.set_flag("depth_head_x4", None)
+            res[flag] = (out, gc)
+        assert max_err(res[1][0], res[0][0]) < 3e-6 * res[0][0].abs().max().item()        # a few ulps
+        assert max_err(res[1][1], res[0][1]) < 5e-6 * max(1.0, res[0][1].abs().max().item())
+
+
 def test_bev_pool_vs_torch(ops):
     g = torch.Generator().manual_seed(31)
     for ydim, p in ((8, 2), (8, 4), (10, 4), (7, 3)):      # the last two leave rows past the last whole window
