@@ -57,6 +57,9 @@ SIGNATURES = {
     "b2_conv2d_stat_rows": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_vp]),
     "b2_conv2d_first_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
     "b2_conv2d_first_dgrad": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_vp]),
+    "b2_channel_concat": (c_int, [c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
+    "b2_channel_split": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_vp]),
+    "b2_add_prefix": (c_int, [c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "b2_conv3d_c1_workspace_bytes": (c_i64, [c_int, c_int, c_int, c_int]),
     "b2_conv3d_c1_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "b2_conv3d_c1_dgrad": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp]),

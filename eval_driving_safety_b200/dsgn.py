@@ -78,6 +78,8 @@ def run_convbn_3d(seq, x, relu=False, res=None, fork=False):
 # in-kernel (fp32-class accuracy, ops.conv2d).  'cudnn' / 'cudnn_tf32x3': the stock cuDNN kernels of
 # round 1, kept for A/B measurements only (TF32 per torch.backends flags / split stacked on the host).
 BACKBONE_IMPL = os.environ.get("B2_BACKBONE", "b2")
+# concat / split glue of the extractor and the heads through the one-launch ops (0: stock torch.cat / slicing, A/B only)
+GLUE_OPS = os.environ.get("B2_GLUE_OPS", "1") != "0"
 
 
 def set_backbone_impl(mode):
@@ -202,10 +204,16 @@ def _interp_matrix(n_in, n_out, device):
 def upsample_bilinear_matmul(x, size):
     """F.interpolate(x, size, 'bilinear', align_corners=False) as two small GEMMs: the SPP maps
     are tiny (1x4 .. 12x39), and ATen's upsample backward serialises on atomics there (7.6 ms per
-    iteration measured); the GEMM form is deterministic and ~100x faster in backward."""
-    ah = _interp_matrix(x.shape[-2], size[0], x.device)
-    aw = _interp_matrix(x.shape[-1], size[1], x.device)
-    return torch.matmul(torch.matmul(ah, x), aw.t())
+    iteration measured); the GEMM form is deterministic and ~100x faster in backward.
+    Both GEMMs run on the channels-last memory as it is ([N*h, w, C] then [N, h, X*C] are contiguous views), so
+    neither direction makes a layout copy and the result is a channels-last map."""
+    n, c, h, w = x.shape
+    ah = _interp_matrix(h, size[0], x.device)
+    aw = _interp_matrix(w, size[1], x.device)
+    xc = x.contiguous(memory_format=torch.channels_last).permute(0, 2, 3, 1)        # [N, h, w, C], contiguous
+    t = torch.matmul(aw, xc.reshape(n * h, w, c))                                   # [N*h, X, C]
+    u = torch.matmul(ah, t.view(n, h, size[1] * c))                                 # [N, Y, X*C]
+    return u.view(n, size[0], size[1], c).permute(0, 3, 1, 2)
 
 
 class FeatureExtraction(nn.Module):
@@ -261,10 +269,17 @@ class FeatureExtraction(nn.Module):
             for br in self.branches:
                 y = run_convbn_2d(br[1], br[0](skip), relu=True)
                 cat.append(upsample_bilinear_matmul(y, size))
-        cat = torch.cat(cat, 1).contiguous(memory_format=torch.channels_last)
+        n_rpn = cat[0].shape[0] if rpn_samples is None else rpn_samples
+        if BACKBONE_IMPL == "b2" and GLUE_OPS:
+            # one launch for the concatenation and one for its backward (contiguous gradient slices); the gradient
+            # of the first n_rpn samples coming from the second head is merged in one launch as well
+            cat = ops.cat_channels(cat)
+            cat, cat_rpn = ops.prefix_fork(cat, n_rpn) if n_rpn < cat.shape[0] else (cat, cat)
+        else:
+            cat = torch.cat(cat, 1).contiguous(memory_format=torch.channels_last)
+            cat_rpn = cat[:n_rpn]
         f = conv2d_any(self.lastconv[2], run_convbn_2d(self.lastconv[0], cat, relu=True))
-        n_rpn = cat.shape[0] if rpn_samples is None else rpn_samples
-        r = conv2d_any(self.rpnconv[2], run_convbn_2d(self.rpnconv[0], cat[:n_rpn], relu=True))
+        r = conv2d_any(self.rpnconv[2], run_convbn_2d(self.rpnconv[0], cat_rpn, relu=True))
         return f, r
 
 
@@ -460,6 +475,8 @@ class StereoNet(nn.Module):
             self._head_cache = (key, w, b, widths)
         _, w, b, widths = self._head_cache
         y = ops.conv2d(bev, w, b, 1, 1)
+        if GLUE_OPS:
+            return ops.split_channels(y, widths)   # views; their gradients are assembled in one launch
         outs, o = [], 0
         for n in widths:
             outs.append(y[:, o:o + n])
@@ -474,7 +491,7 @@ class StereoNet(nn.Module):
         # result equals two separate passes)
         n = imgL.shape[0]
         feat, rpnL = self.feature_extraction(torch.cat([imgL, imgR], 0), rpn_samples=n)
-        featL, featR = feat[:n], feat[n:]
+        featL, featR = ops.split_batch(feat, n) if GLUE_OPS else (feat[:n], feat[n:])
         cost, out, cost1 = self.psv_stage(featL, featR, calibs_fu, calibs_baseline)
         outputs = {'depth_preds': self.depth_head(cost1, imgL.shape[-2:])}
         if self.cfg.RPN3D_ENABLE:

@@ -967,6 +967,157 @@ def groupnorm_act(x, gamma, beta, groups, eps=1e-5, relu=False, res=None, partia
     return y
 
 
+# ---------------------------------------------------------------------------
+# concat / split glue of the extractor (one launch per direction)
+# ---------------------------------------------------------------------------
+def _ptr_array(tensors):
+    return (ctypes.c_void_p * len(tensors))(*[None if t is None else t.data_ptr() for t in tensors])
+
+
+def _int_array(vals):
+    return (ctypes.c_int * len(vals))(*[int(v) for v in vals])
+
+
+def _channel_concat(pieces, widths, n, h, w, device):
+    """[N, sum(widths), H, W] channels-last from channels-last pieces (None = zeros), one launch."""
+    lib = _lib.load()
+    out = empty_cl2(n, sum(widths), h, w, device)
+    with _op("channel_concat", 1, 8 * out.numel()):
+        check(lib.b2_channel_concat(_ptr_array(pieces), _int_array(widths), len(widths), _p(out), n * h * w, _stream()),
+              "channel_concat")
+    return out
+
+
+def _channel_split(wide, widths, want):
+    """Contiguous channels-last pieces of ``wide`` (only those with want[k]), one launch."""
+    lib = _lib.load()
+    n, _, h, w = wide.shape
+    outs = [empty_cl2(n, wk, h, w, wide.device) if wk and k < len(want) and want[k] else None for k, wk in enumerate(widths)]
+    with _op("channel_split", 1, 8 * wide.numel()):
+        check(lib.b2_channel_split(_p(wide), _ptr_array(outs), _int_array(widths), len(widths), n * h * w, _stream()),
+              "channel_split")
+    return outs
+
+
+class CatChannelsFn(Function):
+    """torch.cat(xs, 1) of channels-last maps; the backward hands every input its contiguous gradient slice from ONE
+    launch (stock autograd: strided views of the wide gradient that each consumer copies)."""
+
+    @staticmethod
+    def forward(ctx, *xs):
+        _need_cuda(*xs)
+        xs = [cl2(x) for x in xs]
+        n, _, h, w = xs[0].shape
+        widths = [x.shape[1] for x in xs]
+        if any(x.shape[0] != n or tuple(x.shape[2:]) != (h, w) for x in xs) or len(xs) > 8 or any(c % 4 for c in widths):
+            raise RuntimeError("cat_channels: up to 8 maps of one size with channel counts that are multiples of 4")
+        ctx.widths = widths
+        return _channel_concat(xs, widths, n, h, w, xs[0].device)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        return tuple(_channel_split(cl2(g), ctx.widths, ctx.needs_input_grad))
+
+
+def cat_channels(xs):
+    return CatChannelsFn.apply(*xs)
+
+
+class SplitChannelsFn(Function):
+    """y -> views y[:, 0:w0], y[:, w0:w0+w1], ... (trailing channels beyond sum(widths) are padding); the backward
+    assembles the gradient of y from whichever pieces received one in ONE launch (zeros elsewhere)."""
+
+    @staticmethod
+    def forward(ctx, y, *widths):
+        _need_cuda(y)
+        y = cl2(y)
+        if any(wk % 4 for wk in widths) or y.shape[1] % 4 or sum(widths) > y.shape[1] or len(widths) > 7:
+            raise RuntimeError("split_channels: up to 7 widths, multiples of 4, within the %d channels" % y.shape[1])
+        ctx.widths, ctx.shape = list(widths), tuple(y.shape)
+        ctx.set_materialize_grads(False)
+        outs, o = [], 0
+        for wk in widths:
+            outs.append(y[:, o:o + wk])
+            o += wk
+        return tuple(outs)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, *gs):
+        n, c, h, w = ctx.shape
+        widths = list(ctx.widths)
+        pieces = [None if g is None else cl2(g) for g in gs]
+        if sum(widths) < c:
+            widths.append(c - sum(widths)); pieces.append(None)
+        dev = next(g.device for g in gs if g is not None)
+        return (_channel_concat(pieces, widths, n, h, w, dev),) + (None,) * len(ctx.widths)
+
+
+def split_channels(y, widths):
+    return SplitChannelsFn.apply(y, *widths)
+
+
+class PrefixForkFn(Function):
+    """x -> (x, x[:n]) for a tensor consumed whole AND through its first n samples; the backward merges the two
+    gradients in ONE launch (stock autograd: zero-filled full-size buffer + copy + add)."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        _need_cuda(x)
+        x = cl2(x)
+        ctx.n, ctx.shape = int(n), tuple(x.shape)
+        ctx.set_materialize_grads(False)
+        return x.view_as(x), x[:n]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g_full, g_pre):
+        if g_pre is None:
+            return g_full, None
+        lib = _lib.load()
+        g_pre = cl2(g_pre)
+        if g_full is None:                                        # only the prefix view was used downstream
+            out = torch.zeros(ctx.shape, device=g_pre.device, dtype=g_pre.dtype).contiguous(memory_format=CL2)
+            out[:ctx.n] = g_pre
+            return out, None
+        g_full = cl2(g_full)
+        out = empty_cl2(*g_full.shape, g_full.device)
+        with _op("add_prefix", 1, 4 * (2 * g_full.numel() + g_pre.numel())):
+            check(lib.b2_add_prefix(_p(g_full), _p(g_pre), _p(out), g_full.numel(), g_pre.numel(), _stream()), "add_prefix")
+        return out, None
+
+
+def prefix_fork(x, n):
+    return PrefixForkFn.apply(x, n)
+
+
+class SplitBatchFn(Function):
+    """x -> (x[:n], x[n:]); backward = one concatenation of the two gradients."""
+
+    @staticmethod
+    def forward(ctx, x, n):
+        ctx.n, ctx.shape = int(n), tuple(x.shape)
+        ctx.set_materialize_grads(False)
+        return x[:n], x[n:]
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, ga, gb):
+        n, shape = ctx.n, ctx.shape
+        ref = ga if ga is not None else gb
+        if ga is None:
+            ga = ref.new_zeros((n,) + shape[1:])
+        if gb is None:
+            gb = ref.new_zeros((shape[0] - n,) + shape[1:])
+        fmt = CL2 if len(shape) == 4 else torch.contiguous_format
+        return torch.cat([ga.contiguous(memory_format=fmt), gb.contiguous(memory_format=fmt)], 0), None
+
+
+def split_batch(x, n):
+    return SplitBatchFn.apply(x, n)
+
+
 class BevPoolFn(Function):
     """[N,C,Z,Y,X] volume -> [N, C*(Y/p), Z, X] BEV map (channel = c*(Y/p)+yy), both channels-last:
     F.avg_pool3d(v, (1,p,1)).permute(0,1,3,2,4).reshape(n, c*yy, z, x) in one pass."""

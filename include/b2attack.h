@@ -309,6 +309,24 @@ int b2_groupnorm_bwd_ext(const float* gy, const float* x, const float* y, const 
 int b2_bev_pool_fwd(const float* v, float* bev, int N, int C, int Z, int Y, int X, int p, void* stream);
 int b2_bev_pool_bwd(const float* gbev, float* gv, int N, int C, int Z, int Y, int X, int p, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * Channel concatenation / split of channels-last maps and the gradient merge of a tensor that is also
+ * consumed through a batch prefix: the torch.cat of the SPP branches and the slicing around the extractor's
+ * two heads / the detection heads (upstream feature_extraction.forward, reached from
+ * attack/DSGN/pgd_attack.py:308 / :336).  One streaming launch per direction instead of autograd's strided
+ * views + per-consumer copies + zero fills + adds.
+ *   channel_concat: wide[row][off_k + c] = srcs[k][row][c]; srcs / widths are HOST arrays of n_pieces (<= 8) device
+ *                   pointers / channel counts (multiples of 4); a NULL source contributes zeros; rows = N*H*W.
+ *   channel_split : the reverse; a NULL destination is skipped.
+ *   add_prefix    : out[i] = a[i] + (i < count_prefix ? b[i] : 0)   (a: gradient of the whole batch, b: gradient
+ *                   that arrived through the view of its first samples).
+ * ------------------------------------------------------------------------- */
+int b2_channel_concat(const float* const* srcs, const int* widths, int n_pieces, float* wide, int64_t rows,
+                      void* stream);
+int b2_channel_split(const float* wide, float* const* dsts, const int* widths, int n_pieces, int64_t rows,
+                     void* stream);
+int b2_add_prefix(const float* a, const float* b, float* out, int64_t count, int64_t count_prefix, void* stream);
+
 /* Depth head of the PSV branch (SURVEY 8f "next" row 1), fused and deterministic: trilinear
  * upsample of the 1-channel cost volume cost [N,D,Hc,Wc] to (J,H,W) (align_corners=False),
  * softmax over the J planes, expectation over z_j = z0 + (j+0.5)*dz  ->  depth [N,H,W].

@@ -351,3 +351,80 @@ def test_runner_writes_detections_for_the_evaluation_stage(built_lib, tmp_path):
             assert 1 <= len(dets) <= 20 and all(d["type"] == "Car" and 0.0 <= d["score"] <= 1.0 for d in dets)
     col = parallel.STAT_FIELDS.index("n_det_clean")
     assert (stats[:, col] >= 1).all() and (stats[:, col + 1] >= 1).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# concat / split glue of the extractor (upstream feature_extraction.forward torch.cat + slicing): bit-exact copies
+# ---------------------------------------------------------------------------------------------------------------
+def _cl(t):
+    return t.cuda().contiguous(memory_format=torch.channels_last)
+
+
+def test_cat_and_split_channels_match_torch_cat_and_slicing(built_lib):
+    from eval_driving_safety_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    widths = [64, 128, 32, 32, 32, 32]
+    xs = [_cl(torch.randn(2, c, 13, 21, generator=g)).requires_grad_(True) for c in widths]
+    ref = torch.cat(xs, 1)
+    n0 = ops.LAUNCH_COUNT
+    out = ops.cat_channels(xs)
+    assert ops.LAUNCH_COUNT - n0 == 1 and torch.equal(out, ref)
+    assert out.permute(0, 2, 3, 1).is_contiguous()
+    gy = _cl(torch.randn(ref.shape, generator=g))
+    want = torch.autograd.grad(ref, xs, gy)
+    n0 = ops.LAUNCH_COUNT
+    got = torch.autograd.grad(out, xs, gy)
+    assert ops.LAUNCH_COUNT - n0 == 1
+    for a, b in zip(got, want):
+        assert torch.equal(a, b) and a.permute(0, 2, 3, 1).is_contiguous()
+    # only some inputs need a gradient
+    (g2,) = torch.autograd.grad(ops.cat_channels(xs), xs[2], gy)
+    assert torch.equal(g2, want[2])
+    # split: the fused detection heads (4 + 28 + 4 channels of a 64-wide map)
+    y = _cl(torch.randn(1, 64, 9, 14, generator=g)).requires_grad_(True)
+    a, b, c = ops.split_channels(y, [4, 28, 4])
+    assert torch.equal(a, y[:, :4]) and torch.equal(b, y[:, 4:32]) and torch.equal(c, y[:, 32:36])
+    ga, gc = torch.randn(a.shape, generator=g).cuda(), torch.randn(c.shape, generator=g).cuda()
+    (gy_got,) = torch.autograd.grad((a * ga).sum() + (c * gc).sum(), y)          # b unused -> zeros
+    (gy_ref,) = torch.autograd.grad((y[:, :4] * ga).sum() + (y[:, 32:36] * gc).sum(), y)
+    assert torch.equal(gy_got, gy_ref)
+
+
+def test_prefix_fork_and_split_batch_merge_gradients_like_autograd(built_lib):
+    from eval_driving_safety_b200 import ops
+    g = torch.Generator().manual_seed(12)
+    x = _cl(torch.randn(2, 32, 7, 10, generator=g)).requires_grad_(True)
+    wa, wb = _cl(torch.randn(2, 32, 7, 10, generator=g)), _cl(torch.randn(1, 32, 7, 10, generator=g))
+    (ref,) = torch.autograd.grad((x * wa).sum() + (x[:1] * wb).sum(), x)
+    full, pre = ops.prefix_fork(x, 1)
+    assert torch.equal(full, x) and torch.equal(pre, x[:1])
+    n0 = ops.LAUNCH_COUNT
+    (got,) = torch.autograd.grad((full * wa).sum() + (pre * wb).sum(), x)
+    assert ops.LAUNCH_COUNT - n0 == 1 and torch.equal(got, ref)
+    (only_full,) = torch.autograd.grad((ops.prefix_fork(x, 1)[0] * wa).sum(), x)
+    assert torch.equal(only_full, wa)
+    (only_pre,) = torch.autograd.grad((ops.prefix_fork(x, 1)[1] * wb).sum(), x)
+    assert torch.equal(only_pre[:1], wb) and only_pre[1:].abs().max().item() == 0
+    a, b = ops.split_batch(x, 1)
+    (gs,) = torch.autograd.grad((a * wb).sum() + (b * wa[1:]).sum(), x)
+    (gr,) = torch.autograd.grad((x[:1] * wb).sum() + (x[1:] * wa[1:]).sum(), x)
+    assert torch.equal(gs, gr)
+    (ga,) = torch.autograd.grad((ops.split_batch(x, 1)[0] * wb).sum(), x)
+    assert torch.equal(ga[:1], wb) and ga[1:].abs().max().item() == 0
+
+
+def test_spp_upsample_matmul_equals_interpolate(built_lib):
+    """The SPP branches' bilinear upsampling as two GEMMs on the channels-last memory against F.interpolate."""
+    import torch.nn.functional as F
+    from eval_driving_safety_b200 import dsgn
+    g = torch.Generator().manual_seed(13)
+    for (h, w, size) in ((1, 4, (96, 312)), (3, 9, (96, 312)), (12, 39, (96, 312)), (2, 3, (7, 11))):
+        x = _cl(torch.randn(2, 32, h, w, generator=g)).requires_grad_(True)
+        ref = F.interpolate(x, size, mode="bilinear", align_corners=False)
+        out = dsgn.upsample_bilinear_matmul(x, size)
+        assert out.shape == ref.shape and out.permute(0, 2, 3, 1).is_contiguous()
+        assert (out - ref).abs().max().item() < 1e-5
+        gy = _cl(torch.randn(ref.shape, generator=g))
+        (a,) = torch.autograd.grad(out, x, gy)
+        (b,) = torch.autograd.grad(ref, x, gy)
+        assert (a - b).abs().max().item() < 1e-4 * b.abs().max().item()
