@@ -89,18 +89,25 @@ roi_align_fwd_kernel(const float* __restrict__ feat, const float* __restrict__ r
     }
 }
 
-// Gather backward.  One thread per feature PIXEL (y, x): the (RoI, bin, weight) contributions that
-// reach the pixel do not depend on the channel, so they are enumerated once (RoIs in index order,
-// samples in (iy, ix) order) into a small per-thread list and then replayed for all C channels --
-// the enumeration cost is amortised 256x and the summation order is fixed (deterministic, no
-// float atomics).  A list that fills up is flushed (accumulating into gfeat) and refilled.
+// Gather backward.  One thread per feature PIXEL (y, x) and CHANNEL CHUNK (blockIdx.y): the (RoI, bin, weight)
+// contributions that reach the pixel do not depend on the channel, so they are enumerated once per thread (RoIs in
+// index order, samples in (iy, ix) order) into a small per-thread list and then replayed for the chunk's channels --
+// the summation order is fixed (deterministic, no float atomics).  A list that fills up is flushed (accumulating
+// into gfeat) and refilled.
+// The channel chunks are what keeps the kernel balanced: a pixel under ~100 overlapping proposals has ~700 entries, and
+// replaying them for all 256 channels in ONE thread made the launch take 24 .. 92 ms depending on how the RoI set
+// clusters (measured at 600x1987, R = 256, eight different sets); with 32-channel chunks the longest thread does an
+// eighth of that and there are eight times as many blocks to schedule.  The RoI table (level and box) is staged in
+// shared memory once per block instead of being re-derived (logf / sqrtf / div) by every thread for every RoI.
 constexpr int kRoiEntries = 96;
+constexpr int kRoiTile = 512;            // RoIs staged in smem per pass
+constexpr int kRoiChunk = 32;            // channels per thread
 
 struct RoiEntry { int off; float w; };   // off = r*C*P*P + ph*P + pw ; the channel adds c*P*P
 
 __device__ __forceinline__ void roi_flush(const RoiEntry* e, int n, const float* __restrict__ gout,
-                                          float* __restrict__ gp, int C, int PP, int64_t cstride, bool first) {
-    for (int c = 0; c < C; ++c) {
+                                          float* __restrict__ gp, int c0, int c1, int PP, int64_t cstride, bool first) {
+    for (int c = c0; c < c1; ++c) {
         float acc = first ? 0.f : gp[(int64_t)c * cstride];
         const float* gc = gout + (int64_t)c * PP;
         for (int k = 0; k < n; ++k) acc += e[k].w * __ldg(gc + e[k].off);
@@ -112,63 +119,79 @@ template <bool PYR>
 __global__ void __launch_bounds__(128)
 roi_align_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ rois,
                      float* __restrict__ gfeat, int R, int B, int C, int H, int W, int P, float scale, const PyrLevels lv) {
+    __shared__ float4 box_sh[kRoiTile];          // x1, y1, x2, y2 (image coordinates)
+    __shared__ int key_sh[kRoiTile];             // batch index << 8 | pyramid level - 2
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int level = -1;
+    int level = 0;
+    bool active = true;
     if (PYR) {                                       // pixel of which level?  (batch of 1)
-        if (i >= lv.pix_off[4]) return;
+        if (i >= lv.pix_off[4]) { active = false; i = 0; }
         level = i >= lv.pix_off[3] ? 3 : (i >= lv.pix_off[2] ? 2 : (i >= lv.pix_off[1] ? 1 : 0));
         i -= lv.pix_off[level];
         gfeat = lv.gfeat[level]; H = lv.H[level]; W = lv.W[level]; scale = lv.scale[level];
     } else if (i >= (int64_t)B * H * W) {
-        return;
+        active = false; i = 0;
     }
     const int x = (int)(i % W), y = (int)((i / W) % H), b = (int)(i / ((int64_t)W * H));
     float* gp = gfeat + (int64_t)b * C * H * W + (int64_t)y * W + x;
     const int64_t cstride = (int64_t)H * W;
     const int PP = P * P;
+    const int c0 = blockIdx.y * kRoiChunk, c1 = min(C, c0 + kRoiChunk);
+    const int want = (b << 8) | level;
     RoiEntry ent[kRoiEntries];
     int n = 0;
     bool first = true;
-    for (int r = 0; r < R; ++r) {
-        const float* roi = rois + r * 5;
-        if ((int)__ldg(roi) != b) continue;
-        if (PYR && roi_fpn_level(roi) - 2 != level) continue;
-        const float sw = __ldg(roi + 1) * scale, sh = __ldg(roi + 2) * scale;
-        const float ew = __ldg(roi + 3) * scale, eh = __ldg(roi + 4) * scale;
-        const float rw = fmaxf(ew - sw, 1.f), rh = fmaxf(eh - sh, 1.f);
-        if ((float)y < sh - 2.f || (float)y > sh + rh + 1.f || (float)x < sw - 2.f || (float)x > sw + rw + 1.f) continue;
-        float rr[5] = {(float)b, __ldg(roi + 1), __ldg(roi + 2), __ldg(roi + 3), __ldg(roi + 4)};
-        const RoiGeom g = roi_geom(rr, scale, P);
-        const float sy = g.bin_h / (float)g.grid_h, sx = g.bin_w / (float)g.grid_w;
-        const int ny = P * g.grid_h, nx = P * g.grid_w;
-        const int jy0 = max(0, (int)floorf(((float)y - 1.f - g.start_h) / sy - 0.5f) - 1);
-        const int jy1 = min(ny - 1, (int)ceilf(((float)y + 1.f - g.start_h) / sy - 0.5f) + 1);
-        const int jx0 = max(0, (int)floorf(((float)x - 1.f - g.start_w) / sx - 0.5f) - 1);
-        const int jx1 = min(nx - 1, (int)ceilf(((float)x + 1.f - g.start_w) / sx - 0.5f) + 1);
-        if (jy0 > jy1 || jx0 > jx1) continue;
-        const float inv = 1.f / (float)(g.grid_h * g.grid_w);
-        for (int jy = jy0; jy <= jy1; ++jy) {
-            const int ph = jy / g.grid_h, iy = jy % g.grid_h;
-            const float py = g.start_h + ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.grid_h;
-            int yl, yh; float wyl, wyh;
-            if (!axis_interp(py, H, yl, yh, wyl, wyh)) continue;
-            if (yl != y && yh != y) continue;
-            const float wy = (yl == y ? wyl : 0.f) + (yh == y ? wyh : 0.f);
-            for (int jx = jx0; jx <= jx1; ++jx) {
-                const int pw = jx / g.grid_w, ix = jx % g.grid_w;
-                const float px = g.start_w + pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.grid_w;
-                int xl, xh; float wxl, wxh;
-                if (!axis_interp(px, W, xl, xh, wxl, wxh)) continue;
-                if (xl != x && xh != x) continue;
-                const float wx = (xl == x ? wxl : 0.f) + (xh == x ? wxh : 0.f);
-                if (n == kRoiEntries) { roi_flush(ent, n, gout, gp, C, PP, cstride, first); first = false; n = 0; }
-                ent[n].off = r * C * PP + ph * P + pw;
-                ent[n].w = wy * wx * inv;
-                ++n;
+    for (int r0 = 0; r0 < R; r0 += kRoiTile) {
+        const int rn = min(kRoiTile, R - r0);
+        __syncthreads();
+        for (int t = threadIdx.x; t < rn; t += blockDim.x) {
+            const float* roi = rois + (int64_t)(r0 + t) * 5;
+            box_sh[t] = make_float4(__ldg(roi + 1), __ldg(roi + 2), __ldg(roi + 3), __ldg(roi + 4));
+            key_sh[t] = ((int)__ldg(roi) << 8) | (PYR ? roi_fpn_level(roi) - 2 : 0);
+        }
+        __syncthreads();
+        if (!active) continue;
+        for (int t = 0; t < rn; ++t) {
+            if (key_sh[t] != want) continue;
+            const float4 bx = box_sh[t];
+            const float sw = bx.x * scale, sh = bx.y * scale;
+            const float ew = bx.z * scale, eh = bx.w * scale;
+            const float rw = fmaxf(ew - sw, 1.f), rh = fmaxf(eh - sh, 1.f);
+            if ((float)y < sh - 2.f || (float)y > sh + rh + 1.f || (float)x < sw - 2.f || (float)x > sw + rw + 1.f) continue;
+            const int r = r0 + t;
+            float rr[5] = {(float)b, bx.x, bx.y, bx.z, bx.w};
+            const RoiGeom g = roi_geom(rr, scale, P);
+            const float sy = g.bin_h / (float)g.grid_h, sx = g.bin_w / (float)g.grid_w;
+            const int ny = P * g.grid_h, nx = P * g.grid_w;
+            const int jy0 = max(0, (int)floorf(((float)y - 1.f - g.start_h) / sy - 0.5f) - 1);
+            const int jy1 = min(ny - 1, (int)ceilf(((float)y + 1.f - g.start_h) / sy - 0.5f) + 1);
+            const int jx0 = max(0, (int)floorf(((float)x - 1.f - g.start_w) / sx - 0.5f) - 1);
+            const int jx1 = min(nx - 1, (int)ceilf(((float)x + 1.f - g.start_w) / sx - 0.5f) + 1);
+            if (jy0 > jy1 || jx0 > jx1) continue;
+            const float inv = 1.f / (float)(g.grid_h * g.grid_w);
+            for (int jy = jy0; jy <= jy1; ++jy) {
+                const int ph = jy / g.grid_h, iy = jy % g.grid_h;
+                const float py = g.start_h + ph * g.bin_h + ((float)iy + .5f) * g.bin_h / (float)g.grid_h;
+                int yl, yh; float wyl, wyh;
+                if (!axis_interp(py, H, yl, yh, wyl, wyh)) continue;
+                if (yl != y && yh != y) continue;
+                const float wy = (yl == y ? wyl : 0.f) + (yh == y ? wyh : 0.f);
+                for (int jx = jx0; jx <= jx1; ++jx) {
+                    const int pw = jx / g.grid_w, ix = jx % g.grid_w;
+                    const float px = g.start_w + pw * g.bin_w + ((float)ix + .5f) * g.bin_w / (float)g.grid_w;
+                    int xl, xh; float wxl, wxh;
+                    if (!axis_interp(px, W, xl, xh, wxl, wxh)) continue;
+                    if (xl != x && xh != x) continue;
+                    const float wx = (xl == x ? wxl : 0.f) + (xh == x ? wxh : 0.f);
+                    if (n == kRoiEntries) { roi_flush(ent, n, gout, gp, c0, c1, PP, cstride, first); first = false; n = 0; }
+                    ent[n].off = r * C * PP + ph * P + pw;
+                    ent[n].w = wy * wx * inv;
+                    ++n;
+                }
             }
         }
     }
-    if (n > 0 || first) roi_flush(ent, n, gout, gp, C, PP, cstride, first);
+    if (active && (n > 0 || first)) roi_flush(ent, n, gout, gp, c0, c1, PP, cstride, first);
 }
 
 }  // namespace b2
@@ -192,8 +215,8 @@ extern "C" int b2_roi_align_bwd(const float* gout, const float* rois, float* gfe
     B2_REQUIRE(P >= 1 && C >= 1 && H >= 1 && W >= 1, "roi_align_bwd: bad dims");
     B2_REQUIRE((int64_t)R * C * P * P < ((int64_t)1 << 31), "roi_align_bwd: gout has more than 2^31 elements");
     const int64_t npix = (int64_t)H * W;     // batch of 1 (the attack scripts run batch size 1)
-    roi_align_bwd_kernel<false><<<(unsigned)((npix + 127) / 128), 128, 0, (cudaStream_t)stream>>>(gout, rois, gfeat, R, 1, C, H, W,
-                                                                                                 P, scale, PyrLevels{});
+    roi_align_bwd_kernel<false><<<dim3((unsigned)((npix + 127) / 128), (C + kRoiChunk - 1) / kRoiChunk), 128, 0,
+                                  (cudaStream_t)stream>>>(gout, rois, gfeat, R, 1, C, H, W, P, scale, PyrLevels{});
     return check_launch("roi_align_bwd");
 }
 
@@ -235,7 +258,7 @@ extern "C" int b2_roi_align_pyramid_bwd(const float* gout, const float* rois, fl
     PyrLevels lv{};
     if (int e = fill_levels(lv, nullptr, gfeats, Hs, Ws, im_h, "roi_align_pyramid_bwd")) return e;
     const int64_t npix = lv.pix_off[4];
-    roi_align_bwd_kernel<true><<<(unsigned)((npix + 127) / 128), 128, 0, (cudaStream_t)stream>>>(gout, rois, nullptr, R, 1, C,
-                                                                                                0, 0, P, 0.f, lv);
+    roi_align_bwd_kernel<true><<<dim3((unsigned)((npix + 127) / 128), (C + kRoiChunk - 1) / kRoiChunk), 128, 0,
+                                 (cudaStream_t)stream>>>(gout, rois, nullptr, R, 1, C, 0, 0, P, 0.f, lv);
     return check_launch("roi_align_pyramid_bwd");
 }

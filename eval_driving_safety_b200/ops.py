@@ -814,9 +814,10 @@ def conv2d_with_stats(x, weight, bias=None, stride=1, dilation=1, fork=False):
     [N, rows, 2, Cout] goes to ``groupnorm_act(..., partial=)`` and is None when the kernel serving this shape has
     no statistics epilogue (the 3-channel first layer, odd widths)."""
     if weight.shape[1] != 3 and weight.shape[0] % 32:
-        y = conv2d(x, weight, bias, stride, dilation)
-        assert not fork
-        return y, None
+        if fork:
+            raise RuntimeError("conv2d_with_stats: a forked input needs an output width that is a multiple of 32 (got %d)"
+                               % weight.shape[0])
+        return conv2d(x, weight, bias, stride, dilation), None
     out = Conv2dFn.apply(x, weight, bias, stride, dilation, bool(fork), True, getattr(x, "_b2_gn", None))
     y, part = out[0], out[1]
     part = part if part.numel() else None
