@@ -80,9 +80,9 @@ SIGNATURES = {
     "b2_depth_head_bwd": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_f32,
                                   c_f32, c_vp, c_vp]),
     "b2_roi_align_fwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),
-    "b2_roi_align_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_vp]),
+    "b2_roi_align_bwd": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f32, c_int, c_vp]),
     "b2_roi_align_pyramid_fwd": (c_int, [_PP, _IP, _IP, c_vp, c_vp, c_int, c_int, c_int, c_f32, c_vp]),
-    "b2_roi_align_pyramid_bwd": (c_int, [c_vp, c_vp, _PP, _IP, _IP, c_int, c_int, c_int, c_f32, c_vp]),
+    "b2_roi_align_pyramid_bwd": (c_int, [c_vp, c_vp, _PP, _IP, _IP, c_int, c_int, c_int, c_f32, c_int, c_vp]),
 }
 
 _lib = None

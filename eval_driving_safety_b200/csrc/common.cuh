@@ -13,7 +13,7 @@ void set_error(const char* fmt, ...);
 
 // Kernel-variant switches (A/B measurements, tests of both variants): value from b2_set_flag() if set, else from the
 // environment variable B2_<NAME>, else `dflt`.
-enum Flag { kFlagConvDcPair = 0, kFlagConv2dHalo = 1, kFlagConvG2Pair = 2, kFlagDepthHeadX4 = 3, kNumFlags };
+enum Flag { kFlagConvDcPair = 0, kFlagConv2dHalo = 1, kFlagConvG2Pair = 2, kFlagDepthHeadX4 = 3, kFlagRoiBwdWarp = 4, kNumFlags };
 int flag_value(Flag f, const char* env_name, int dflt);
 
 inline int check_launch(const char* what) {

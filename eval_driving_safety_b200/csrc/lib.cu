@@ -21,7 +21,7 @@ int conv3d_tcgen05_launch(const float* in, const float* wp, float* out, int N, i
                           int Hi, int Wi, int Do, int Ho, int Wo, int stride, int mode, cudaStream_t st,
                           const EpiFusion& ef, int* stat_rows, bool query, int* addend_ok);
 
-static int g_flags[kNumFlags] = {-1, -1, -1, -1};
+static int g_flags[kNumFlags] = {-1, -1, -1, -1, -1};
 
 int flag_value(Flag f, const char* env_name, int dflt) {
     if (g_flags[f] >= 0) return g_flags[f];
@@ -41,6 +41,7 @@ extern "C" int b2_set_flag(const char* name, int value) {
     else if (!strcmp(name, "conv2d_halo")) idx = b2::kFlagConv2dHalo;
     else if (!strcmp(name, "conv_s2_pair")) idx = b2::kFlagConvG2Pair;
     else if (!strcmp(name, "depth_head_x4")) idx = b2::kFlagDepthHeadX4;
+    else if (!strcmp(name, "roi_bwd_warp")) idx = b2::kFlagRoiBwdWarp;
     B2_REQUIRE(idx >= 0, "set_flag: unknown flag '%s'", name);
     b2::g_flags[idx] = value < 0 ? -1 : value;
     return 0;

@@ -1194,6 +1194,14 @@ def depth_head(cost1, size, z0, dz):
 # ---------------------------------------------------------------------------
 # RoIAlign (Stereo R-CNN, config 5)
 # ---------------------------------------------------------------------------
+def _roi_gout(gout, c):
+    """(gradient of the pooled features as the backward kernel reads it, its layout code): [R,P,P,C] memory (one copy
+    unless the producer already wrote channels-last) for the FPN widths, the upstream [R,C,P,P] otherwise."""
+    if c % 32 == 0 and c <= 256:
+        return gout.contiguous(memory_format=CL2), 1
+    return gout.contiguous(), 0
+
+
 class RoIAlignFn(Function):
     @staticmethod
     def forward(ctx, feat, rois, pooled, scale):
@@ -1217,10 +1225,10 @@ class RoIAlignFn(Function):
         lib = _lib.load()
         (rois,) = ctx.saved_tensors
         r, c, h, w, pooled, scale = ctx.cfg
-        g = gout.contiguous()
+        g, layout = _roi_gout(gout, c)
         gfeat = torch.empty((1, c, h, w), device=g.device, dtype=torch.float32)
         with _op("roi_align_bwd", 1, 4 * (g.numel() + gfeat.numel())):
-            check(lib.b2_roi_align_bwd(_p(g), _p(rois), _p(gfeat), r, c, h, w, pooled, scale, _stream()),
+            check(lib.b2_roi_align_bwd(_p(g), _p(rois), _p(gfeat), r, c, h, w, pooled, scale, layout, _stream()),
                   "roi_align_bwd")
         return gfeat, None, None, None
 
@@ -1259,13 +1267,13 @@ class PyramidRoIAlignFn(Function):
         lib = _lib.load()
         (rois,) = ctx.saved_tensors
         r, c, pooled, im_h, shapes = ctx.cfg
-        g = gout.contiguous()
+        g, layout = _roi_gout(gout, c)
         gfeats = [torch.empty(s, device=g.device, dtype=torch.float32) for s in shapes]
         hs = (ctypes.c_int * 4)(*[s[2] for s in shapes])
         ws = (ctypes.c_int * 4)(*[s[3] for s in shapes])
         ptrs = ctypes.cast(_lib.ptr_array(gfeats), ctypes.POINTER(ctypes.c_void_p))
         with _op("roi_align_bwd", 1, 4 * (g.numel() + sum(t.numel() for t in gfeats))):
-            check(lib.b2_roi_align_pyramid_bwd(_p(g), _p(rois), ptrs, hs, ws, r, c, pooled, im_h, _stream()),
+            check(lib.b2_roi_align_pyramid_bwd(_p(g), _p(rois), ptrs, hs, ws, r, c, pooled, im_h, layout, _stream()),
                   "roi_align_pyramid_bwd")
         return (None, None, None) + tuple(gfeats)
 

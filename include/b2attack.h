@@ -40,7 +40,9 @@ const char* b2_last_error(void);
  *   "conv_dc_pair"  1 = CTA-pair (tcgen05 cta_group::2) transposed-conv kernel (default), 0 = single-CTA;
  *   "conv_s2_pair"  1 = CTA-pair variant of the one-tap-per-stage kernel that serves the stride-2 convs (default), 0 = single-CTA;
  *   "conv2d_halo"   1 = halo-reuse stride-1 3x3 2-D conv kernel (default), 0 = one tap per stage;
- *   "depth_head_x4" 1 = unrolled depth-head kernels when every upsampling ratio is 4 (default), 0 = the generic ones.
+ *   "depth_head_x4" 1 = unrolled depth-head kernels when every upsampling ratio is 4 (default), 0 = the generic ones;
+ *   "roi_bwd_warp"  1 = warp-per-pixel RoIAlign backward for C % 32 == 0, C <= 256 (default), 0 = thread per pixel and
+ *                   channel chunk.
  * value < 0 returns the flag to its default (environment variable B2_<NAME>, else the built-in default). */
 int b2_set_flag(const char* name, int value);
 
@@ -349,12 +351,14 @@ int b2_depth_head_bwd(const float* cost, const float* gdepth, float* gcost, cons
  * attack/Stereo-RCNN/stereo_rcnn.py:44-45 and dispatched per FPN level at
  * :110-141.  feat [1,C,H,W] (NCHW, as the upstream op), rois [R,5]
  * (batch,x1,y1,x2,y2), out [R,C,P,P]; legacy (unaligned) sampling, adaptive
- * sampling ratio (0).  Backward is gather-form over feature pixels.
+ * sampling ratio (0).  Backward is gather-form over feature pixels (fixed summation order, no atomics);
+ * gout_layout 0 = [R,C,P,P] as the upstream op hands it back, 1 = [R,P,P,C] (channels-last memory: the
+ * C values of one bin are contiguous, which is what the warp-per-pixel kernel reads fastest).
  * ------------------------------------------------------------------------- */
 int b2_roi_align_fwd(const float* feat, const float* rois, float* out, int R, int C, int H, int W,
                      int P, float scale, void* stream);
 int b2_roi_align_bwd(const float* gout, const float* rois, float* gfeat, int R, int C, int H, int W,
-                     int P, float scale, void* stream);
+                     int P, float scale, int gout_layout, void* stream);
 
 /* The whole FPN dispatch of _StereoRCNN.PyramidRoI_Feat (attack/Stereo-RCNN/stereo_rcnn.py:110-141) in ONE launch
  * per direction: every RoI's level = clamp(round(log(sqrt(h w) / 224) + 4), 2, 5) (natural log, :113-119) is
@@ -366,7 +370,7 @@ int b2_roi_align_bwd(const float* gout, const float* rois, float* gfeat, int R, 
 int b2_roi_align_pyramid_fwd(const float* const* feats, const int* Hs, const int* Ws, const float* rois, float* out,
                              int R, int C, int P, float im_h, void* stream);
 int b2_roi_align_pyramid_bwd(const float* gout, const float* rois, float* const* gfeats, const int* Hs, const int* Ws,
-                             int R, int C, int P, float im_h, void* stream);
+                             int R, int C, int P, float im_h, int gout_layout, void* stream);
 
 #ifdef __cplusplus
 }

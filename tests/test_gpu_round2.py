@@ -428,3 +428,43 @@ def test_spp_upsample_matmul_equals_interpolate(built_lib):
         (a,) = torch.autograd.grad(out, x, gy)
         (b,) = torch.autograd.grad(ref, x, gy)
         assert (a - b).abs().max().item() < 1e-4 * b.abs().max().item()
+
+
+@pytest.mark.parametrize("pooled,c", [(7, 64), (14, 32), (7, 256)])
+def test_roi_align_backward_warp_kernel_equals_the_chunked_one(built_lib, pooled, c):
+    """FPN widths take the warp-per-pixel backward reading the channels-last gradient [R,P,P,C]; it must give the bits of
+    the thread-per-pixel kernel on [R,C,P,P] (same entries, same order), single level and pyramid, and be deterministic."""
+    from eval_driving_safety_b200 import _lib, ops, stereo_rcnn as S
+    g = torch.Generator().manual_seed(40 + pooled + c)
+    im_h, im_w = 600, 1987
+    feats = [torch.randn(1, c, h, w, generator=g).cuda().requires_grad_(True) for (h, w) in ((150, 497), (75, 249), (38, 125), (19, 63))]
+    rois, _ = S.synthetic_rois(200, im_h, im_w, seed=7)
+    rois = rois.cuda()
+    res = {}
+    for flag in (0, 1):
+        _lib.set_flag("roi_bwd_warp", flag)
+        try:
+            out = S.pyramid_roi_feat(feats, rois, float(im_h), pooled)
+            gy = torch.randn(out.shape, generator=torch.Generator().manual_seed(1)).cuda()
+            gp = torch.autograd.grad(out, feats, gy)
+            single = ops.roi_align(feats[2], rois, pooled, 38 / im_h)
+            (gs,) = torch.autograd.grad(single, feats[2], gy)
+        finally:
+            _lib.set_flag("roi_bwd_warp", None)
+        res[flag] = (gp, gs)
+    for a, b in zip(res[0][0], res[1][0]):
+        assert torch.equal(a, b)
+    assert torch.equal(res[0][1], res[1][1])
+    # 600 RoIs: more than one shared-memory RoI tile
+    many, _ = S.synthetic_rois(600, im_h, im_w, seed=9)
+    many = many.cuda()
+    outs = []
+    for flag in (0, 1, 1):
+        _lib.set_flag("roi_bwd_warp", flag)
+        try:
+            o = ops.roi_align(feats[1], many, pooled, 75 / im_h)
+            gy = torch.randn(o.shape, generator=torch.Generator().manual_seed(2)).cuda()
+            outs.append(torch.autograd.grad(o, feats[1], gy)[0])
+        finally:
+            _lib.set_flag("roi_bwd_warp", None)
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])
