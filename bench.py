@@ -292,7 +292,7 @@ def run_b200(args):
                    "execution": "eager" if args.eager else
                    "CUDA graph of %d concurrent pair-iteration(s) on parallel streams, replayed" % lanes,
                    "parity_of_this_mode": "tests/test_gpu_fullsize.py on this exact engine: per-iteration gradient-sign agreement mean "
-                                          "99.944 % / min 99.901 %, updated pixels identical to the CPU oracle mean 98.34 % / min 98.17 % "
+                                          "99.942 % / min 99.893 %, updated pixels identical to the CPU oracle mean 98.33 % / min 98.14 % "
                                           "(10 iterations x 2 full-size pairs); cost volume bit-exact",
                    "l2_policy": "per-iteration working set (~10 GB of activations per pair) is far larger than the 126 MB L2"},
         "e2e": {"value": units / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

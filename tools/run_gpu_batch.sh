@@ -1,7 +1,5 @@
 #!/bin/bash
 tag=${1:-b}
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -k "roi or srcnn or stereo_rcnn or pyramid" > gpurun_out/${tag}_pytest.log 2>&1
-echo "gpu tests rc=$?"; tail -4 gpurun_out/${tag}_pytest.log
-timeout 600 python bench.py --config srcnn --steps 10 --warmup 3 > gpurun_out/${tag}_srcnn.json 2> gpurun_out/${tag}_srcnn.err
-python -c "import json;d=json.load(open('gpurun_out/${tag}_srcnn.json'));print('srcnn', round(d['value'],2), 'e2e', round(d['e2e']['value'],2), round(d['ms_per_step'],2), d['clocks'])"
+timeout 1500 python -m pytest tests/test_gpu_fullsize.py -m gpu -q -s > gpurun_out/${tag}_fullsize.log 2>&1
+echo "rc=$?"; grep -n "CONFIG\|free-running pair\|passed\|failed" gpurun_out/${tag}_fullsize.log | cut -c1-400
