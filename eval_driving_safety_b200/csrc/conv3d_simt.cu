@@ -160,7 +160,7 @@ conv3d_c1_partial_kernel(const float4* __restrict__ in, const float4* __restrict
     }
 }
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 conv3d_c1_gather_kernel(const float* __restrict__ P, float* __restrict__ out, int N, int D, int H, int W) {
     const int64_t nvox = (int64_t)N * D * H * W;
     for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox; v += (int64_t)gridDim.x * blockDim.x) {

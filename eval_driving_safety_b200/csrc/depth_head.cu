@@ -153,7 +153,7 @@ depth_head_gather_kernel(const float* __restrict__ G, float* __restrict__ gcost,
 // Same operation order per plane as the generic kernel (ATen's l0*c0 + l1*c1, ascending planes).
 // ---------------------------------------------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 depth_head_pixel_x4_kernel(const float* __restrict__ cost, const float* __restrict__ gdepth,
                            float* __restrict__ depth, float* __restrict__ G, DhGeom g,
                            float2* __restrict__ sm_out, const float2* __restrict__ sm_in,

@@ -128,7 +128,10 @@ grid_sample2d_fwd_kernel(const float4* __restrict__ in, const float* __restrict_
 // 4-float4 variant, 64 B per voxel per instruction, doubled the L1 tag work per byte and needed 128 registers:
 // ncu l1tex 66 %, 21 % occupancy, 0.239 ms).
 // =============================================================================================
-__global__ void __launch_bounds__(256, 3)
+// Occupancy is what this latency-bound gather wants: measured 0.198 ms with 3 resident blocks per SM (80 registers, all
+// loads of a batch in flight), 0.165 with 4 (63), 0.161 with 5 (48), **0.154 with 6** (40 registers, 8 bytes spilled),
+// 0.157 / 0.158 with 7 / 8; streaming stores or issuing the image-feature loads first change nothing.
+__global__ void __launch_bounds__(256, 6)
 lift_fwd_kernel(const float4* __restrict__ psv, const float4* __restrict__ img, const float* __restrict__ grid,
                 float* __restrict__ out, int N, int D, int H, int W, int Hi, int Wi, int64_t nvox_per_n, int align) {
     constexpr int LPV = 8, R3 = 16, R2 = 8, CO = 96;        // lanes per voxel, float4 per PSV row / image row
@@ -139,6 +142,25 @@ lift_fwd_kernel(const float4* __restrict__ psv, const float4* __restrict__ img, 
     const float* g = grid + v * 3;
     float gg[3] = {__ldg(g), __ldg(g + 1), __ldg(g + 2)};
     const Corners3 c = corners3(gg, D, H, W, align);
+    float4* orow = reinterpret_cast<float4*>(out + v * CO) + lane;
+    // the image feature at the same (u, v); its size may differ from the PSV's, so its corners are recomputed
+    float4 v2[4];
+    float w2[4];
+    auto img_loads = [&]() {
+        float g2[3] = {gg[0], gg[1], -1.f};
+        const Corners3 c2 = corners3(g2, 1, Hi, Wi, align);
+        const float4* base2 = img + (int64_t)n * Hi * Wi * R2 + lane;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int dy = k >> 1, dx = k & 1;
+            int yy = c2.y0 + dy, xx = c2.x0 + dx;
+            const bool ok = yy >= 0 && yy < Hi && xx >= 0 && xx < Wi;
+            const float w = (dx ? c2.wx1 : 1.f - c2.wx1) * (dy ? c2.wy1 : 1.f - c2.wy1);
+            w2[k] = ok ? w : 0.f;
+            yy = min(max(yy, 0), Hi - 1); xx = min(max(xx, 0), Wi - 1);
+            v2[k] = __ldg(base2 + (uint32_t)((yy * Wi + xx) * R2));
+        }
+    };
     float4 acc[2] = {make_float4(0.f, 0.f, 0.f, 0.f), make_float4(0.f, 0.f, 0.f, 0.f)};
     const bool any_in = c.z0 >= -1 && c.z0 < D && c.y0 >= -1 && c.y0 < H && c.x0 >= -1 && c.x0 < W;
     if (any_in) {
@@ -164,31 +186,13 @@ lift_fwd_kernel(const float4* __restrict__ psv, const float4* __restrict__ img, 
             for (int kk = 0; kk < 4; ++kk) { fma4(acc[0], wgt[kk], val[kk][0]); fma4(acc[1], wgt[kk], val[kk][1]); }
         }
     }
-    float4* orow = reinterpret_cast<float4*>(out + v * CO) + lane;
     orow[0] = acc[0];
     orow[LPV] = acc[1];
-    {
-        // the image feature at the same (u, v); its size may differ from the PSV's, so its corners are recomputed
-        float g2[3] = {gg[0], gg[1], -1.f};
-        const Corners3 c2 = corners3(g2, 1, Hi, Wi, align);
-        const float4* base2 = img + (int64_t)n * Hi * Wi * R2 + lane;
-        float4 a2 = make_float4(0.f, 0.f, 0.f, 0.f);
-        float4 v2[4];
-        float w2[4];
+    img_loads();
+    float4 a2 = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int dy = k >> 1, dx = k & 1;
-            int yy = c2.y0 + dy, xx = c2.x0 + dx;
-            const bool ok = yy >= 0 && yy < Hi && xx >= 0 && xx < Wi;
-            const float w = (dx ? c2.wx1 : 1.f - c2.wx1) * (dy ? c2.wy1 : 1.f - c2.wy1);
-            w2[k] = ok ? w : 0.f;
-            yy = min(max(yy, 0), Hi - 1); xx = min(max(xx, 0), Wi - 1);
-            v2[k] = __ldg(base2 + (uint32_t)((yy * Wi + xx) * R2));
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) fma4(a2, w2[k], v2[k]);
-        orow[R3] = a2;
-    }
+    for (int k = 0; k < 4; ++k) fma4(a2, w2[k], v2[k]);
+    orow[R3] = a2;
 }
 
 // ---------------------------------------------------------------------------
@@ -444,7 +448,7 @@ extern "C" int b2_lift_fwd(const float* psv, const float* img, const float* grid
     if (nvox == 0) return 0;
     const int64_t nblk = (nvox + 31) / 32;
     B2_REQUIRE(nblk < ((int64_t)1 << 31), "lift_fwd: too many voxels");
-    lift_fwd_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>((const float4*)psv, (const float4*)img, grid, out, N,
-                                                                       D, H, W, Hi, Wi, nvox_per_n, align_corners);
+    lift_fwd_kernel<<<(unsigned)nblk, 256, 0, (cudaStream_t)stream>>>(
+        (const float4*)psv, (const float4*)img, grid, out, N, D, H, W, Hi, Wi, nvox_per_n, align_corners);
     return check_launch("lift_fwd");
 }
