@@ -250,3 +250,78 @@ def test_decode_detections_inverts_the_target_assignment_and_writes_kitti_files(
     # nothing above the threshold -> empty file, as the reference writes for an image without detections
     none = dsgn.decode_detections(cfg, {"bbox_cls": torch.full_like(lab["cls"], -10.0), "bbox_reg": lab["reg"]}, P[0])
     assert none == [] and kitti_io.read_detections(kitti_io.write_detections(str(tmp_path), 8, none)) == []
+
+
+# ---------------------------------------------------------------- GnLink: the hand-off of backward sums is self-validating
+def _gnlink_graph(second_consumer, hold):
+    """y = norm(a); consumers of y: a 'conv' whose backward writes the gradient g2 (and offers sums computed from it
+    through the link) and, optionally, a plain second consumer.  Returns what the norm's backward saw."""
+    from eval_driving_safety_b200.ops import GnLink
+    seen = {}
+    link = GnLink() if hold else None
+
+    class Conv(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, y):
+            return y * 2.0
+
+        @staticmethod
+        def backward(ctx, g):
+            g2 = g * 2.0
+            seen["offered"] = (g2.data_ptr(), g2._version)
+            seen["offered_values"] = g2.clone()
+            if link is not None:
+                link.offer(torch.ones(1), g2)
+            return g2
+
+    class Norm(torch.autograd.Function):
+        @staticmethod
+        def forward(ctx, a):
+            return a + 1.0
+
+        @staticmethod
+        def backward(ctx, gy):
+            seen["arrived"] = (gy.data_ptr(), gy._version)
+            seen["arrived_values"] = gy.clone()
+            seen["taken"] = link.take(gy) if link is not None else None
+            return gy
+
+    a = torch.randn(64, 64, requires_grad=True)
+    y = Norm.apply(a)
+    w = torch.randn(64, 64)
+    if second_consumer == "before":
+        other = (y * w).sum()
+        loss = Conv.apply(y).sum() + other
+    elif second_consumer == "after":
+        loss = Conv.apply(y).sum() + (y * w).sum()
+    else:
+        loss = Conv.apply(y).sum()
+    torch.autograd.grad(loss, a)
+    return seen
+
+
+def test_gnlink_hands_the_sums_over_only_for_the_untouched_gradient():
+    """Single consumer: the norm's backward receives the very tensor the conv wrote -> the sums are taken.
+    Second consumer without the fork: the engine adds the two gradients; because the link holds the conv's tensor the
+    sum always arrives as ANOTHER tensor (never an in-place update of the offered one), and the sums are dropped."""
+    s = _gnlink_graph(None, hold=True)
+    assert s["arrived"] == s["offered"] and s["taken"] is not None
+    for order in ("before", "after"):
+        s = _gnlink_graph(order, hold=True)
+        assert not torch.equal(s["arrived_values"], s["offered_values"])          # the accumulated gradient ...
+        assert s["arrived"][0] != s["offered"][0] and s["taken"] is None          # ... is not the offered tensor
+
+
+def test_autograd_accumulates_in_place_into_an_unreferenced_gradient():
+    """The hazard the link guards against (documented behaviour of the engine's input buffer): without an extra
+    reference, a second consumer's gradient can be added IN PLACE into the conv's gradient tensor -- same address,
+    other values.  If this ever stops being true the guard is merely redundant, so only the safe direction is asserted:
+    whenever the addresses coincide, the values must have changed (i.e. address equality alone proves nothing)."""
+    hit = False
+    for order in ("before", "after"):
+        s = _gnlink_graph(order, hold=False)
+        if s["arrived"][0] == s["offered"][0]:
+            hit = True
+            assert not torch.equal(s["arrived_values"], s["offered_values"])
+    if not hit:
+        pytest.skip("this torch build accumulated out of place in both orders")
