@@ -403,7 +403,7 @@ class GnLink:
     into a new tensor after which the conv's tensor is freed and the caching allocator may hand its address to the
     NEXT sum.  Either way a tensor with the recorded address could arrive that the sums no longer describe (measured:
     2.8 % error in the extractor's input gradient).  While the link holds the conv's tensor neither can happen: the
-    engine must add out of place, and the address cannot be reused until ``take``.
+    engine must add out of place, and the address cannot be reused until ``take``."""
     __slots__ = ("x", "stats", "groups", "mode", "bwd_partial", "gy", "gy_key")
 
     def __init__(self):
