@@ -325,3 +325,36 @@ def test_autograd_accumulates_in_place_into_an_unreferenced_gradient():
             assert not torch.equal(s["arrived_values"], s["offered_values"])
     if not hit:
         pytest.skip("this torch build accumulated out of place in both orders")
+
+
+# ---------------------------------------------------------------- pure-torch glue that also runs on the CPU
+def test_spp_upsample_as_two_gemms_equals_bilinear_interpolate_on_cpu():
+    """dsgn.upsample_bilinear_matmul (the SPP branches' upsampling as two GEMMs on the channels-last memory) against
+    F.interpolate(bilinear, align_corners=False), forward and backward, incl. the 1x4 map of the largest pool."""
+    import torch.nn.functional as F
+    from eval_driving_safety_b200 import dsgn
+    g = torch.Generator().manual_seed(13)
+    for (h, w, size) in ((1, 4, (24, 78)), (3, 9, (24, 78)), (6, 19, (24, 78)), (2, 3, (7, 11))):
+        x = torch.randn(2, 8, h, w, generator=g).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        ref = F.interpolate(x, size, mode="bilinear", align_corners=False)
+        out = dsgn.upsample_bilinear_matmul(x, size)
+        assert out.shape == ref.shape and out.permute(0, 2, 3, 1).is_contiguous()
+        assert (out - ref).abs().max().item() < 1e-5
+        gy = torch.randn(ref.shape, generator=g)
+        (a,) = torch.autograd.grad(out, x, gy)
+        (b,) = torch.autograd.grad(ref, x, gy)
+        assert (a - b).abs().max().item() < 1e-4 * b.abs().max().item()
+
+
+def test_split_batch_backward_is_one_concatenation():
+    from eval_driving_safety_b200 import ops
+    g = torch.Generator().manual_seed(14)
+    x = torch.randn(3, 8, 5, 6, generator=g).contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    wa, wb = torch.randn(1, 8, 5, 6, generator=g), torch.randn(2, 8, 5, 6, generator=g)
+    a, b = ops.split_batch(x, 1)
+    assert torch.equal(a, x[:1]) and torch.equal(b, x[1:])
+    (got,) = torch.autograd.grad((a * wa).sum() + (b * wb).sum(), x)
+    (ref,) = torch.autograd.grad((x[:1] * wa).sum() + (x[1:] * wb).sum(), x)
+    assert torch.equal(got, ref)
+    (only_b,) = torch.autograd.grad((ops.split_batch(x, 1)[1] * wb).sum(), x)
+    assert torch.equal(only_b[1:], wb) and only_b[:1].abs().max().item() == 0
